@@ -1,0 +1,112 @@
+"""Build helpers: every native artefact is built IN-TREE so it travels to the GPU box.
+
+  libracon_b200.so  — the product: C-ABI (include/racon_b200.h) + sm_100a CUDA kernels + C++ host mirror
+  libracon_synth.so — synthetic window generator (bench/test input maker, no CUDA)
+  oracle/_build/libpoa_oracle.so, oracle/_ref/libracon_ref.so — test infrastructure (see oracle/Makefile)
+"""
+import os
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "racon_b200", "csrc")
+LIBDIR = os.path.join(ROOT, "racon_b200", "lib")
+ORACLE = os.path.join(ROOT, "oracle")
+
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
+
+
+def _run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def _csrc_files(exts):
+    out = []
+    for d, _, files in os.walk(CSRC):
+        for f in files:
+            if f.endswith(exts):
+                out.append(os.path.join(d, f))
+    return sorted(out)
+
+
+def build_synth(force=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libracon_synth.so")
+    src = os.path.join(CSRC, "synth.c")
+    if force or _newer(out, [src]):
+        _run(["gcc", "-O2", "-fPIC", "-shared", "-o", out, src])
+    return out
+
+
+def nvcc_path():
+    p = shutil.which("nvcc")
+    if p:
+        return p
+    p = "/usr/local/cuda/bin/nvcc"
+    if os.path.exists(p):
+        return p
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+
+
+def build_cuda(force=False, verbose=False):
+    """Compile the product library for sm_100a (cross-compiles without a GPU)."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libracon_b200.so")
+    cu = [os.path.join(CSRC, "rp_api.cu")]
+    deps = _csrc_files((".cu", ".cuh", ".h", ".hpp", ".cpp")) + [os.path.join(ROOT, "include", "racon_b200.h")]
+    if force or _newer(out, deps):
+        cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo"] + NVCC_ARCH + [
+            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+            "-o", out] + cu + [os.path.join(CSRC, "host_mirror.cpp")]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        log = _run(cmd)
+        if verbose:
+            print(log)
+    return out
+
+
+def build_sim(force=False):
+    """Host build of the device code (32 cooperative fibres per simulated warp) — tests only."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libracon_sim.so")
+    deps = _csrc_files((".cu", ".cuh", ".h", ".hpp", ".cpp"))
+    if force or _newer(out, deps):
+        _run(["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-DRP_HOST_SIM=1", "-x", "c++",
+              "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out,
+              os.path.join(CSRC, "sim_main.cu")])
+    return out
+
+
+def build_oracle(force=False):
+    out = os.path.join(ORACLE, "_build", "libpoa_oracle.so")
+    srcs = [os.path.join(ORACLE, f) for f in ("poa_oracle.cpp", "myers_oracle.cpp")]
+    if force or _newer(out, srcs):
+        _run(["make", "-C", ORACLE, "oracle"])
+    return out
+
+
+def build_ref(force=False):
+    """oracle/_ref: the unmodified reference compiled from /root/reference (only where it exists)."""
+    out = os.path.join(ORACLE, "_ref", "libracon_ref.so")
+    srcs = [os.path.join(ORACLE, f) for f in ("ref_harness.cpp", "ref_edlib_harness.cpp")]
+    if os.path.isdir("/root/reference/src") and (force or _newer(out, srcs)):
+        _run(["make", "-C", ORACLE, "ref"])
+    return out if os.path.exists(out) else None
+
+
+def build_all(force=False):
+    build_synth(force)
+    build_cuda(force)
+    build_oracle(force)
+    build_ref(force)

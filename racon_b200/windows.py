@@ -1,0 +1,132 @@
+"""Flat "window set" arrays — the one input format every consumer reads.
+
+A window set describes many racon windows (reference: racon::Window, /root/reference/src/window.hpp:31-74):
+sequence 0 of each window is the backbone, the rest are layers with inclusive backbone coordinates
+(begin, end) exactly as passed to Window::add_layer (/root/reference/src/window.cpp:42-63).
+"""
+import ctypes as C
+import dataclasses
+import os
+
+import numpy as np
+
+from . import build
+
+
+@dataclasses.dataclass
+class WindowSet:
+    bases: np.ndarray          # uint8, concatenated sequence bytes
+    quals: np.ndarray          # uint8 (same offsets) or None
+    seq_off: np.ndarray        # uint64, n_seq + 1
+    seq_has_qual: np.ndarray   # uint8, n_seq (or None)
+    seq_begin: np.ndarray      # uint32, n_seq
+    seq_end: np.ndarray        # uint32, n_seq
+    win_first: np.ndarray      # uint32, n_windows + 1
+    win_type: np.ndarray       # uint8, n_windows (0 = kNGS, 1 = kTGS)
+
+    @property
+    def n_windows(self):
+        return len(self.win_first) - 1
+
+    @property
+    def n_seqs(self):
+        return len(self.seq_off) - 1
+
+    def window(self, w):
+        """Returns [(bases_bytes, quals_bytes_or_None, begin, end), ...] for window w."""
+        out = []
+        for s in range(int(self.win_first[w]), int(self.win_first[w + 1])):
+            a, b = int(self.seq_off[s]), int(self.seq_off[s + 1])
+            q = None
+            if self.quals is not None and self.seq_has_qual is not None and self.seq_has_qual[s]:
+                q = self.quals[a:b].tobytes()
+            out.append((self.bases[a:b].tobytes(), q, int(self.seq_begin[s]), int(self.seq_end[s])))
+        return out
+
+    def subset(self, idx):
+        """New WindowSet holding windows `idx` (in that order)."""
+        wins = [self.window(int(w)) for w in idx]
+        types = [int(self.win_type[int(w)]) for w in idx]
+        return from_lists(wins, types)
+
+
+def from_lists(windows, types=None):
+    """windows: list of [(bases, quals|None, begin, end), ...]; backbone first."""
+    bases, quals, off, hasq, beg, end, first = [], [], [0], [], [], [], [0]
+    any_q = False
+    for win in windows:
+        for (b, q, s, e) in win:
+            b = b if isinstance(b, bytes) else b.encode()
+            bases.append(b)
+            if q is not None:
+                q = q if isinstance(q, bytes) else q.encode()
+                assert len(q) == len(b)
+                quals.append(q)
+                any_q = True
+            else:
+                quals.append(b"!" * len(b))
+            hasq.append(0 if q is None else 1)
+            off.append(off[-1] + len(b))
+            beg.append(s)
+            end.append(e)
+        first.append(len(off) - 1)
+    if types is None:
+        types = [1] * len(windows)
+    return WindowSet(
+        bases=np.frombuffer(b"".join(bases), dtype=np.uint8).copy(),
+        quals=np.frombuffer(b"".join(quals), dtype=np.uint8).copy() if any_q else None,
+        seq_off=np.asarray(off, dtype=np.uint64),
+        seq_has_qual=np.asarray(hasq, dtype=np.uint8) if any_q else None,
+        seq_begin=np.asarray(beg, dtype=np.uint32),
+        seq_end=np.asarray(end, dtype=np.uint32),
+        win_first=np.asarray(first, dtype=np.uint32),
+        win_type=np.asarray(types, dtype=np.uint8),
+    )
+
+
+_synth = None
+
+
+def _synth_lib():
+    global _synth
+    if _synth is None:
+        path = build.build_synth()
+        lib = C.CDLL(path)
+        lib.rp_synth_windows.restype = C.c_uint64
+        lib.rp_synth_windows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
+                                         C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
+        lib.rp_fnv1a64.restype = C.c_uint64
+        lib.rp_fnv1a64.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64]
+        _synth = lib
+    return _synth
+
+
+def synth_windows(n_windows, truth_len=500, depth=32, err=0.12, state=42):
+    """SURVEY.md §8(d) generator.  Returns (WindowSet, new_state)."""
+    lib = _synth_lib()
+    n_seq = n_windows * (depth + 1)
+    cap = int(n_seq * truth_len * (1.0 + err) + 4096 * (depth + 1))
+    bases = np.empty(cap, dtype=np.uint8)
+    seq_off = np.empty(n_seq + 1, dtype=np.uint64)
+    beg = np.empty(n_seq, dtype=np.uint32)
+    end = np.empty(n_seq, dtype=np.uint32)
+    first = np.empty(n_windows + 1, dtype=np.uint32)
+    st = C.c_uint64(state)
+    nb = lib.rp_synth_windows(C.byref(st), n_windows, truth_len, depth, float(err), bases.ctypes.data, cap,
+                              seq_off.ctypes.data, beg.ctypes.data, end.ctypes.data, first.ctypes.data)
+    if nb == 2 ** 64 - 1:
+        raise RuntimeError("synthetic generator: capacity too small")
+    ws = WindowSet(bases=bases[:nb].copy(), quals=None, seq_off=seq_off, seq_has_qual=None, seq_begin=beg,
+                   seq_end=end, win_first=first, win_type=np.ones(n_windows, dtype=np.uint8))
+    return ws, st.value
+
+
+def fnv1a64(chunks):
+    lib = _synth_lib()
+    h = 1469598103934665603
+    for c in chunks:
+        if len(c):
+            buf = np.frombuffer(c, dtype=np.uint8) if isinstance(c, (bytes, bytearray)) else np.ascontiguousarray(c)
+            h = lib.rp_fnv1a64(h, buf.ctypes.data, buf.size)
+    return h
