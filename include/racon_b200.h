@@ -1,0 +1,121 @@
+/*
+ * racon_b200.h — C ABI of the B200-native POA consensus / pre-alignment hot path.
+ *
+ * Drop-in boundary for racon's GPU batch objects.  Every entry point names the
+ * reference interface it replaces; INTEGRATION.md shows the shim a racon maintainer adds in
+ * src/cuda/cudabatch.cpp / src/cuda/cudaaligner.cpp.
+ *
+ * Conventions (same as the reference batch objects):
+ *   - sequence / quality pointers passed to add_* are BORROWED only for the duration of the call
+ *     (bytes are copied into the object's pinned staging, as cudapoa's add_poa_group does);
+ *   - buffers returned by fetch_* are owned by the object and stay valid until reset/destroy;
+ *   - one object is used by one host thread at a time; objects are independent (own stream, own device);
+ *   - soft per-item status (window did not fit a limit) vs hard errors (negative rp_status);
+ *   - no exceptions cross this ABI, no global state besides CUDA contexts;
+ *   - there is NO CPU fallback behind any of these calls: without a usable CUDA device rp_*_create fails.
+ */
+#ifndef RACON_B200_H_
+#define RACON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t rp_status;
+enum {
+    RP_OK = 0,
+    RP_BATCH_FULL = 1,      /* item not added: run the batch, reset, add it again (cudabatch.cpp:126-132) */
+    RP_ERR_INVALID = -1,    /* bad argument / malformed window (the reference exit(1)s: window.cpp:19-23,49-58) */
+    RP_ERR_CUDA = -2,       /* CUDA runtime failure; rp_last_error() has the text */
+    RP_ERR_NOMEM = -3,
+    RP_ERR_STATE = -4,      /* call order violated (e.g. fetch before run) */
+    RP_ERR_NO_DEVICE = -5   /* no CUDA device: the hot path has no CPU fallback */
+};
+
+/* per-window soft status reported by rp_poa_window_status (0 = consensus produced on the GPU) */
+enum {
+    RP_WIN_OK = 0,
+    RP_WIN_NODE_LIMIT = 1,
+    RP_WIN_EDGE_LIMIT = 2,
+    RP_WIN_ALIGNED_LIMIT = 3,
+    RP_WIN_NEEDS_INT32 = 4,
+    RP_WIN_SEQ_TOO_LONG = 5,
+    RP_WIN_STACK_LIMIT = 6,
+    RP_WIN_ALPHABET_LIMIT = 7,
+    RP_WIN_INTERNAL = 8
+};
+
+enum { RP_WINDOW_NGS = 0, RP_WINDOW_TGS = 1 }; /* racon::WindowType, src/window.hpp:20-23 */
+
+const char* rp_strerror(rp_status s);
+const char* rp_last_error(void);          /* thread-local text of the last hard error */
+int rp_device_count(void);                /* cudaGetDeviceCount; <= 0 when no device (cudapolisher.cpp:48) */
+const char* rp_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * POA consensus batch — replaces racon::CUDABatchProcessor (src/cuda/cudabatch.hpp:27-122) and the
+ * cudapoa::Batch it wraps (vendor/GenomeWorks/cudapoa/include/.../batch.hpp:45-56,108-159);
+ * per window it computes what Window::generate_consensus (src/window.cpp:65-149) computes.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rp_poa rp_poa;
+
+/* createCUDABatch(max_window_depth, device, avail_mem, gap, mismatch, match, banded), cudabatch.cpp:23-72.
+ * mem_bytes: device-memory budget for this object (0 = 80 % of what is free).
+ * window_len_hint: racon -w (sizes per-window scratch; 0 = 500).  max_depth_hint: 0 = unlimited
+ * (unlike cudapoa's MAX_DEPTH 200, cudapolisher.cpp:226, no layers are dropped). */
+rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match, int8_t mismatch, int8_t gap,
+                        int banded, uint32_t window_len_hint, uint32_t max_depth_hint);
+void rp_poa_destroy(rp_poa* p);
+
+/* CUDABatchProcessor::addWindow (cudabatch.cpp:77-175) = Window ctor + add_layer (window.cpp:30-63).
+ * seq[0]/qual[0] = backbone (qual[0] may be NULL => dummy '!' quality, polisher.cpp:174,396-399);
+ * seq[k>0] = layers with inclusive backbone coordinates begin[k]..end[k] (begin[0], end[0] ignored);
+ * qual[k] NULL => weight 1.  Layers with len == 0 or begin == end are skipped like add_layer does.
+ * Returns RP_OK, RP_BATCH_FULL, or RP_ERR_INVALID. */
+rp_status rp_poa_add_window(rp_poa* p, uint32_t n_seq, const char* const* seq, const uint32_t* len,
+                            const char* const* qual, const uint32_t* begin, const uint32_t* end, int window_type,
+                            int trim);
+
+/* Bulk form of rp_poa_add_window over flat arrays (see racon_b200/windows.py): adds windows
+ * [first, first + count) of the set until the batch is full; *added = how many were taken. */
+rp_status rp_poa_add_window_set(rp_poa* p, uint32_t first, uint32_t count, const char* bases, const char* quals,
+                                const uint64_t* seq_off, const uint8_t* seq_has_qual, const uint32_t* seq_begin,
+                                const uint32_t* seq_end, const uint32_t* win_first, const uint8_t* win_type, int trim,
+                                uint32_t* added);
+
+uint32_t rp_poa_size(const rp_poa* p);    /* windows in the batch (CUDABatchProcessor::hasWindows) */
+
+/* CUDABatchProcessor::generateConsensus = generate_poa + get_consensus (cudabatch.cpp:193-270):
+ * rp_poa_run = upload + launch + download, asynchronous on the object's stream; rp_poa_sync waits. */
+rp_status rp_poa_run(rp_poa* p);
+rp_status rp_poa_sync(rp_poa* p);
+/* the three stages separately (bench.py times rp_poa_launch alone with inputs resident in HBM) */
+rp_status rp_poa_upload(rp_poa* p);
+rp_status rp_poa_launch(rp_poa* p);
+rp_status rp_poa_download(rp_poa* p);
+
+/* Window::consensus() + the bool generate_consensus returns (window.cpp:65-149); coverage = per-base
+ * coverage of the returned consensus (Graph::GenerateConsensus summary, graph.cpp:377-398). */
+rp_status rp_poa_fetch(rp_poa* p, uint32_t i, const char** consensus, uint32_t* len, const uint16_t** coverage,
+                       int* polished);
+rp_status rp_poa_window_status(rp_poa* p, uint32_t i, uint32_t* status);
+/* bulk fetch: out is n x stride bytes; any output pointer may be NULL */
+rp_status rp_poa_fetch_all(rp_poa* p, char* out, uint32_t stride, uint32_t* lens, uint8_t* polished,
+                           uint32_t* status);
+
+rp_status rp_poa_reset(rp_poa* p);        /* CUDABatchProcessor::reset (cudabatch.cpp:272-278) */
+
+/* stream / measurement hooks */
+rp_status rp_poa_set_stream(rp_poa* p, void* cuda_stream);   /* use the caller's cudaStream_t */
+/* info[0] kernel launches so far, [1] last H2D bytes, [2] last D2H bytes, [3] worker warps,
+ * [4] scratch bytes per warp, [5] device alignments done (if counters enabled), [6] DP cells, [7] sink ties */
+rp_status rp_poa_info(rp_poa* p, uint64_t info[8]);
+rp_status rp_poa_enable_counters(rp_poa* p, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RACON_B200_H_ */

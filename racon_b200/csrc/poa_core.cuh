@@ -1,0 +1,1095 @@
+/*
+ * poa_core.cuh — B200-native per-window partial-order-alignment consensus (device code).
+ *
+ * What the reference does per window (Window::generate_consensus, /root/reference/src/window.cpp:65-149,
+ * driving spoa: vendor/spoa/src/graph.cpp and sisd/simd alignment engines) is done here by ONE WARP per
+ * window, many windows in flight per SM, in one persistent kernel launch:
+ *
+ *   for every layer:   [subgraph marking]  ->  DP "program" build  ->  NW-linear graph x read DP
+ *                      ->  traceback  ->  graph merge  ->  incremental topological order update
+ *   then:              spoa-order DFS sort -> heaviest-bundle consensus -> coverage -> TGS trim
+ *
+ * Design (not a port):
+ *   * The POA graph lives in HBM as flat per-node slot arrays (in-edge slots with weights, aligned-node
+ *     slots, per-node sequence counters instead of per-edge label lists).  Every graph phase is a
+ *     lane-strided data-parallel loop, so HBM latency is overlapped 32-wide.
+ *   * The DP keeps a whole 512-column row chunk in registers: lane l owns 16 consecutive columns as
+ *     8 packed int16x2 registers; predecessor rows come from a shared-memory ring of the most recent
+ *     rows (conflict-free swizzled 128-bit loads) or, for far predecessors, from the HBM copy; the cell
+ *     update is two DPX VIADDMNMX.S16x2 per predecessor per register; the in-row gap recurrence is a
+ *     lane-local max-plus chain plus a 5-step warp shuffle scan.
+ *   * Rows are processed in an incrementally maintained topological order (aligned clusters kept
+ *     contiguous).  Cell values and the traceback do not depend on which valid topological order is
+ *     used; spoa's own DFS order (graph.cpp:249-303) is only needed to break ties between equally
+ *     scoring sink rows and for the final consensus, and is computed on demand.
+ *   * H rows are streamed once to HBM (coalesced 1 KB row stores) for the traceback.
+ *
+ * Exact semantics reproduced: A.1 DP / sink choice / traceback priority,
+ * A.2 graph merge, A.3 topological order (on demand), A.4 heaviest bundle + branch completion,
+ * A.5 coverage + trim, A.6 subgraph.
+ */
+#pragma once
+#include "rp_warp.cuh"
+
+namespace rp {
+
+constexpr uint16_t kNone = 0xffffu;
+constexpr int kChunkCols = 512;          // columns per register-resident row chunk (32 lanes x 16)
+constexpr int32_t kNeg16 = -31744;       // INT16_MIN + 1024, the reference's kNegativeInfinity (simd impl :541)
+constexpr int32_t kNeg32 = -(1 << 28);
+
+/* window status codes (soft, per window; mirrored in include/racon_b200.h) */
+enum : uint32_t {
+    kWinOk = 0,
+    kWinNodeLimit = 1,
+    kWinEdgeLimit = 2,
+    kWinAlignedLimit = 3,
+    kWinNeedsInt32 = 4,
+    kWinSeqTooLong = 5,
+    kWinStackLimit = 6,
+    kWinAlphabetLimit = 7,
+    kWinInternal = 8,
+};
+
+struct PoaLimits {
+    uint32_t nmax;   // max graph nodes per window
+    uint32_t lmax;   // max layer length
+    uint32_t lp;     // padded row length in int16 cells: multiple of kChunkCols, >= lmax + 1
+    uint32_t ki;     // in-edge slots per node
+    uint32_t ka;     // aligned-node slots per node
+    uint32_t stack_cap;
+};
+
+struct SlotLayout {
+    uint64_t code, flags, in_cnt, al_cnt, cov, in_tail, in_w, al, order_a, order_b, rank_of, dp_order, dp_rank,
+        rec, pred_ovf, H, aln, cur, wts_unused, member, has_out_sub, score, cpred, sorder, srank, marks, stack,
+        newlist, bytes;
+};
+
+RP_HD uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+RP_HD SlotLayout make_layout(const PoaLimits& L) {
+    SlotLayout s;
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) {
+        uint64_t r = o;
+        o = align_up(o + bytes, 256);
+        return r;
+    };
+    uint64_t n = L.nmax;
+    s.code = take(n);
+    s.flags = take(n);
+    s.in_cnt = take(n);
+    s.al_cnt = take(n);
+    s.cov = take(n * 2);
+    s.in_tail = take(n * L.ki * 2);
+    s.in_w = take(n * L.ki * 4);
+    s.al = take(n * L.ka * 2);
+    s.order_a = take((n + 2 + 64) * 2);
+    s.order_b = take((n + 2 + 64) * 2);
+    s.rank_of = take(n * 2);
+    s.dp_order = take((n + 2 + 64) * 2);
+    s.dp_rank = take(n * 2);
+    s.rec = take((n + 1 + 64) * 8);
+    s.pred_ovf = take((n + 1) * L.ki * 2);
+    s.H = take((n + 1) * static_cast<uint64_t>(L.lp) * 2);
+    s.aln = take((static_cast<uint64_t>(L.lmax) + 1) * 2);
+    s.cur = take((static_cast<uint64_t>(L.lmax) + 1) * 2);
+    s.wts_unused = o;
+    s.member = take(n);
+    s.has_out_sub = take(n);
+    s.score = take(n * 8);
+    s.cpred = take(n * 2);
+    s.sorder = take(n * 2);
+    s.srank = take(n * 2);
+    s.marks = take(n);
+    s.stack = take(static_cast<uint64_t>(L.stack_cap) * 2);
+    s.newlist = take((static_cast<uint64_t>(L.lmax) + 1) * 4);
+    s.bytes = align_up(o, 4096);
+    return s;
+}
+
+/* Launch-wide parameters (plain pointers into HBM). */
+struct PoaParams {
+    int32_t match, mismatch, gap;
+    uint32_t n_windows;
+    /* inputs, packed by the host in processing order (backbone first, layers sorted as window.cpp:85-86) */
+    const uint8_t* bases;
+    const uint8_t* weights;       // per base: quality - 33, or 1 (layers without quality), 0 (dummy backbone)
+    const uint32_t* seq_off;      // n_seq + 1
+    const uint32_t* seq_begin;
+    const uint32_t* seq_end;
+    const uint8_t* seq_flags;     // bit0: full-span layer (window.cpp:92-93 test evaluated on the host)
+    const uint32_t* win_first;    // n_windows + 1
+    const uint8_t* win_flags;     // bit0: trim (type == kTGS && trim)
+    const uint64_t* win_alpha;    // up to 8 distinct characters of the window, low byte first
+    const uint32_t* queue;        // processing order of windows (longest first)
+    uint32_t* queue_head;         // atomic cursor
+    /* outputs */
+    uint8_t* cons;                // window w at cons + out_off[w], capacity out_cap[w]
+    uint16_t* cons_cov;           // same offsets (per-base coverage of the returned consensus)
+    const uint32_t* out_off;
+    const uint32_t* out_cap;
+    uint32_t* cons_len;
+    uint32_t* status;
+    uint64_t* stats;              // optional device counters (may be null): [0] alignments, [1] dp cells, ...
+    /* scratch */
+    uint8_t* scratch;
+    PoaLimits lim;
+    SlotLayout lay;
+    uint32_t smem_per_warp;       // bytes of shared memory owned by each warp
+};
+
+RP_DEV uint32_t swz(uint32_t e) {  // element index -> swizzled element index (16 B granules, LDS.128 conflict-free)
+    uint32_t q = e >> 3;
+    return ((q ^ ((q >> 3) & 1u)) << 3) | (e & 7u);
+}
+
+struct Row8 {
+    uint32_t r[8];
+};
+
+struct alignas(16) U4 {
+    uint32_t x, y, z, w;
+};
+
+RP_DEV Row8 load_row_smem(const int16_t* row, uint32_t chunk, int lane) {
+    uint32_t q0 = chunk * 64u + 2u * static_cast<uint32_t>(lane);
+    uint32_t p0 = q0 ^ ((q0 >> 3) & 1u);
+    uint32_t p1 = (q0 + 1u) ^ (((q0 + 1u) >> 3) & 1u);
+    const U4* b = reinterpret_cast<const U4*>(row);
+    U4 a = b[p0], c = b[p1];
+    Row8 o;
+    o.r[0] = a.x; o.r[1] = a.y; o.r[2] = a.z; o.r[3] = a.w;
+    o.r[4] = c.x; o.r[5] = c.y; o.r[6] = c.z; o.r[7] = c.w;
+    return o;
+}
+RP_DEV void store_row_smem(int16_t* row, uint32_t chunk, int lane, const Row8& v) {
+    uint32_t q0 = chunk * 64u + 2u * static_cast<uint32_t>(lane);
+    uint32_t p0 = q0 ^ ((q0 >> 3) & 1u);
+    uint32_t p1 = (q0 + 1u) ^ (((q0 + 1u) >> 3) & 1u);
+    U4* b = reinterpret_cast<U4*>(row);
+    b[p0] = U4{v.r[0], v.r[1], v.r[2], v.r[3]};
+    b[p1] = U4{v.r[4], v.r[5], v.r[6], v.r[7]};
+}
+RP_DEV Row8 load_row_gmem(const int16_t* row, uint32_t chunk, int lane) {
+    const U4* b = reinterpret_cast<const U4*>(row) + chunk * 64u + 2u * static_cast<uint32_t>(lane);
+    U4 a = b[0], c = b[1];
+    Row8 o;
+    o.r[0] = a.x; o.r[1] = a.y; o.r[2] = a.z; o.r[3] = a.w;
+    o.r[4] = c.x; o.r[5] = c.y; o.r[6] = c.z; o.r[7] = c.w;
+    return o;
+}
+RP_DEV void store_row_gmem(int16_t* row, uint32_t chunk, int lane, const Row8& v) {
+    U4* b = reinterpret_cast<U4*>(row) + chunk * 64u + 2u * static_cast<uint32_t>(lane);
+    b[0] = U4{v.r[0], v.r[1], v.r[2], v.r[3]};
+    b[1] = U4{v.r[4], v.r[5], v.r[6], v.r[7]};
+}
+
+/* One warp's view of its scratch slot + shared memory. All scalar members are warp-uniform. */
+struct PoaWarp {
+    const PoaParams* P;
+    int lane;
+    /* graph (HBM) */
+    uint8_t *code, *flags, *in_cnt, *al_cnt, *member, *has_out_sub, *marks;
+    uint16_t *cov, *in_tail, *al, *order, *order_nxt, *rank_of, *dp_order, *dp_rank, *pred_ovf, *aln, *cur, *cpred,
+        *sorder, *srank, *stack;
+    int32_t* in_w;
+    uint64_t* rec;
+    int16_t* H;
+    int64_t* score;
+    uint32_t* newlist;
+    /* shared memory */
+    int16_t* ring;       // ring_rows x lp_a
+    int16_t* prof;       // ncodes x lp_a
+    uint8_t* smem;
+    uint32_t smem_bytes;
+    /* state */
+    uint32_t N;          // nodes
+    uint32_t ki, ka, nmax;
+    uint32_t status;
+    uint64_t alpha;
+    uint32_t ncodes;
+    uint32_t n_added;    // sequences merged so far (incl. backbone)
+
+    RP_DEV void bind(const PoaParams* p, uint8_t* slot, uint8_t* sm, uint32_t sm_bytes) {
+        P = p;
+        lane = lane_id();
+        const SlotLayout& y = p->lay;
+        code = slot + y.code;
+        flags = slot + y.flags;
+        in_cnt = slot + y.in_cnt;
+        al_cnt = slot + y.al_cnt;
+        cov = reinterpret_cast<uint16_t*>(slot + y.cov);
+        in_tail = reinterpret_cast<uint16_t*>(slot + y.in_tail);
+        in_w = reinterpret_cast<int32_t*>(slot + y.in_w);
+        al = reinterpret_cast<uint16_t*>(slot + y.al);
+        order = reinterpret_cast<uint16_t*>(slot + y.order_a);
+        order_nxt = reinterpret_cast<uint16_t*>(slot + y.order_b);
+        rank_of = reinterpret_cast<uint16_t*>(slot + y.rank_of);
+        dp_order = reinterpret_cast<uint16_t*>(slot + y.dp_order);
+        dp_rank = reinterpret_cast<uint16_t*>(slot + y.dp_rank);
+        rec = reinterpret_cast<uint64_t*>(slot + y.rec);
+        pred_ovf = reinterpret_cast<uint16_t*>(slot + y.pred_ovf);
+        H = reinterpret_cast<int16_t*>(slot + y.H);
+        aln = reinterpret_cast<uint16_t*>(slot + y.aln);
+        cur = reinterpret_cast<uint16_t*>(slot + y.cur);
+        member = slot + y.member;
+        has_out_sub = slot + y.has_out_sub;
+        score = reinterpret_cast<int64_t*>(slot + y.score);
+        cpred = reinterpret_cast<uint16_t*>(slot + y.cpred);
+        sorder = reinterpret_cast<uint16_t*>(slot + y.sorder);
+        srank = reinterpret_cast<uint16_t*>(slot + y.srank);
+        marks = slot + y.marks;
+        stack = reinterpret_cast<uint16_t*>(slot + y.stack);
+        newlist = reinterpret_cast<uint32_t*>(slot + y.newlist);
+        smem = sm;
+        smem_bytes = sm_bytes;
+        ki = p->lim.ki;
+        ka = p->lim.ka;
+        nmax = p->lim.nmax;
+    }
+
+    RP_DEV void fail(uint32_t st) {
+        if (status == kWinOk) status = st;
+    }
+
+    RP_DEV uint32_t code_index(uint8_t c) const {  // position of character c in the window alphabet
+        uint32_t k = 0;
+        for (; k < ncodes; ++k)
+            if (static_cast<uint8_t>(alpha >> (8 * k)) == c) break;
+        return k;
+    }
+
+    /* ---------------------------------------------------------------- backbone (graph.cpp:186-190, 93-110) */
+    RP_DEV void init_backbone(const uint8_t* seq, const uint8_t* w, uint32_t len) {
+        for (uint32_t v = lane; v < len; v += 32) {
+            code[v] = seq[v];
+            al_cnt[v] = 0;
+            flags[v] = (v + 1 < len) ? 1 : 0;
+            cov[v] = len >= 2 ? 1 : 0;
+            if (v > 0) {
+                in_cnt[v] = 1;
+                in_tail[v * ki] = static_cast<uint16_t>(v - 1);
+                in_w[v * ki] = static_cast<int32_t>(w[v - 1]) + static_cast<int32_t>(w[v]);
+            } else {
+                in_cnt[v] = 0;
+            }
+            order[v + 1] = static_cast<uint16_t>(v);
+            rank_of[v] = static_cast<uint16_t>(v + 1);
+        }
+        if (lane == 0) order[0] = kNone;
+        N = len;
+        n_added = 1;
+        syncwarp();
+    }
+
+    /* ---------------------------------------------------------------- subgraph (graph.cpp:518-539) */
+    /* Backward DFS from backbone node `end` over in-edges and aligned nodes, keeping ids >= begin.
+     * Serial (lane 0); only partial-span layers take this path. */
+    RP_DEV void mark_subgraph(uint32_t begin, uint32_t end) {
+        for (uint32_t v = lane; v < N; v += 32) member[v] = 0;
+        syncwarp();
+        if (lane == 0) {
+            uint32_t sp = 0;
+            const uint32_t cap = P->lim.stack_cap;
+            stack[sp++] = static_cast<uint16_t>(end);
+            while (sp > 0) {
+                uint32_t c = stack[--sp];
+                if (member[c] || c < begin) continue;
+                uint32_t ni = in_cnt[c], na = al_cnt[c];
+                if (sp + ni + na > cap) {
+                    fail(kWinStackLimit);
+                    break;
+                }
+                for (uint32_t k = 0; k < ni; ++k) stack[sp++] = in_tail[c * ki + k];
+                for (uint32_t k = 0; k < na; ++k) stack[sp++] = al[c * ka + k];
+                member[c] = 1;
+            }
+        }
+        status = shfl(status, 0);
+        syncwarp();
+    }
+
+    /* Compact DP order over the member nodes (rank order preserved). Returns number of DP rows. */
+    RP_DEV uint32_t build_dp_order_subgraph() {
+        uint32_t base = 0;
+        for (uint32_t r0 = 1; r0 <= N; r0 += 32) {
+            uint32_t r = r0 + lane;
+            uint32_t v = r <= N ? order[r] : 0;
+            bool in = r <= N && member[v];
+            uint32_t tot;
+            uint32_t pos = warp_rank(in, &tot);
+            if (in) {
+                dp_order[base + pos + 1] = static_cast<uint16_t>(v);
+                dp_rank[v] = static_cast<uint16_t>(base + pos + 1);
+            }
+            base += tot;
+        }
+        for (uint32_t v = lane; v < N; v += 32) has_out_sub[v] = 0;
+        syncwarp();
+        /* sinks of the subgraph: members without an out-edge to another member (graph.cpp:575-580) */
+        for (uint32_t v = lane; v < N; v += 32) {
+            if (!member[v]) continue;
+            uint32_t ni = in_cnt[v];
+            for (uint32_t k = 0; k < ni; ++k) {
+                uint32_t t = in_tail[v * ki + k];
+                if (member[t]) has_out_sub[t] = 1;
+            }
+        }
+        syncwarp();
+        return base;
+    }
+
+    /* ---------------------------------------------------------------- DP program (one 8-byte record per row)
+     * byte0 code index, byte1 = npred(7 bits) | sink<<7, bytes2..7 = first three predecessor DP ranks
+     * (0 = virtual root row).  Further predecessors spill to pred_ovf. */
+    RP_DEV void build_program(uint32_t nrows, bool sub) {
+        const uint16_t* ord = sub ? dp_order : order;
+        const uint16_t* rk = sub ? dp_rank : rank_of;
+        for (uint32_t r = 1 + lane; r <= nrows; r += 32) {
+            uint32_t v = ord[r];
+            uint32_t ni = in_cnt[v];
+            uint32_t np = 0;
+            uint64_t preds = 0;
+            for (uint32_t k = 0; k < ni; ++k) {
+                uint32_t t = in_tail[v * ki + k];
+                if (sub && !member[t]) continue;
+                uint32_t pr = rk[t];
+                if (np < 3)
+                    preds |= static_cast<uint64_t>(pr) << (16 * np);
+                else
+                    pred_ovf[r * ki + np] = static_cast<uint16_t>(pr);
+                ++np;
+            }
+            bool sink = sub ? !has_out_sub[v] : !(flags[v] & 1);
+            uint64_t rc = static_cast<uint64_t>(code_index(code[v])) | (static_cast<uint64_t>(np & 0x7f) << 8) |
+                          (static_cast<uint64_t>(sink ? 1 : 0) << 15) | (preds << 16);
+            rec[r] = rc;
+        }
+        if (lane == 0) rec[0] = 0;
+        syncwarp();
+    }
+
+    /* ---------------------------------------------------------------- profile (sisd :123-131) */
+    RP_DEV void build_profile(const uint8_t* seq, uint32_t len, uint32_t lpa) {
+        int32_t m = P->match, x = P->mismatch;
+        for (uint32_t k = 0; k < ncodes; ++k) {
+            uint8_t c = static_cast<uint8_t>(alpha >> (8 * k));
+            int16_t* row = prof + k * lpa;
+            for (uint32_t col = lane; col < lpa; col += 32) {
+                int16_t v = static_cast<int16_t>(x);
+                if (col >= 1 && col <= len && seq[col - 1] == c) v = static_cast<int16_t>(m);
+                row[swz(col)] = v;
+            }
+        }
+        syncwarp();
+    }
+
+    /* ---------------------------------------------------------------- the DP (sisd :292-360, simd :760-906)
+     * Column c of a row holds H[row][c] for c = 0..len (column 0 is spoa's first_column); column -1 is
+     * -infinity, which makes column 0 follow the general recurrence.  Returns the best sink row
+     * (first strictly greater in processing order) in *best_row, its score, and the number of sink rows
+     * that reach that score. */
+    RP_DEV void dp(uint32_t nrows, uint32_t len, uint32_t lpa, uint32_t ring_rows, uint32_t* best_row,
+                   int32_t* best_score, uint32_t* n_best) {
+        const int32_t g = P->gap;
+        const uint32_t g2 = pack16(g, g);
+        const uint32_t neg2 = pack16(kNeg16, kNeg16);
+        const uint32_t nch = lpa / kChunkCols;
+        /* root row: H[0][c] = c * g */
+        for (uint32_t col = lane; col < lpa; col += 32) {
+            int16_t v = static_cast<int16_t>(static_cast<int32_t>(col) * g);
+            H[col] = v;
+            ring[swz(col)] = v;  // ring slot 0 <- rank 0
+        }
+        syncwarp();
+        int32_t best = kNeg32;
+        uint32_t bi = 0, nb = 0;
+        uint32_t rec_lo = 0, rec_hi = 0;
+        for (uint32_t i = 1; i <= nrows; ++i) {
+            if (((i - 1) & 31u) == 0) {
+                uint64_t t = rec[i + lane];  // rec[] is padded
+                rec_lo = static_cast<uint32_t>(t);
+                rec_hi = static_cast<uint32_t>(t >> 32);
+            }
+            uint32_t lo = shfl(rec_lo, (i - 1) & 31), hi = shfl(rec_hi, (i - 1) & 31);
+            uint32_t cidx = lo & 0xff;
+            uint32_t np = (lo >> 8) & 0x7f;
+            bool sink = (lo >> 15) & 1;
+            uint32_t npe = np ? np : 1;
+            int16_t* myrow_s = ring + (i % ring_rows) * lpa;
+            int16_t* myrow_g = H + static_cast<uint64_t>(i) * lpa;
+            int32_t chunk_carry = kNeg32;
+            for (uint32_t ch = 0; ch < nch; ++ch) {
+                uint32_t acc[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r] = neg2;
+                Row8 pf = load_row_smem(prof + cidx * lpa, ch, lane);
+                for (uint32_t k = 0; k < npe; ++k) {
+                    uint32_t p;
+                    if (np == 0)
+                        p = 0;
+                    else if (k == 0)
+                        p = lo >> 16;
+                    else if (k == 1)
+                        p = hi & 0xffff;
+                    else if (k == 2)
+                        p = hi >> 16;
+                    else
+                        p = pred_ovf[i * ki + k];
+                    bool near = (i - p) < ring_rows;
+                    const int16_t* prow_s = ring + (p % ring_rows) * lpa;
+                    const int16_t* prow_g = H + static_cast<uint64_t>(p) * lpa;
+                    Row8 pr = near ? load_row_smem(prow_s, ch, lane) : load_row_gmem(prow_g, ch, lane);
+                    uint32_t left = shfl_up(pr.r[7], 1);
+                    if (lane == 0) {
+                        int32_t lv = kNeg16;
+                        if (ch > 0) lv = near ? prow_s[swz(ch * kChunkCols - 1)] : prow_g[ch * kChunkCols - 1];
+                        left = pack16(0, lv);
+                    }
+                    uint32_t d = byte_perm(left, pr.r[0], 0x5432);
+                    acc[0] = viaddmax_s16x2(d, pf.r[0], acc[0]);
+                    acc[0] = viaddmax_s16x2(pr.r[0], g2, acc[0]);
+#pragma unroll
+                    for (int r = 1; r < 8; ++r) {
+                        d = byte_perm(pr.r[r - 1], pr.r[r], 0x5432);
+                        acc[r] = viaddmax_s16x2(d, pf.r[r], acc[r]);
+                        acc[r] = viaddmax_s16x2(pr.r[r], g2, acc[r]);
+                    }
+                }
+                /* in-row gap recurrence H[c] = max(H[c], H[c-1] + g): lane-local chain + warp max-plus scan */
+                int32_t y[16];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    y[2 * r] = lo16(acc[r]);
+                    y[2 * r + 1] = hi16(acc[r]);
+                }
+#pragma unroll
+                for (int k = 1; k < 16; ++k) y[k] = viaddmax_s32(y[k - 1], g, y[k]);
+                int32_t t = y[15];
+                if (lane == 0) t = viaddmax_s32(chunk_carry, 16 * g, t);
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    int32_t o = shfl_up(t, dd);
+                    if (lane >= dd) t = viaddmax_s32(o, dd * 16 * g, t);
+                }
+                int32_t carry = shfl_up(t, 1);
+                if (lane == 0) carry = chunk_carry;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) y[k] = viaddmax_s32(carry, (k + 1) * g, y[k]);
+                chunk_carry = shfl(y[15], 31);
+                Row8 out;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) out.r[r] = pack16(y[2 * r], y[2 * r + 1]);
+                store_row_smem(myrow_s, ch, lane, out);
+                store_row_gmem(myrow_g, ch, lane, out);
+            }
+            syncwarp();
+            if (sink) {
+                int32_t s = myrow_s[swz(len)];
+                if (s > best) {
+                    best = s;
+                    bi = i;
+                    nb = 1;
+                } else if (s == best) {
+                    ++nb;
+                }
+            }
+        }
+        *best_row = bi;
+        *best_score = best;
+        *n_best = nb;
+        syncwarp();
+    }
+
+    /* ---------------------------------------------------------------- spoa's DFS order (graph.cpp:249-303)
+     * Serial (lane 0).  With `sub`, runs on the subgraph exactly as spoa would on Graph::Subgraph():
+     * nodes in ascending id, in-edges/aligned nodes filtered to members, original list orders kept. */
+    RP_DEV void spoa_sort(bool sub) {
+        for (uint32_t v = lane; v < N; v += 32) marks[v] = 0;  // bits0-1 mark, bit2 ignored
+        syncwarp();
+        if (lane == 0) {
+            const uint32_t cap = P->lim.stack_cap;
+            uint32_t out = 0, sp = 0;
+            for (uint32_t root = 0; root < N && status == kWinOk; ++root) {
+                if (sub && !member[root]) continue;
+                if ((marks[root] & 3) != 0) continue;
+                stack[sp++] = static_cast<uint16_t>(root);
+                while (sp > 0) {
+                    uint32_t c = stack[sp - 1];
+                    bool valid = true;
+                    uint8_t mk = marks[c];
+                    if ((mk & 3) != 2) {
+                        uint32_t ni = in_cnt[c], na = al_cnt[c];
+                        if (sp + ni + na > cap) {
+                            fail(kWinStackLimit);
+                            break;
+                        }
+                        for (uint32_t k = 0; k < ni; ++k) {
+                            uint32_t t = in_tail[c * ki + k];
+                            if (sub && !member[t]) continue;
+                            if ((marks[t] & 3) != 2) {
+                                stack[sp++] = static_cast<uint16_t>(t);
+                                valid = false;
+                            }
+                        }
+                        if (!(mk & 4)) {
+                            for (uint32_t k = 0; k < na; ++k) {
+                                uint32_t a = al[c * ka + k];
+                                if (sub && !member[a]) continue;
+                                if ((marks[a] & 3) != 2) {
+                                    stack[sp++] = static_cast<uint16_t>(a);
+                                    marks[a] |= 4;
+                                    valid = false;
+                                }
+                            }
+                        }
+                        if (valid) {
+                            marks[c] = static_cast<uint8_t>((marks[c] & 4) | 2);
+                            if (!(marks[c] & 4)) {
+                                srank[c] = static_cast<uint16_t>(out);
+                                sorder[out++] = static_cast<uint16_t>(c);
+                                for (uint32_t k = 0; k < na; ++k) {
+                                    uint32_t a = al[c * ka + k];
+                                    if (sub && !member[a]) continue;
+                                    srank[a] = static_cast<uint16_t>(out);
+                                    sorder[out++] = static_cast<uint16_t>(a);
+                                }
+                            }
+                        } else {
+                            marks[c] = static_cast<uint8_t>((marks[c] & 4) | 1);
+                        }
+                    }
+                    if (valid) --sp;
+                }
+            }
+        }
+        status = shfl(status, 0);
+        syncwarp();
+    }
+
+    /* Among sink rows whose last-column score equals `best`, the one spoa visits first (sisd :353-355). */
+    RP_DEV uint32_t resolve_sink_tie(uint32_t nrows, uint32_t len, uint32_t lpa, int32_t best, bool sub) {
+        spoa_sort(sub);
+        const uint16_t* ord = sub ? dp_order : order;
+        uint32_t bestkey = 0xffffffffu;
+        for (uint32_t r = 1 + lane; r <= nrows; r += 32) {
+            uint64_t rc = rec[r];
+            if (!((rc >> 15) & 1)) continue;
+            if (H[static_cast<uint64_t>(r) * lpa + len] != best) continue;
+            uint32_t key = (static_cast<uint32_t>(srank[ord[r]]) << 16) | r;
+            if (key < bestkey) bestkey = key;
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            uint32_t o = shfl_down(bestkey, d);
+            if (o < bestkey) bestkey = o;
+        }
+        bestkey = shfl(bestkey, 0);
+        return bestkey & 0xffffu;
+    }
+
+    /* ---------------------------------------------------------------- traceback (sisd :366-459)
+     * Priority: diagonal over predecessors in in-edge order, then vertical in the same order, then
+     * horizontal.  Lanes test predecessors in parallel; the lowest lane that matches wins.
+     * Output: aln[j] = node aligned to read position j, or kNone (new node). */
+    RP_DEV void traceback(uint32_t best_row, uint32_t len, uint32_t lpa, const uint8_t* seq, bool sub) {
+        const int32_t g = P->gap, m = P->match, x = P->mismatch;
+        const uint16_t* ord = sub ? dp_order : order;
+        uint32_t i = best_row, j = len;
+        uint32_t tile_base = 0xffffffffu;
+        uint32_t t_lo = 0, t_hi = 0, t_node = 0;
+        while (i != 0) {
+            if ((i & ~31u) != tile_base) {
+                tile_base = i & ~31u;
+                uint64_t t = rec[tile_base + lane];
+                t_lo = static_cast<uint32_t>(t);
+                t_hi = static_cast<uint32_t>(t >> 32);
+                t_node = ord[tile_base + lane];  // dp_order/order arrays are padded past nmax
+            }
+            uint32_t lo = shfl(t_lo, i & 31), hi = shfl(t_hi, i & 31);
+            uint32_t node = shfl(t_node, i & 31);
+            uint32_t cidx = lo & 0xff, np = (lo >> 8) & 0x7f;
+            uint32_t npe = np ? np : 1;
+            int32_t hij = H[static_cast<uint64_t>(i) * lpa + j];
+            int32_t mc = 0;
+            if (j > 0) mc = (static_cast<uint8_t>(alpha >> (8 * cidx)) == seq[j - 1]) ? m : x;
+            uint32_t found_p = 0;
+            int move = 0;  // 1 diag, 2 vert, 3 horiz
+            /* pass 1: diagonal, pass 2: vertical */
+            for (int pass = 1; pass <= 2 && !move; ++pass) {
+                if (pass == 1 && j == 0) continue;
+                for (uint32_t k0 = 0; k0 < npe && !move; k0 += 32) {
+                    uint32_t k = k0 + lane;
+                    uint32_t p = 0;
+                    bool ok = false;
+                    if (k < npe) {
+                        if (np == 0)
+                            p = 0;
+                        else if (k == 0)
+                            p = lo >> 16;
+                        else if (k == 1)
+                            p = hi & 0xffff;
+                        else if (k == 2)
+                            p = hi >> 16;
+                        else
+                            p = pred_ovf[i * ki + k];
+                        const int16_t* pr = H + static_cast<uint64_t>(p) * lpa;
+                        ok = (pass == 1) ? (hij == pr[j - 1] + mc) : (hij == pr[j] + g);
+                    }
+                    uint32_t msk = ballot(ok);
+                    if (msk) {
+                        found_p = shfl(p, ffs_(msk) - 1);
+                        move = pass;
+                    }
+                }
+            }
+            if (!move) move = 3;
+            if (move == 1) {
+                if (lane == 0) aln[j - 1] = static_cast<uint16_t>(node);
+                i = found_p;
+                --j;
+            } else if (move == 2) {
+                i = found_p;
+            } else {
+                if (j == 0) {  // unreachable for a consistent matrix (column 0 always has a vertical move)
+                    fail(kWinInternal);
+                    break;
+                }
+                if (lane == 0) aln[j - 1] = kNone;
+                --j;
+            }
+        }
+        /* row 0: remaining columns are horizontal moves (insertions at the start of the read) */
+        for (uint32_t c = lane; c < j; c += 32) aln[c] = kNone;
+        syncwarp();
+    }
+
+    /* ---------------------------------------------------------------- graph merge (graph.cpp:155-247) +
+     * incremental order update.  aln[j] = aligned node or kNone for every read position j. */
+    RP_DEV void add_alignment(const uint8_t* seq, const uint8_t* w, uint32_t len) {
+        const uint32_t n_old = N;
+        uint16_t* delta = reinterpret_cast<uint16_t*>(smem);  // n_old + 2 counters (ring is idle now)
+        /* Phase A: target node per position (existing node, aligned sibling with the same character, or new) */
+        uint32_t n_new = 0;
+        for (uint32_t j0 = 0; j0 < len; j0 += 32) {
+            uint32_t j = j0 + lane;
+            bool is_new = false;
+            uint32_t tgt = kNone, anchor = kNone;
+            if (j < len) {
+                uint32_t a = aln[j];
+                uint8_t c = seq[j];
+                if (a == kNone) {
+                    is_new = true;
+                } else if (code[a] == c) {
+                    tgt = a;
+                } else {
+                    uint32_t na = al_cnt[a];
+                    for (uint32_t k = 0; k < na; ++k) {
+                        uint32_t s = al[a * ka + k];
+                        if (code[s] == c) {
+                            tgt = s;
+                            break;
+                        }
+                    }
+                    if (tgt == kNone) {
+                        is_new = true;
+                        anchor = a;
+                    }
+                }
+            }
+            uint32_t tot;
+            uint32_t pos = warp_rank(is_new, &tot);
+            if (is_new) {
+                uint32_t id = n_old + n_new + pos;
+                tgt = id;
+                if (id < nmax) {
+                    code[id] = seq[j];
+                    flags[id] = 0;
+                    in_cnt[id] = 0;
+                    cov[id] = 0;
+                    al_cnt[id] = 0;
+                }
+                newlist[n_new + pos] = (j << 16) | anchor;  // anchor kNone => unaligned insertion
+            }
+            if (j < len) cur[j] = static_cast<uint16_t>(tgt);
+            n_new += tot;
+        }
+        if (n_old + n_new > nmax) {
+            fail(kWinNodeLimit);
+            return;
+        }
+        syncwarp();
+        /* K_j: rank after which position j's node sits / is inserted (non-decreasing along the read) */
+        /* Phase B: aligned-cluster membership of new nodes + per-position order keys */
+        /* keys are kept in cur-parallel scratch: reuse `aln` as uint16 key array after reading it */
+        bool lim_a = false;
+        for (uint32_t k0 = 0; k0 < n_new; k0 += 32) {
+            uint32_t k = k0 + lane;
+            if (k < n_new) {
+                uint32_t e = newlist[k];
+                uint32_t anchor = e & 0xffffu;
+                uint32_t id = n_old + k;
+                if (anchor != kNone) {
+                    uint32_t na = al_cnt[anchor];
+                    if (na + 1 > ka) {
+                        lim_a = true;
+                    } else {
+                        for (uint32_t q = 0; q < na; ++q) {
+                            uint32_t s = al[anchor * ka + q];
+                            al[id * ka + q] = static_cast<uint16_t>(s);
+                            uint32_t ns = al_cnt[s];
+                            al[s * ka + ns] = static_cast<uint16_t>(id);
+                            al_cnt[s] = static_cast<uint8_t>(ns + 1);
+                        }
+                        al[id * ka + na] = static_cast<uint16_t>(anchor);
+                        al_cnt[id] = static_cast<uint8_t>(na + 1);
+                        al[anchor * ka + na] = static_cast<uint16_t>(id);
+                        al_cnt[anchor] = static_cast<uint8_t>(na + 1);
+                    }
+                }
+            }
+        }
+        if (ballot(lim_a)) {
+            fail(kWinAlignedLimit);
+            return;
+        }
+        syncwarp();
+        /* order keys: for an old target (or the anchor of an aligned new node) the end of its cluster block */
+        int32_t run = 0;  // running max of keys over previous positions (K_{-1} = 0: right after the root)
+        for (uint32_t j0 = 0; j0 < len; j0 += 32) {
+            uint32_t j = j0 + lane;
+            int32_t own = 0;
+            if (j < len) {
+                uint32_t t = cur[j];
+                uint32_t base_node = kNone;
+                if (t < n_old) {
+                    base_node = t;
+                } else {
+                    uint32_t anchor = newlist[t - n_old] & 0xffffu;
+                    if (anchor != kNone) base_node = anchor;
+                }
+                if (base_node != kNone) {
+                    uint32_t r = rank_of[base_node];
+                    uint32_t na = al_cnt[base_node];
+                    for (uint32_t q = 0; q < na; ++q) {
+                        uint32_t s = al[base_node * ka + q];
+                        if (s < n_old) {
+                            uint32_t rs = rank_of[s];
+                            if (rs > r) r = rs;
+                        }
+                    }
+                    own = static_cast<int32_t>(r);
+                }
+            }
+            int32_t inc = warp_incl_max(own);
+            if (inc < run) inc = run;
+            if (j < len) aln[j] = static_cast<uint16_t>(inc);  // aln now holds K_j
+            run = shfl(inc, 31);
+        }
+        syncwarp();
+        /* Phase C: edges (graph.cpp:81-91,236-243) + per-node sequence counters (Node::Coverage, :32-47) */
+        bool lim_e = false;
+        for (uint32_t j0 = 0; j0 < len; j0 += 32) {
+            uint32_t j = j0 + lane;
+            if (j < len) {
+                uint32_t c = cur[j];
+                if (len >= 2) cov[c] = static_cast<uint16_t>(cov[c] + 1);
+                if (j > 0) {
+                    uint32_t pv = cur[j - 1];
+                    int32_t wt = static_cast<int32_t>(w[j - 1]) + static_cast<int32_t>(w[j]);
+                    uint32_t ni = in_cnt[c];
+                    uint32_t q = 0;
+                    for (; q < ni; ++q)
+                        if (in_tail[c * ki + q] == pv) break;
+                    if (q < ni) {
+                        in_w[c * ki + q] += wt;
+                    } else if (ni < ki && ni < 127) {
+                        in_tail[c * ki + ni] = static_cast<uint16_t>(pv);
+                        in_w[c * ki + ni] = wt;
+                        in_cnt[c] = static_cast<uint8_t>(ni + 1);
+                        flags[pv] |= 1;  // several lanes may set different nodes' flags; each pv is unique per lane
+                    } else {
+                        lim_e = true;
+                    }
+                }
+            }
+        }
+        if (ballot(lim_e)) {
+            fail(kWinEdgeLimit);
+            return;
+        }
+        syncwarp();
+        /* Phase D: merge new nodes into the processing order.  New node k (read order) with key K goes to
+         * rank K + 1 + k; an old node at rank q moves to q + #{new nodes with key < q}. */
+        if (n_new > 0) {
+            if ((n_old + 4) * 2 > smem_bytes) {
+                fail(kWinNodeLimit);
+                return;
+            }
+            for (uint32_t q = lane; q < n_old + 2; q += 32) delta[q] = 0;
+            syncwarp();
+            for (uint32_t k = lane; k < n_new; k += 32) {
+                uint32_t j = newlist[k] >> 16;
+                uint32_t key = aln[j];  // aligned new node: end of its cluster block; insertion: K_{j-1}
+                uint32_t id = n_old + k;
+                uint32_t nr = key + 1 + k;
+                order_nxt[nr] = static_cast<uint16_t>(id);
+                rank_of[id] = static_cast<uint16_t>(nr);
+#if defined(RP_HOST_SIM)
+                delta[key + 1] = static_cast<uint16_t>(delta[key + 1] + 1);
+#else
+                atomicAdd(reinterpret_cast<unsigned int*>(delta + ((key + 1) & ~1u)), (key + 1) & 1u ? 0x10000u : 1u);
+#endif
+            }
+            syncwarp();
+            uint32_t carry = 0;
+            for (uint32_t q0 = 1; q0 <= n_old; q0 += 32) {
+                uint32_t q = q0 + lane;
+                uint32_t d = q <= n_old ? delta[q] : 0;
+                uint32_t inc = warp_incl_sum(d) + carry;
+                if (q <= n_old) {
+                    uint32_t v = order[q];
+                    order_nxt[q + inc] = static_cast<uint16_t>(v);
+                    rank_of[v] = static_cast<uint16_t>(q + inc);
+                }
+                carry = shfl(inc, 31);
+            }
+            if (lane == 0) order_nxt[0] = kNone;
+            uint16_t* t = order;
+            order = order_nxt;
+            order_nxt = t;
+            N = n_old + n_new;
+        }
+        ++n_added;
+        syncwarp();
+    }
+
+    /* ---------------------------------------------------------------- consensus (graph.cpp:433-516, 377-398) */
+    RP_DEV void better(uint32_t it, uint32_t t, int64_t wgt) {
+        int64_t si = score[it];
+        if (si < wgt || (si == wgt && cpred[it] != kNone && score[cpred[it]] <= score[t])) {
+            score[it] = wgt;
+            cpred[it] = static_cast<uint16_t>(t);
+        }
+    }
+
+    RP_DEV uint32_t consensus(uint8_t* out, uint16_t* out_cov, uint32_t out_cap, bool trim, uint32_t n_seq) {
+        spoa_sort(false);
+        if (status != kWinOk) return 0;
+        for (uint32_t v = lane; v < N; v += 32) {
+            score[v] = -1;
+            cpred[v] = kNone;
+        }
+        syncwarp();
+        uint32_t mx = kNone;
+        if (lane == 0) {
+            for (uint32_t r = 0; r < N; ++r) {
+                uint32_t it = sorder[r];
+                uint32_t ni = in_cnt[it];
+                for (uint32_t k = 0; k < ni; ++k) better(it, in_tail[it * ki + k], in_w[it * ki + k]);
+                if (cpred[it] != kNone) score[it] += score[cpred[it]];
+                if (mx == kNone || score[mx] < score[it]) mx = it;
+            }
+        }
+        mx = shfl(mx, 0);
+        syncwarp();
+        /* branch completion (graph.cpp:478-516) while the best node still has out-edges */
+        while (flags[mx] & 1) {
+            /* heads of mx's out-edges = nodes with an in-edge from mx; their other tails are invalidated */
+            for (uint32_t v = lane; v < N; v += 32) {
+                uint32_t ni = in_cnt[v];
+                bool hit = false;
+                for (uint32_t k = 0; k < ni; ++k) hit |= (in_tail[v * ki + k] == mx);
+                if (hit)
+                    for (uint32_t k = 0; k < ni; ++k) {
+                        uint32_t t = in_tail[v * ki + k];
+                        if (t != mx) score[t] = -1;
+                    }
+            }
+            syncwarp();
+            uint32_t nm = kNone;
+            if (lane == 0) {
+                for (uint32_t r = static_cast<uint32_t>(srank[mx]) + 1; r < N; ++r) {
+                    uint32_t it = sorder[r];
+                    score[it] = -1;
+                    cpred[it] = kNone;
+                    uint32_t ni = in_cnt[it];
+                    for (uint32_t k = 0; k < ni; ++k) {
+                        uint32_t t = in_tail[it * ki + k];
+                        if (score[t] == -1) continue;
+                        better(it, t, in_w[it * ki + k]);
+                    }
+                    if (cpred[it] != kNone) score[it] += score[cpred[it]];
+                    if (nm == kNone || score[nm] < score[it]) nm = it;
+                }
+            }
+            nm = shfl(nm, 0);
+            syncwarp();
+            if (nm == kNone) break;  // cannot happen: a node with out-edges has successors of higher rank
+            mx = nm;
+        }
+        /* walk predecessors back; the path is stored reversed in `stack`, then emitted forward */
+        uint32_t clen = 0;
+        if (lane == 0) {
+            uint32_t v = mx;
+            while (v != kNone && clen < P->lim.stack_cap) {
+                stack[clen++] = static_cast<uint16_t>(v);
+                v = cpred[v];
+            }
+        }
+        clen = shfl(clen, 0);
+        syncwarp();
+        /* coverage (graph.cpp:388-394): node + its aligned nodes, counted as sequences through the node */
+        uint32_t thr = (n_seq - 1) / 2;
+        uint32_t first = 0xffffffffu, last = 0;
+        for (uint32_t k = lane; k < clen; k += 32) {
+            uint32_t v = stack[clen - 1 - k];
+            uint32_t c = cov[v];
+            uint32_t na = al_cnt[v];
+            for (uint32_t q = 0; q < na; ++q) c += cov[al[v * ka + q]];
+            if (c > 0xffffu) c = 0xffffu;
+            dp_rank[k] = static_cast<uint16_t>(c);  // dp_rank is idle here: per-base coverage scratch
+            if (c >= thr) {
+                if (k < first) first = k;
+                if (k + 1 > last) last = k + 1;
+            }
+        }
+        return finish_consensus(out, out_cov, out_cap, trim, clen, first, last);
+    }
+
+    RP_DEV uint32_t finish_consensus(uint8_t* out, uint16_t* out_cov, uint32_t out_cap, bool trim, uint32_t clen,
+                                      uint32_t first, uint32_t last) {
+        for (int d = 16; d > 0; d >>= 1) {
+            uint32_t of = shfl_down(first, d), ol = shfl_down(last, d);
+            if (of < first) first = of;
+            if (ol > last) last = ol;
+        }
+        first = shfl(first, 0);
+        last = shfl(last, 0);
+        uint32_t b = 0, e = clen;  // [b, e)
+        if (trim) {
+            /* window.cpp:125-146: begin = first index with coverage >= thr, end = last such index;
+             * keep [begin, end] only when begin < end */
+            if (first != 0xffffffffu && last >= 1 && first < last - 1) {
+                b = first;
+                e = last;
+            }
+        }
+        uint32_t n = e - b;
+        if (n > out_cap) {
+            fail(kWinInternal);
+            return 0;
+        }
+        for (uint32_t k = b + lane; k < e; k += 32) {
+            uint32_t v = stack[clen - 1 - k];
+            out[k - b] = code[v];
+            out_cov[k - b] = cur_cov(k);
+        }
+        syncwarp();
+        return n;
+    }
+
+    RP_DEV uint16_t cur_cov(uint32_t k) const { return dp_rank[k]; }
+};
+
+/* int16 is safe iff spoa's own criterion holds (alignment_engine.cpp:101-110, simd impl :699-745) */
+RP_DEV bool fits_int16(int32_t m, int32_t g, int64_t len, int64_t nodes) {
+    int64_t i = len + 8, j = nodes;
+    int64_t mn = i < j ? i : j;
+    int64_t df = i > j ? i - j : j - i;
+    int64_t a = -1 * (m * mn + g * df);
+    int64_t b = g * i + g * j;
+    int64_t worst = a < b ? a : b;
+    return worst >= static_cast<int64_t>(-32768 + 1024);
+}
+
+/* Processes one window end to end. `slot`: this warp's HBM scratch, `smem`: this warp's shared memory. */
+RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* smem) {
+    PoaWarp W;
+    W.bind(&P, slot, smem, P.smem_per_warp);
+    W.status = kWinOk;
+    const uint32_t s0 = P.win_first[w], s1 = P.win_first[w + 1];
+    W.alpha = P.win_alpha[w];
+    uint32_t nc = 0;
+    while (nc < 8 && ((W.alpha >> (8 * nc)) & 0xff) != 0) ++nc;
+    W.ncodes = nc;
+    const uint32_t lane = W.lane;
+    uint8_t* out = P.cons + P.out_off[w];
+    uint16_t* out_cov = P.cons_cov + P.out_off[w];
+
+    uint32_t boff = P.seq_off[s0];
+    uint32_t blen = P.seq_off[s0 + 1] - boff;
+    if (blen > P.lim.nmax) {
+        if (lane == 0) {
+            P.status[w] = kWinNodeLimit;
+            P.cons_len[w] = 0;
+        }
+        return;
+    }
+    W.init_backbone(P.bases + boff, P.weights + boff, blen);
+
+    for (uint32_t s = s0 + 1; s < s1 && W.status == kWinOk; ++s) {
+        uint32_t off = P.seq_off[s];
+        uint32_t len = P.seq_off[s + 1] - off;
+        const uint8_t* seq = P.bases + off;
+        const uint8_t* wts = P.weights + off;
+        if (len > P.lim.lmax) {
+            W.fail(kWinSeqTooLong);
+            break;
+        }
+        bool sub = !(P.seq_flags[s] & 1);
+        uint32_t nrows = W.N;
+        if (sub) {
+            W.mark_subgraph(P.seq_begin[s], P.seq_end[s]);
+            if (W.status != kWinOk) break;
+            nrows = W.build_dp_order_subgraph();
+        }
+        if (!fits_int16(P.match, P.gap, len, nrows)) {
+            W.fail(kWinNeedsInt32);
+            break;
+        }
+        uint32_t lpa = (len + 1 + kChunkCols - 1) / kChunkCols * kChunkCols;
+        /* shared memory split: profile rows first, the rest is the ring of recent DP rows */
+        uint32_t prof_bytes = W.ncodes * lpa * 2;
+        uint32_t ring_rows = (P.smem_per_warp - prof_bytes) / (lpa * 2);
+        if (prof_bytes + 2 * lpa * 2 > P.smem_per_warp) {
+            W.fail(kWinSeqTooLong);
+            break;
+        }
+        W.prof = reinterpret_cast<int16_t*>(smem);
+        W.ring = reinterpret_cast<int16_t*>(smem + prof_bytes);
+        W.build_program(nrows, sub);
+        W.build_profile(seq, len, lpa);
+        uint32_t best_row, n_best;
+        int32_t best;
+        W.dp(nrows, len, lpa, ring_rows, &best_row, &best, &n_best);
+        if (n_best > 1) {
+            best_row = W.resolve_sink_tie(nrows, len, lpa, best, sub);
+            if (W.status != kWinOk) break;
+        }
+        W.traceback(best_row, len, lpa, seq, sub);
+        W.add_alignment(seq, wts, len);
+        if (P.stats && lane == 0) {
+#if !defined(RP_HOST_SIM)
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.stats), 1ull);
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 1),
+                      static_cast<unsigned long long>(nrows + 1) * (len + 1));
+            if (n_best > 1) atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 2), 1ull);
+#else
+            P.stats[0] += 1;
+            P.stats[1] += static_cast<uint64_t>(nrows + 1) * (len + 1);
+            if (n_best > 1) P.stats[2] += 1;
+#endif
+        }
+    }
+    uint32_t clen = 0;
+    if (W.status == kWinOk) clen = W.consensus(out, out_cov, P.out_cap[w], (P.win_flags[w] & 1) != 0, s1 - s0);
+    if (lane == 0) {
+        P.status[w] = W.status;
+        P.cons_len[w] = W.status == kWinOk ? clen : 0;
+    }
+    syncwarp();
+}
+
+}  // namespace rp

@@ -1,0 +1,218 @@
+/*
+ * poa_pack.hpp — host-side packing of racon windows into the flat HBM layout the POA kernel reads.
+ *
+ * Mirrors, on the host, the parts of the reference that decide WHAT is aligned and in which order:
+ *   racon::createWindow / Window::add_layer validation and skipping  (src/window.cpp:15-63)
+ *   "< 3 sequences => consensus = backbone, false"                     (src/window.cpp:68-71)
+ *   layer order = std::sort of indices by begin position (unstable!)   (src/window.cpp:79-86)
+ *   full-span test begin < 0.01*len && end > len - 0.01*len            (src/window.cpp:88-94)
+ *   weights = quality - 33, or 1 without quality                       (vendor/spoa/src/graph.cpp:121-146)
+ * Pure C++ (no CUDA): shared by the product library (pinned buffers) and the test-only host simulation.
+ */
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace rp {
+
+/* growable POD buffer whose storage comes from a pluggable allocator (pinned host memory in the product) */
+struct HostAllocator {
+    void* (*alloc)(size_t);
+    void (*release)(void*);
+};
+
+template <typename T>
+struct GrowBuf {
+    T* data = nullptr;
+    size_t size = 0, cap = 0;
+    const HostAllocator* al = nullptr;
+    explicit GrowBuf(const HostAllocator* a) : al(a) {}
+    GrowBuf(const GrowBuf&) = delete;
+    GrowBuf& operator=(const GrowBuf&) = delete;
+    ~GrowBuf() {
+        if (data) al->release(data);
+    }
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        size_t nc = cap ? cap : 1024;
+        while (nc < n) nc *= 2;
+        T* nd = static_cast<T*>(al->alloc(nc * sizeof(T)));
+        if (!nd) return false;
+        if (size) std::memcpy(nd, data, size * sizeof(T));
+        if (data) al->release(data);
+        data = nd;
+        cap = nc;
+        return true;
+    }
+    bool push(const T& v) {
+        if (!reserve(size + 1)) return false;
+        data[size++] = v;
+        return true;
+    }
+    T* extend(size_t n) {  // returns pointer to n new (uninitialised) elements
+        if (!reserve(size + n)) return nullptr;
+        T* p = data + size;
+        size += n;
+        return p;
+    }
+    void clear() { size = 0; }
+    size_t bytes() const { return size * sizeof(T); }
+};
+
+enum PackResult { kPackOk = 0, kPackFull = 1, kPackInvalid = -1, kPackNoMem = -3 };
+
+struct PackedBatch {
+    /* device-bound arrays */
+    GrowBuf<uint8_t> bases, weights, seq_flags, win_flags;
+    GrowBuf<uint32_t> seq_off, seq_begin, seq_end, win_first, out_off, out_cap, queue;
+    GrowBuf<uint64_t> win_alpha;
+    /* host-only bookkeeping, one entry per ADDED window (in add order) */
+    std::vector<int32_t> gpu_index;        // index among GPU windows, or -1 (trivial), -2 (alphabet limit)
+    std::vector<std::string> trivial;      // consensus of trivial windows (backbone copy), indexed by added order
+    std::vector<uint32_t> cost;            // per GPU window: total bases (queue ordering)
+    uint64_t out_total = 0;
+    /* limits */
+    uint64_t max_bases = 0xfff00000ull;    // uint32 offsets
+    uint32_t max_windows = 1u << 22;
+    uint32_t max_seq_len = 65000;
+
+    explicit PackedBatch(const HostAllocator* a)
+        : bases(a), weights(a), seq_flags(a), win_flags(a), seq_off(a), seq_begin(a), seq_end(a), win_first(a),
+          out_off(a), out_cap(a), queue(a), win_alpha(a) {
+        reset();
+    }
+
+    void reset() {
+        bases.clear(); weights.clear(); seq_flags.clear(); win_flags.clear();
+        seq_off.clear(); seq_begin.clear(); seq_end.clear(); win_first.clear();
+        out_off.clear(); out_cap.clear(); queue.clear(); win_alpha.clear();
+        seq_off.push(0);
+        win_first.push(0);
+        gpu_index.clear();
+        trivial.clear();
+        cost.clear();
+        out_total = 0;
+    }
+
+    uint32_t n_added() const { return static_cast<uint32_t>(gpu_index.size()); }
+    uint32_t n_gpu() const { return static_cast<uint32_t>(win_flags.size); }
+
+    /* One window; same argument meaning as rp_poa_add_window (include/racon_b200.h). */
+    int add(uint32_t n_seq, const char* const* seq, const uint32_t* len, const char* const* qual,
+            const uint32_t* begin, const uint32_t* end, int window_type, int trim) {
+        if (n_seq == 0 || !seq || !len || !seq[0] || len[0] == 0) return kPackInvalid;  // window.cpp:19-23
+        const uint32_t blen = len[0];
+        if (blen > max_seq_len) return kPackInvalid;
+        /* Window::add_layer, window.cpp:42-63 */
+        std::vector<uint32_t> kept;
+        kept.push_back(0);
+        uint64_t tot = blen;
+        for (uint32_t k = 1; k < n_seq; ++k) {
+            if (len[k] == 0 || begin[k] == end[k]) continue;
+            if (!seq[k] || begin[k] >= end[k] || begin[k] > blen || end[k] > blen) return kPackInvalid;
+            if (len[k] > max_seq_len) return kPackInvalid;
+            kept.push_back(k);
+            tot += len[k];
+        }
+        if (kept.size() < 3) {  // window.cpp:68-71
+            gpu_index.push_back(-1);
+            trivial.emplace_back(seq[0], blen);
+            return kPackOk;
+        }
+        /* layer order, window.cpp:79-86 — the same std::sort call on the same element type */
+        std::vector<uint32_t> rank(kept.size());
+        for (uint32_t i = 0; i < rank.size(); ++i) rank[i] = i;
+        std::sort(rank.begin() + 1, rank.end(),
+                  [&](uint32_t l, uint32_t r) { return begin[kept[l]] < begin[kept[r]]; });
+        const uint32_t offset = static_cast<uint32_t>(0.01 * blen);  // window.cpp:88
+        for (uint32_t i = 1; i < rank.size(); ++i) {
+            uint32_t k = kept[rank[i]];
+            bool full = begin[k] < offset && end[k] > blen - offset;
+            if (!full && end[k] >= blen) return kPackInvalid;  // Subgraph(begin, end) needs backbone node `end`
+        }
+        if (bases.size + tot > max_bases || n_gpu() >= max_windows) return kPackFull;
+
+        /* alphabet: distinct characters in first-seen order */
+        uint64_t alpha = 0;
+        uint32_t ncodes = 0;
+        bool seen[256] = {false};
+        bool too_many = false;
+        for (uint32_t i = 0; i < rank.size() && !too_many; ++i) {
+            uint32_t k = kept[rank[i]];
+            for (uint32_t j = 0; j < len[k]; ++j) {
+                uint8_t c = static_cast<uint8_t>(seq[k][j]);
+                if (c == 0) return kPackInvalid;
+                if (!seen[c]) {
+                    seen[c] = true;
+                    if (ncodes == 8) {
+                        too_many = true;
+                        break;
+                    }
+                    alpha |= static_cast<uint64_t>(c) << (8 * ncodes++);
+                }
+            }
+        }
+        if (too_many) {
+            gpu_index.push_back(-2);
+            trivial.emplace_back();
+            return kPackOk;
+        }
+
+        uint8_t* b = bases.extend(tot);
+        uint8_t* w = weights.extend(tot);
+        if (!b || !w) return kPackNoMem;
+        uint32_t off = seq_off.data[seq_off.size - 1];
+        for (uint32_t i = 0; i < rank.size(); ++i) {
+            uint32_t k = kept[rank[i]];
+            std::memcpy(b, seq[k], len[k]);
+            const char* q = qual ? qual[k] : nullptr;
+            if (q) {
+                for (uint32_t j = 0; j < len[k]; ++j) w[j] = static_cast<uint8_t>(q[j] - 33);
+            } else {
+                std::memset(w, i == 0 ? 0 : 1, len[k]);  // dummy '!' backbone => 0; layer without quality => 1
+            }
+            b += len[k];
+            w += len[k];
+            off += len[k];
+            bool full = i > 0 && begin[k] < offset && end[k] > blen - offset;
+            if (!seq_off.push(off) || !seq_begin.push(i ? begin[k] : 0) || !seq_end.push(i ? end[k] : 0) ||
+                !seq_flags.push(full ? 1 : 0))
+                return kPackNoMem;
+        }
+        uint32_t cap = 2 * blen + 64;
+        if (!win_first.push(static_cast<uint32_t>(seq_off.size - 1)) ||
+            !win_flags.push((window_type == 1 && trim) ? 1 : 0) || !win_alpha.push(alpha) ||
+            !out_off.push(static_cast<uint32_t>(out_total)) || !out_cap.push(cap))
+            return kPackNoMem;
+        out_total += cap;
+        gpu_index.push_back(static_cast<int32_t>(n_gpu() - 1));
+        trivial.emplace_back();
+        cost.push_back(static_cast<uint32_t>(tot));
+        return kPackOk;
+    }
+
+    /* processing order: most expensive windows first (persistent warps pull from this queue) */
+    bool build_queue() {
+        uint32_t n = n_gpu();
+        queue.clear();
+        if (!queue.reserve(n ? n : 1)) return false;
+        std::vector<uint32_t> idx(n);
+        for (uint32_t i = 0; i < n; ++i) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t c) { return cost[a] > cost[c]; });
+        for (uint32_t i = 0; i < n; ++i) queue.push(idx[i]);
+        return true;
+    }
+
+    uint32_t max_layer_len() const {
+        uint32_t m = 0;
+        for (size_t s = 0; s + 1 < seq_off.size; ++s) m = std::max(m, seq_off.data[s + 1] - seq_off.data[s]);
+        return m;
+    }
+};
+
+}  // namespace rp
