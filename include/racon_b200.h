@@ -111,7 +111,8 @@ rp_status rp_poa_reset(rp_poa* p);        /* CUDABatchProcessor::reset (cudabatc
 /* stream / measurement hooks */
 rp_status rp_poa_set_stream(rp_poa* p, void* cuda_stream);   /* use the caller's cudaStream_t */
 /* info[0] kernel launches so far, [1] last H2D bytes, [2] last D2H bytes, [3] worker warps,
- * [4] scratch bytes per warp, [5] device alignments done (if counters enabled), [6] DP cells, [7] sink ties */
+ * [4] scratch bytes per warp; with counters enabled: [5] alignments done, [6] DP cells sum (L+1)(N+1),
+ * [7] predecessor cells sum (L+1)*E (E = sum over rows of max(1, in-degree)) — SURVEY.md §8(d) byte model */
 rp_status rp_poa_info(rp_poa* p, uint64_t info[8]);
 rp_status rp_poa_enable_counters(rp_poa* p, int on);
 

@@ -1,0 +1,249 @@
+"""ctypes binding of the C ABI (include/racon_b200.h) — used by tests/, bench.py and __graft_entry__.py.
+
+The product is libracon_b200.so (C ABI + sm_100a kernels + C++ host mirror); this module only calls it.
+Loading fails loudly when the library is missing; creating a batch fails loudly without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build
+
+_lib = None
+
+RP_OK = 0
+RP_BATCH_FULL = 1
+
+
+class RaconB200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(build.LIBDIR, "libracon_b200.so")
+
+
+def load(build_if_missing=True):
+    """Loads libracon_b200.so (building it in-tree first if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if build_if_missing:
+        try:
+            path = build.build_cuda()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    if not os.path.exists(path):
+        raise RaconB200Error("libracon_b200.so is missing: run __graft_entry__.build() (no CPU fallback exists)")
+    lib = C.CDLL(path)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.rp_strerror.restype = C.c_char_p
+    lib.rp_strerror.argtypes = [C.c_int32]
+    lib.rp_last_error.restype = C.c_char_p
+    lib.rp_version.restype = C.c_char_p
+    lib.rp_device_count.restype = C.c_int
+    lib.rp_poa_create.restype = C.c_int32
+    lib.rp_poa_create.argtypes = [C.POINTER(vp), C.c_int, C.c_size_t, C.c_int8, C.c_int8, C.c_int8, C.c_int, u32, u32]
+    lib.rp_poa_destroy.restype = None
+    lib.rp_poa_destroy.argtypes = [vp]
+    lib.rp_poa_add_window.restype = C.c_int32
+    lib.rp_poa_add_window.argtypes = [vp, u32, vp, vp, vp, vp, vp, C.c_int, C.c_int]
+    lib.rp_poa_add_window_set.restype = C.c_int32
+    lib.rp_poa_add_window_set.argtypes = [vp, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    lib.rp_poa_size.restype = u32
+    lib.rp_poa_size.argtypes = [vp]
+    for name in ("rp_poa_run", "rp_poa_sync", "rp_poa_upload", "rp_poa_launch", "rp_poa_download", "rp_poa_reset"):
+        getattr(lib, name).restype = C.c_int32
+        getattr(lib, name).argtypes = [vp]
+    lib.rp_poa_fetch.restype = C.c_int32
+    lib.rp_poa_fetch.argtypes = [vp, u32, vp, vp, vp, vp]
+    lib.rp_poa_window_status.restype = C.c_int32
+    lib.rp_poa_window_status.argtypes = [vp, u32, vp]
+    lib.rp_poa_fetch_all.restype = C.c_int32
+    lib.rp_poa_fetch_all.argtypes = [vp, vp, u32, vp, vp, vp]
+    lib.rp_poa_set_stream.restype = C.c_int32
+    lib.rp_poa_set_stream.argtypes = [vp, vp]
+    lib.rp_poa_info.restype = C.c_int32
+    lib.rp_poa_info.argtypes = [vp, vp]
+    lib.rp_poa_enable_counters.restype = C.c_int32
+    lib.rp_poa_enable_counters.argtypes = [vp, C.c_int]
+    if hasattr(lib, "rp_mirror_consensus"):
+        lib.rp_mirror_consensus.restype = C.c_double
+        lib.rp_mirror_consensus.argtypes = [u32] + [vp] * 8 + [C.c_int8, C.c_int8, C.c_int8, u32, C.c_int, u32, vp,
+                                                               u32, vp, vp]
+    _lib = lib
+    return lib
+
+
+def _check(lib, st, what):
+    if st < 0:
+        raise RaconB200Error("%s: %s (%s)" % (what, lib.rp_strerror(st).decode(), lib.rp_last_error().decode()))
+    return st
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class PoaBatch:
+    """racon::CUDABatchProcessor-shaped batch object (add windows -> run -> fetch)."""
+
+    def __init__(self, device=0, mem_bytes=0, match=3, mismatch=-5, gap=-4, banded=False, window_length=500,
+                 max_depth=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.rp_poa_create(C.byref(self.h), device, mem_bytes, match, mismatch, gap,
+                                                1 if banded else 0, window_length, max_depth), "rp_poa_create")
+
+    def close(self):
+        if self.h:
+            self.lib.rp_poa_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_window_set(self, ws, first=0, count=None, trim=True):
+        """Adds windows [first, first+count) of a WindowSet; returns how many fit."""
+        if count is None:
+            count = ws.n_windows - first
+        added = C.c_uint32(0)
+        st = self.lib.rp_poa_add_window_set(self.h, first, count, _ptr(ws.bases), _ptr(ws.quals), _ptr(ws.seq_off),
+                                            _ptr(ws.seq_has_qual), _ptr(ws.seq_begin), _ptr(ws.seq_end),
+                                            _ptr(ws.win_first), _ptr(ws.win_type), 1 if trim else 0, C.byref(added))
+        _check(self.lib, st, "rp_poa_add_window_set")
+        return added.value
+
+    def add_window(self, seqs, window_type=1, trim=True):
+        """seqs: [(bases, quals|None, begin, end), ...], backbone first.  Returns RP_OK or RP_BATCH_FULL."""
+        n = len(seqs)
+        keep = []
+        sp = (C.c_char_p * n)()
+        qp = (C.c_char_p * n)()
+        ln = (C.c_uint32 * n)()
+        bg = (C.c_uint32 * n)()
+        en = (C.c_uint32 * n)()
+        for i, (b, q, s, e) in enumerate(seqs):
+            keep.append((b, q))
+            sp[i] = b
+            qp[i] = q
+            ln[i] = len(b)
+            bg[i] = s
+            en[i] = e
+        st = self.lib.rp_poa_add_window(self.h, n, sp, ln, qp, bg, en, window_type, 1 if trim else 0)
+        return _check(self.lib, st, "rp_poa_add_window")
+
+    def size(self):
+        return self.lib.rp_poa_size(self.h)
+
+    def set_stream(self, cuda_stream):
+        _check(self.lib, self.lib.rp_poa_set_stream(self.h, C.c_void_p(cuda_stream)), "rp_poa_set_stream")
+
+    def upload(self):
+        _check(self.lib, self.lib.rp_poa_upload(self.h), "rp_poa_upload")
+
+    def launch(self):
+        _check(self.lib, self.lib.rp_poa_launch(self.h), "rp_poa_launch")
+
+    def download(self):
+        _check(self.lib, self.lib.rp_poa_download(self.h), "rp_poa_download")
+
+    def run(self):
+        _check(self.lib, self.lib.rp_poa_run(self.h), "rp_poa_run")
+
+    def sync(self):
+        _check(self.lib, self.lib.rp_poa_sync(self.h), "rp_poa_sync")
+
+    def reset(self):
+        _check(self.lib, self.lib.rp_poa_reset(self.h), "rp_poa_reset")
+
+    def enable_counters(self, on=True):
+        _check(self.lib, self.lib.rp_poa_enable_counters(self.h, 1 if on else 0), "rp_poa_enable_counters")
+
+    def info(self):
+        a = (C.c_uint64 * 8)()
+        _check(self.lib, self.lib.rp_poa_info(self.h, a), "rp_poa_info")
+        keys = ["launches", "h2d_bytes", "d2h_bytes", "workers", "scratch_bytes_per_worker", "alignments",
+                "dp_cells", "pred_cells"]
+        return dict(zip(keys, [int(v) for v in a]))
+
+    def fetch_all(self, stride):
+        n = self.size()
+        out = np.zeros((n, stride), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.uint32)
+        pol = np.zeros(n, dtype=np.uint8)
+        st = np.zeros(n, dtype=np.uint32)
+        _check(self.lib, self.lib.rp_poa_fetch_all(self.h, out.ctypes.data, stride, lens.ctypes.data,
+                                                   pol.ctypes.data, st.ctypes.data), "rp_poa_fetch_all")
+        return out, lens, pol.astype(bool), st
+
+    def fetch(self, i):
+        c = C.c_char_p()
+        l = C.c_uint32()
+        cov = C.POINTER(C.c_uint16)()
+        pol = C.c_int()
+        _check(self.lib, self.lib.rp_poa_fetch(self.h, i, C.byref(c), C.byref(l), C.byref(cov), C.byref(pol)),
+               "rp_poa_fetch")
+        cons = C.string_at(c, l.value) if l.value else b""
+        coverage = np.ctypeslib.as_array(cov, shape=(l.value,)).copy() if (l.value and cov) else np.zeros(0, np.uint16)
+        return cons, coverage, bool(pol.value)
+
+
+def consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=500, device=0, want_coverage=False,
+              mem_bytes=0):
+    """Convenience: whole WindowSet through PoaBatch (multiple batches if needed).
+    Returns (consensus list, polished bool array, status uint32 array[, coverages])."""
+    batch = PoaBatch(device=device, mem_bytes=mem_bytes, match=match, mismatch=mismatch, gap=gap,
+                     window_length=window_length)
+    n = ws.n_windows
+    lens_in = np.diff(ws.seq_off.astype(np.int64))
+    stride = int(2 * (lens_in.max() if len(lens_in) else 1) + 64)
+    cons, pol, st, covs = [], [], [], []
+    first = 0
+    try:
+        while first < n:
+            batch.reset()
+            took = batch.add_window_set(ws, first, n - first, trim=trim)
+            if took == 0:
+                raise RaconB200Error("window %d does not fit an empty batch" % first)
+            batch.run()
+            batch.sync()
+            out, lens, p, s = batch.fetch_all(stride)
+            for i in range(took):
+                cons.append(out[i, :lens[i]].tobytes())
+                if want_coverage:
+                    covs.append(batch.fetch(i)[1])
+            pol.append(p)
+            st.append(s)
+            first += took
+    finally:
+        batch.close()
+    pol = np.concatenate(pol) if pol else np.zeros(0, bool)
+    st = np.concatenate(st) if st else np.zeros(0, np.uint32)
+    if want_coverage:
+        return cons, pol, st, covs
+    return cons, pol, st
+
+
+def mirror_consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=500, device=0):
+    """Drives the C++ host mirror (createWindow/add_layer/BatchProcessor) through its test hook."""
+    lib = load()
+    n = ws.n_windows
+    lens_in = np.diff(ws.seq_off.astype(np.int64))
+    stride = int(2 * (lens_in.max() if len(lens_in) else 1) + 64)
+    out = np.zeros((n, stride), dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.uint32)
+    pol = np.zeros(n, dtype=np.uint8)
+    r = lib.rp_mirror_consensus(n, _ptr(ws.bases), _ptr(ws.quals), _ptr(ws.seq_off), _ptr(ws.seq_has_qual),
+                                _ptr(ws.seq_begin), _ptr(ws.seq_end), _ptr(ws.win_first), _ptr(ws.win_type), match,
+                                mismatch, gap, window_length, 1 if trim else 0, device, out.ctypes.data, stride,
+                                lens.ctypes.data, pol.ctypes.data)
+    if r < 0:
+        raise RaconB200Error("rp_mirror_consensus failed (%r)" % r)
+    return [out[w, :lens[w]].tobytes() for w in range(n)], pol.astype(bool)

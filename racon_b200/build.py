@@ -2,7 +2,8 @@
 
   libracon_b200.so  — the product: C-ABI (include/racon_b200.h) + sm_100a CUDA kernels + C++ host mirror
   libracon_synth.so — synthetic window generator (bench/test input maker, no CUDA)
-  oracle/_build/libpoa_oracle.so, oracle/_ref/libracon_ref.so — test infrastructure (see oracle/Makefile)
+  libracon_sim.so   — TEST-ONLY host simulation of the device code (tests/ only)
+The checkers (restated CPU model and the compiled reference) have their own recipe outside this package.
 """
 import os
 import shutil
@@ -11,7 +12,6 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "racon_b200", "csrc")
 LIBDIR = os.path.join(ROOT, "racon_b200", "lib")
-ORACLE = os.path.join(ROOT, "oracle")
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -88,25 +88,6 @@ def build_sim(force=False):
     return out
 
 
-def build_oracle(force=False):
-    out = os.path.join(ORACLE, "_build", "libpoa_oracle.so")
-    srcs = [os.path.join(ORACLE, f) for f in ("poa_oracle.cpp", "myers_oracle.cpp")]
-    if force or _newer(out, srcs):
-        _run(["make", "-C", ORACLE, "oracle"])
-    return out
-
-
-def build_ref(force=False):
-    """oracle/_ref: the unmodified reference compiled from /root/reference (only where it exists)."""
-    out = os.path.join(ORACLE, "_ref", "libracon_ref.so")
-    srcs = [os.path.join(ORACLE, f) for f in ("ref_harness.cpp", "ref_edlib_harness.cpp")]
-    if os.path.isdir("/root/reference/src") and (force or _newer(out, srcs)):
-        _run(["make", "-C", ORACLE, "ref"])
-    return out if os.path.exists(out) else None
-
-
 def build_all(force=False):
     build_synth(force)
     build_cuda(force)
-    build_oracle(force)
-    build_ref(force)

@@ -344,9 +344,10 @@ struct PoaWarp {
     /* ---------------------------------------------------------------- DP program (one 8-byte record per row)
      * byte0 code index, byte1 = npred(7 bits) | sink<<7, bytes2..7 = first three predecessor DP ranks
      * (0 = virtual root row).  Further predecessors spill to pred_ovf. */
-    RP_DEV void build_program(uint32_t nrows, bool sub) {
+    RP_DEV uint32_t build_program(uint32_t nrows, bool sub) {
         const uint16_t* ord = sub ? dp_order : order;
         const uint16_t* rk = sub ? dp_rank : rank_of;
+        uint32_t pred_rows = 0;
         for (uint32_t r = 1 + lane; r <= nrows; r += 32) {
             uint32_t v = ord[r];
             uint32_t ni = in_cnt[v];
@@ -366,9 +367,11 @@ struct PoaWarp {
             uint64_t rc = static_cast<uint64_t>(code_index(code[v])) | (static_cast<uint64_t>(np & 0x7f) << 8) |
                           (static_cast<uint64_t>(sink ? 1 : 0) << 15) | (preds << 16);
             rec[r] = rc;
+            pred_rows += np ? np : 1;
         }
         if (lane == 0) rec[0] = 0;
         syncwarp();
+        return pred_rows;  // per-lane partial sum (only summed when the device counters are on)
     }
 
     /* ---------------------------------------------------------------- profile (sisd :123-131) */
@@ -1059,7 +1062,7 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         }
         W.prof = reinterpret_cast<int16_t*>(smem);
         W.ring = reinterpret_cast<int16_t*>(smem + prof_bytes);
-        W.build_program(nrows, sub);
+        uint32_t pred_rows = W.build_program(nrows, sub);
         W.build_profile(seq, len, lpa);
         uint32_t best_row, n_best;
         int32_t best;
@@ -1070,14 +1073,19 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         }
         W.traceback(best_row, len, lpa, seq, sub);
         W.add_alignment(seq, wts, len);
+        if (P.stats) pred_rows = warp_incl_sum(pred_rows);
+        if (P.stats) pred_rows = shfl(pred_rows, 31);
         if (P.stats && lane == 0) {
 #if !defined(RP_HOST_SIM)
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 3),
+                      static_cast<unsigned long long>(pred_rows) * (len + 1));
             atomicAdd(reinterpret_cast<unsigned long long*>(P.stats), 1ull);
             atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 1),
                       static_cast<unsigned long long>(nrows + 1) * (len + 1));
             if (n_best > 1) atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 2), 1ull);
 #else
             P.stats[0] += 1;
+            P.stats[3] += static_cast<uint64_t>(pred_rows) * (len + 1);
             P.stats[1] += static_cast<uint64_t>(nrows + 1) * (len + 1);
             if (n_best > 1) P.stats[2] += 1;
 #endif

@@ -1,0 +1,490 @@
+/*
+ * rp_api.cu — the C ABI (include/racon_b200.h) over the sm_100a kernels.  Product library
+ * libracon_b200.so = this file + host_mirror.cpp.  There is no CPU implementation behind these calls.
+ *
+ * POA batch object = racon::CUDABatchProcessor + cudapoa::Batch (src/cuda/cudabatch.cpp:23-278):
+ *   add (copy into pinned staging) -> upload (H2D) -> launch (one persistent kernel) -> download (D2H).
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "poa_core.cuh"
+#include "poa_pack.hpp"
+#include "racon_b200.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+rp_status fail(rp_status s, const std::string& msg) {
+    g_last_error = msg;
+    return s;
+}
+
+#define RP_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(RP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+void* pinned_alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void pinned_free(void* p) { cudaFreeHost(p); }
+const rp::HostAllocator kPinned{pinned_alloc, pinned_free};
+
+/* growable device buffer */
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t nc = cap ? cap : 4096;
+        while (nc < n) nc *= 2;
+        cudaError_t e = cudaMalloc(&p, nc);
+        cap = e == cudaSuccess ? nc : 0;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kBlocksPerSm = 4;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kernel(rp::PoaParams P) {
+    extern __shared__ __align__(16) uint8_t smem_all[];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + warp;
+    uint8_t* slot = P.scratch + static_cast<uint64_t>(worker) * P.lay.bytes;
+    uint8_t* smem = smem_all + static_cast<uint32_t>(warp) * P.smem_per_warp;
+    for (;;) {
+        uint32_t q = 0;
+        if ((threadIdx.x & 31) == 0) q = atomicAdd(P.queue_head, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= P.n_windows) break;
+        rp::poa_window(P, P.queue[q], slot, smem);
+    }
+}
+
+}  // namespace
+
+struct rp_poa {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    rp::PackedBatch batch;
+    rp::PoaParams P;
+    /* device input buffers */
+    DevBuf d_bases, d_weights, d_seq_flags, d_win_flags, d_seq_off, d_seq_begin, d_seq_end, d_win_first, d_out_off,
+        d_out_cap, d_queue, d_win_alpha, d_cons, d_cov, d_len, d_status, d_head, d_stats, d_scratch;
+    /* pinned results */
+    rp::GrowBuf<uint8_t> h_cons;
+    rp::GrowBuf<uint16_t> h_cov;
+    rp::GrowBuf<uint32_t> h_len, h_status;
+    uint64_t h_stats[8] = {0};
+    uint32_t workers = 0;
+    int grid = 0;
+    uint32_t smem_block = 0;
+    bool uploaded = false, launched = false, downloaded = false, synced = false;
+    bool counters = false;
+    uint64_t launches = 0, last_h2d = 0, last_d2h = 0;
+    int banded = 0;
+
+    rp_poa() : batch(&kPinned), h_cons(&kPinned), h_cov(&kPinned), h_len(&kPinned), h_status(&kPinned) {
+        std::memset(&P, 0, sizeof(P));
+    }
+};
+
+extern "C" {
+
+const char* rp_strerror(rp_status s) {
+    switch (s) {
+        case RP_OK: return "ok";
+        case RP_BATCH_FULL: return "batch full";
+        case RP_ERR_INVALID: return "invalid argument or malformed window";
+        case RP_ERR_CUDA: return "CUDA error";
+        case RP_ERR_NOMEM: return "out of memory";
+        case RP_ERR_STATE: return "call order violated";
+        case RP_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        default: return "unknown status";
+    }
+}
+
+const char* rp_last_error(void) { return g_last_error.c_str(); }
+
+const char* rp_version(void) { return "racon_b200 0.1 (sm_100a)"; }
+
+int rp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match, int8_t mismatch, int8_t gap,
+                        int banded, uint32_t window_len_hint, uint32_t max_depth_hint) {
+    (void)max_depth_hint;
+    if (!out) return fail(RP_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (gap > 0) return fail(RP_ERR_INVALID, "gap penalty must be non-positive (alignment_engine.cpp:47-51)");
+    int ndev = rp_device_count();
+    if (ndev <= 0) return fail(RP_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RP_ERR_INVALID, "device index out of range");
+    RP_CUDA(cudaSetDevice(device));
+    rp_poa* p = new (std::nothrow) rp_poa();
+    if (!p) return fail(RP_ERR_NOMEM, "host allocation failed");
+    p->device = device;
+    p->banded = banded;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(RP_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (mem_bytes == 0 || mem_bytes > free_b) mem_bytes = static_cast<size_t>(free_b * 0.8);
+
+    const uint32_t wl = window_len_hint ? window_len_hint : 500;
+    rp::PoaLimits lim;
+    lim.nmax = std::min<uint32_t>(65000, std::max<uint32_t>(1024, 6 * wl + 64));
+    lim.lmax = std::min<uint32_t>(16000, 2 * wl + 23);
+    lim.lp = (lim.lmax + 1 + rp::kChunkCols - 1) / rp::kChunkCols * rp::kChunkCols;
+    lim.ki = 16;
+    lim.ka = 8;
+    lim.stack_cap = lim.nmax * 4 + 64;
+    p->P.lim = lim;
+    p->P.lay = rp::make_layout(lim);
+    p->P.match = match;
+    p->P.mismatch = mismatch;
+    p->P.gap = gap;
+
+    /* launch shape: persistent blocks of 4 independent warps, 4 blocks per SM (16 windows in flight per SM) */
+    uint32_t smem_per_sm = static_cast<uint32_t>(prop.sharedMemPerMultiprocessor);
+    uint32_t per_block = smem_per_sm / kBlocksPerSm - 1024;                     // 1 KB reserved per block
+    if (per_block > prop.sharedMemPerBlockOptin) per_block = static_cast<uint32_t>(prop.sharedMemPerBlockOptin);
+    uint32_t per_warp = (per_block / kWarpsPerBlock) & ~1023u;
+    p->P.smem_per_warp = per_warp;
+    p->smem_block = per_warp * kWarpsPerBlock;
+    e = cudaFuncSetAttribute(rp_poa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_block));
+    int occ = 0;
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp_poa_kernel, kWarpsPerBlock * 32, p->smem_block);
+    if (e != cudaSuccess || occ < 1) {
+        rp_poa_destroy(p);
+        return fail(RP_ERR_CUDA, std::string("kernel configuration: ") + cudaGetErrorString(e));
+    }
+    uint64_t max_workers = static_cast<uint64_t>(prop.multiProcessorCount) * occ * kWarpsPerBlock;
+    uint64_t scratch_budget = mem_bytes / 2;
+    uint64_t fit = scratch_budget / p->P.lay.bytes;
+    if (fit < kWarpsPerBlock) {
+        rp_poa_destroy(p);
+        return fail(RP_ERR_NOMEM, "memory budget too small for one block of POA workers");
+    }
+    uint64_t workers = std::min(max_workers, fit) / kWarpsPerBlock * kWarpsPerBlock;
+    p->workers = static_cast<uint32_t>(workers);
+    p->grid = static_cast<int>(workers / kWarpsPerBlock);
+    e = p->d_scratch.reserve(workers * p->P.lay.bytes);
+    if (e == cudaSuccess) e = p->d_head.reserve(256);
+    if (e == cudaSuccess) e = p->d_stats.reserve(256);
+    if (e != cudaSuccess) {
+        rp_poa_destroy(p);
+        return fail(RP_ERR_NOMEM, std::string("scratch allocation: ") + cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(p->d_stats.p, 0, 256, p->stream);
+    p->batch.max_seq_len = lim.lmax > lim.nmax ? lim.nmax : 65000;
+    *out = p;
+    return RP_OK;
+}
+
+void rp_poa_destroy(rp_poa* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    DevBuf* bufs[] = {&p->d_bases, &p->d_weights, &p->d_seq_flags, &p->d_win_flags, &p->d_seq_off, &p->d_seq_begin,
+                      &p->d_seq_end, &p->d_win_first, &p->d_out_off, &p->d_out_cap, &p->d_queue, &p->d_win_alpha,
+                      &p->d_cons, &p->d_cov, &p->d_len, &p->d_status, &p->d_head, &p->d_stats, &p->d_scratch};
+    for (DevBuf* b : bufs) b->release();
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+rp_status rp_poa_set_stream(rp_poa* p, void* cuda_stream) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    if (p->own_stream && p->stream) {
+        cudaStreamSynchronize(p->stream);
+        cudaStreamDestroy(p->stream);
+    }
+    p->stream = static_cast<cudaStream_t>(cuda_stream);
+    p->own_stream = false;
+    return RP_OK;
+}
+
+static rp_status map_pack(int r) {
+    switch (r) {
+        case rp::kPackOk: return RP_OK;
+        case rp::kPackFull: return RP_BATCH_FULL;
+        case rp::kPackNoMem: return fail(RP_ERR_NOMEM, "pinned staging allocation failed");
+        default: return fail(RP_ERR_INVALID, "malformed window (see Window::add_layer checks, window.cpp:42-63)");
+    }
+}
+
+rp_status rp_poa_add_window(rp_poa* p, uint32_t n_seq, const char* const* seq, const uint32_t* len,
+                            const char* const* qual, const uint32_t* begin, const uint32_t* end, int window_type,
+                            int trim) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    if (p->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
+    return map_pack(p->batch.add(n_seq, seq, len, qual, begin, end, window_type, trim));
+}
+
+rp_status rp_poa_add_window_set(rp_poa* p, uint32_t first, uint32_t count, const char* bases, const char* quals,
+                                const uint64_t* seq_off, const uint8_t* seq_has_qual, const uint32_t* seq_begin,
+                                const uint32_t* seq_end, const uint32_t* win_first, const uint8_t* win_type, int trim,
+                                uint32_t* added) {
+    if (!p || !bases || !seq_off || !win_first || !seq_begin || !seq_end)
+        return fail(RP_ERR_INVALID, "null argument");
+    if (p->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
+    std::vector<const char*> sp, qp;
+    std::vector<uint32_t> ln;
+    uint32_t n = 0;
+    rp_status st = RP_OK;
+    for (uint32_t w = first; w < first + count; ++w) {
+        uint32_t s0 = win_first[w], s1 = win_first[w + 1];
+        sp.clear();
+        qp.clear();
+        ln.clear();
+        for (uint32_t s = s0; s < s1; ++s) {
+            sp.push_back(bases + seq_off[s]);
+            bool q = quals && seq_has_qual && seq_has_qual[s];
+            qp.push_back(q ? quals + seq_off[s] : nullptr);
+            ln.push_back(static_cast<uint32_t>(seq_off[s + 1] - seq_off[s]));
+        }
+        st = map_pack(p->batch.add(s1 - s0, sp.data(), ln.data(), qp.data(), seq_begin + s0, seq_end + s0,
+                                   win_type ? win_type[w] : 1, trim));
+        if (st != RP_OK) break;
+        ++n;
+    }
+    if (added) *added = n;
+    return st == RP_BATCH_FULL && n > 0 ? RP_OK : st;
+}
+
+uint32_t rp_poa_size(const rp_poa* p) { return p ? p->batch.n_added() : 0; }
+
+rp_status rp_poa_upload(rp_poa* p) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    RP_CUDA(cudaSetDevice(p->device));
+    rp::PackedBatch& b = p->batch;
+    if (!b.build_queue()) return fail(RP_ERR_NOMEM, "queue allocation failed");
+    const uint32_t n = b.n_gpu();
+    uint64_t h2d = 0;
+    auto up = [&](DevBuf& d, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = d.reserve(bytes ? bytes : 16);
+        if (e != cudaSuccess) return e;
+        h2d += bytes;
+        return bytes ? cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, p->stream) : cudaSuccess;
+    };
+    RP_CUDA(up(p->d_bases, b.bases.data, b.bases.bytes()));
+    RP_CUDA(up(p->d_weights, b.weights.data, b.weights.bytes()));
+    RP_CUDA(up(p->d_seq_off, b.seq_off.data, b.seq_off.bytes()));
+    RP_CUDA(up(p->d_seq_begin, b.seq_begin.data, b.seq_begin.bytes()));
+    RP_CUDA(up(p->d_seq_end, b.seq_end.data, b.seq_end.bytes()));
+    RP_CUDA(up(p->d_seq_flags, b.seq_flags.data, b.seq_flags.bytes()));
+    RP_CUDA(up(p->d_win_first, b.win_first.data, b.win_first.bytes()));
+    RP_CUDA(up(p->d_win_flags, b.win_flags.data, b.win_flags.bytes()));
+    RP_CUDA(up(p->d_win_alpha, b.win_alpha.data, b.win_alpha.bytes()));
+    RP_CUDA(up(p->d_out_off, b.out_off.data, b.out_off.bytes()));
+    RP_CUDA(up(p->d_out_cap, b.out_cap.data, b.out_cap.bytes()));
+    RP_CUDA(up(p->d_queue, b.queue.data, b.queue.bytes()));
+    RP_CUDA(p->d_cons.reserve(b.out_total + 16));
+    RP_CUDA(p->d_cov.reserve((b.out_total + 16) * 2));
+    RP_CUDA(p->d_len.reserve((n + 1) * 4));
+    RP_CUDA(p->d_status.reserve((n + 1) * 4));
+    if (!p->h_cons.reserve(b.out_total + 16) || !p->h_cov.reserve(b.out_total + 16) || !p->h_len.reserve(n + 1) ||
+        !p->h_status.reserve(n + 1))
+        return fail(RP_ERR_NOMEM, "pinned result allocation failed");
+    rp::PoaParams& P = p->P;
+    P.n_windows = n;
+    P.bases = static_cast<const uint8_t*>(p->d_bases.p);
+    P.weights = static_cast<const uint8_t*>(p->d_weights.p);
+    P.seq_off = static_cast<const uint32_t*>(p->d_seq_off.p);
+    P.seq_begin = static_cast<const uint32_t*>(p->d_seq_begin.p);
+    P.seq_end = static_cast<const uint32_t*>(p->d_seq_end.p);
+    P.seq_flags = static_cast<const uint8_t*>(p->d_seq_flags.p);
+    P.win_first = static_cast<const uint32_t*>(p->d_win_first.p);
+    P.win_flags = static_cast<const uint8_t*>(p->d_win_flags.p);
+    P.win_alpha = static_cast<const uint64_t*>(p->d_win_alpha.p);
+    P.queue = static_cast<const uint32_t*>(p->d_queue.p);
+    P.queue_head = static_cast<uint32_t*>(p->d_head.p);
+    P.cons = static_cast<uint8_t*>(p->d_cons.p);
+    P.cons_cov = static_cast<uint16_t*>(p->d_cov.p);
+    P.out_off = static_cast<const uint32_t*>(p->d_out_off.p);
+    P.out_cap = static_cast<const uint32_t*>(p->d_out_cap.p);
+    P.cons_len = static_cast<uint32_t*>(p->d_len.p);
+    P.status = static_cast<uint32_t*>(p->d_status.p);
+    P.stats = p->counters ? static_cast<uint64_t*>(p->d_stats.p) : nullptr;
+    P.scratch = static_cast<uint8_t*>(p->d_scratch.p);
+    p->last_h2d = h2d;
+    p->uploaded = true;
+    p->launched = p->downloaded = p->synced = false;
+    return RP_OK;
+}
+
+rp_status rp_poa_launch(rp_poa* p) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    if (!p->uploaded) return fail(RP_ERR_STATE, "launch before upload");
+    RP_CUDA(cudaSetDevice(p->device));
+    if (p->P.n_windows > 0) {
+        RP_CUDA(cudaMemsetAsync(p->d_head.p, 0, 4, p->stream));
+        p->P.stats = p->counters ? static_cast<uint64_t*>(p->d_stats.p) : nullptr;
+        rp_poa_kernel<<<p->grid, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(p->P);
+        RP_CUDA(cudaGetLastError());
+        p->launches += 1;
+    }
+    p->launched = true;
+    p->downloaded = p->synced = false;
+    return RP_OK;
+}
+
+rp_status rp_poa_download(rp_poa* p) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    if (!p->launched) return fail(RP_ERR_STATE, "download before launch");
+    RP_CUDA(cudaSetDevice(p->device));
+    const uint32_t n = p->P.n_windows;
+    uint64_t d2h = 0;
+    if (n > 0) {
+        size_t tot = p->batch.out_total;
+        RP_CUDA(cudaMemcpyAsync(p->h_cons.data, p->d_cons.p, tot, cudaMemcpyDeviceToHost, p->stream));
+        RP_CUDA(cudaMemcpyAsync(p->h_cov.data, p->d_cov.p, tot * 2, cudaMemcpyDeviceToHost, p->stream));
+        RP_CUDA(cudaMemcpyAsync(p->h_len.data, p->d_len.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+        RP_CUDA(cudaMemcpyAsync(p->h_status.data, p->d_status.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+        d2h = tot * 3 + static_cast<uint64_t>(n) * 8;
+    }
+    if (p->counters)
+        RP_CUDA(cudaMemcpyAsync(p->h_stats, p->d_stats.p, 64, cudaMemcpyDeviceToHost, p->stream));
+    p->last_d2h = d2h;
+    p->downloaded = true;
+    p->synced = false;
+    return RP_OK;
+}
+
+rp_status rp_poa_run(rp_poa* p) {
+    rp_status s = rp_poa_upload(p);
+    if (s != RP_OK) return s;
+    s = rp_poa_launch(p);
+    if (s != RP_OK) return s;
+    return rp_poa_download(p);
+}
+
+rp_status rp_poa_sync(rp_poa* p) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    RP_CUDA(cudaSetDevice(p->device));
+    RP_CUDA(cudaStreamSynchronize(p->stream));
+    if (p->downloaded) p->synced = true;
+    return RP_OK;
+}
+
+static rp_status ensure_results(rp_poa* p) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    if (!p->downloaded) return fail(RP_ERR_STATE, "fetch before run/download");
+    if (!p->synced) return rp_poa_sync(p);
+    return RP_OK;
+}
+
+rp_status rp_poa_fetch(rp_poa* p, uint32_t i, const char** consensus, uint32_t* len, const uint16_t** coverage,
+                       int* polished) {
+    rp_status s = ensure_results(p);
+    if (s != RP_OK) return s;
+    if (i >= p->batch.n_added()) return fail(RP_ERR_INVALID, "window index out of range");
+    int32_t gi = p->batch.gpu_index[i];
+    if (gi < 0) {
+        const std::string& c = p->batch.trivial[i];
+        if (consensus) *consensus = c.data();
+        if (len) *len = static_cast<uint32_t>(c.size());
+        if (coverage) *coverage = nullptr;
+        if (polished) *polished = 0;
+        return RP_OK;
+    }
+    uint32_t off = p->batch.out_off.data[gi];
+    bool ok = p->h_status.data[gi] == rp::kWinOk;
+    if (consensus) *consensus = reinterpret_cast<const char*>(p->h_cons.data + off);
+    if (len) *len = ok ? p->h_len.data[gi] : 0;
+    if (coverage) *coverage = p->h_cov.data + off;
+    if (polished) *polished = ok ? 1 : 0;
+    return RP_OK;
+}
+
+rp_status rp_poa_window_status(rp_poa* p, uint32_t i, uint32_t* status) {
+    rp_status s = ensure_results(p);
+    if (s != RP_OK) return s;
+    if (i >= p->batch.n_added() || !status) return fail(RP_ERR_INVALID, "window index out of range");
+    int32_t gi = p->batch.gpu_index[i];
+    *status = gi == -1 ? RP_WIN_OK : (gi == -2 ? RP_WIN_ALPHABET_LIMIT : p->h_status.data[gi]);
+    return RP_OK;
+}
+
+rp_status rp_poa_fetch_all(rp_poa* p, char* out, uint32_t stride, uint32_t* lens, uint8_t* polished,
+                           uint32_t* status) {
+    rp_status s = ensure_results(p);
+    if (s != RP_OK) return s;
+    const uint32_t n = p->batch.n_added();
+    for (uint32_t i = 0; i < n; ++i) {
+        const char* c = nullptr;
+        uint32_t l = 0;
+        int pol = 0;
+        uint32_t st = 0;
+        rp_poa_fetch(p, i, &c, &l, nullptr, &pol);
+        rp_poa_window_status(p, i, &st);
+        if (out) {
+            if (l > stride) return fail(RP_ERR_INVALID, "stride too small for a consensus");
+            std::memcpy(out + static_cast<uint64_t>(i) * stride, c, l);
+        }
+        if (lens) lens[i] = l;
+        if (polished) polished[i] = static_cast<uint8_t>(pol);
+        if (status) status[i] = st;
+    }
+    return RP_OK;
+}
+
+rp_status rp_poa_reset(rp_poa* p) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    cudaSetDevice(p->device);
+    if (p->stream) RP_CUDA(cudaStreamSynchronize(p->stream));
+    p->batch.reset();
+    p->uploaded = p->launched = p->downloaded = p->synced = false;
+    return RP_OK;
+}
+
+rp_status rp_poa_info(rp_poa* p, uint64_t info[8]) {
+    if (!p || !info) return fail(RP_ERR_INVALID, "null argument");
+    info[0] = p->launches;
+    info[1] = p->last_h2d;
+    info[2] = p->last_d2h;
+    info[3] = p->workers;
+    info[4] = p->P.lay.bytes;
+    info[5] = p->h_stats[0];
+    info[6] = p->h_stats[1];
+    info[7] = p->h_stats[3];
+    return RP_OK;
+}
+
+rp_status rp_poa_enable_counters(rp_poa* p, int on) {
+    if (!p) return fail(RP_ERR_INVALID, "null object");
+    p->counters = on != 0;
+    return RP_OK;
+}
+
+}  // extern "C"

@@ -11,8 +11,8 @@
  * The reference consumes such windows through racon::createWindow / Window::add_layer
  * (/root/reference/src/window.cpp:15-63).
  *
- * This file has no dependency on CUDA or on oracle/.  It is used by bench.py and tests/ to
- * build the flat "window set" arrays that every consumer (C-ABI, oracle, oracle/_ref) reads.
+ * This file has no dependency on CUDA or on the checkers.  It is used by bench.py and tests/ to
+ * build the flat "window set" arrays that every consumer (the C ABI and the checkers) reads.
  */
 #include <stdint.h>
 #include <stdlib.h>

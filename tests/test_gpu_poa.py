@@ -1,0 +1,139 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the oracle,
+the committed golden fixtures and the reference's known-answer checksums.  Integer/byte work => bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from racon_b200 import api, windows
+from tests import util
+from tests.test_oracle import KAT
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "fullspan": dict(n=48, wlen=500, depth=32, err=0.12),
+    "partial": dict(n=48, wlen=500, depth=30, err=0.10, partial_frac=0.5),
+    "partial_qual": dict(n=48, wlen=500, depth=24, err=0.12, partial_frac=0.3, with_qual=True, backbone_qual=True),
+    "ngs_short": dict(n=96, wlen=200, depth=40, err=0.01, partial_frac=0.9, with_qual=True, types=0),
+    "acgtn": dict(n=32, wlen=300, depth=20, err=0.15, partial_frac=0.2, alphabet=b"ACGTN"),
+    "shallow": dict(n=64, wlen=120, depth=3, err=0.2, partial_frac=0.3),
+    "higherr": dict(n=32, wlen=300, depth=40, err=0.3),
+    "long_layers": dict(n=8, wlen=700, depth=12, err=0.1, partial_frac=0.2),
+}
+
+
+def _mk(name, seed):
+    kw = dict(CASES[name])
+    n = kw.pop("n")
+    t = kw.pop("types", None)
+    ws = util.make_set(seed, n, **kw)
+    if t is not None:
+        ws.win_type[:] = t
+    return ws
+
+
+def _compare(ws, scores=(3, -5, -4), trim=True, window_length=500):
+    m, x, g = scores
+    cons, pol, st, covs = api.consensus(ws, m, x, g, trim=trim, window_length=window_length, want_coverage=True)
+    ora, opol, _, ocov = ob.oracle_consensus(ws, m, x, g, trim=trim, threads=os.cpu_count() or 4, want_coverage=True)
+    assert (st == 0).all(), "device limit statuses: %s" % np.unique(st)
+    bad = [w for w in range(ws.n_windows) if cons[w] != ora[w]]
+    assert not bad, "consensus differs on windows %s" % bad[:8]
+    assert (pol == opol).all()
+    for w in range(ws.n_windows):
+        if pol[w]:
+            assert (covs[w].astype(np.uint32) == ocov[w]).all(), "coverage differs on window %d" % w
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_equals_oracle(name):
+    _compare(_mk(name, seed=101), window_length=1000 if name == "long_layers" else 500)
+
+
+@pytest.mark.parametrize("scores", [(5, -4, -8), (1, -1, -1)])
+def test_gpu_equals_oracle_other_scores(scores):
+    _compare(_mk("partial_qual", seed=55), scores=scores)
+    _compare(_mk("higherr", seed=56), scores=scores)
+
+
+def test_gpu_no_trim_and_trivial_windows():
+    _compare(_mk("partial", seed=9), trim=False)
+    tiny = windows.from_lists([[(b"ACGTACGT", None, 0, 0), (b"ACGTTCGT", None, 0, 7)], [(b"AC", None, 0, 0)]])
+    cons, pol, st = api.consensus(tiny)
+    assert cons == [b"ACGTACGT", b"AC"] and not pol.any() and (st == 0).all()
+
+
+@pytest.mark.parametrize("err,n,expect", KAT)
+def test_gpu_known_answer_checksums_of_the_reference(err, n, expect):
+    """FNV-1a-64 over the consensus of the SURVEY.md §8(d) synthetic windows, as produced by the reference."""
+    ws, _ = windows.synth_windows(n, err=err)
+    cons, pol, st = api.consensus(ws)
+    assert (st == 0).all() and pol.all()
+    assert "%016x" % windows.fnv1a64(cons) == expect
+
+
+def test_gpu_matches_golden_fixtures():
+    path = os.path.join(os.path.dirname(__file__), "golden", "poa_golden.json")
+    gold = json.load(open(path))
+    for case in gold["cases"]:
+        ws = windows.from_lists([[(s[0].encode(), s[1].encode() if s[1] else None, s[2], s[3]) for s in win]
+                                 for win in case["windows"]], case["types"])
+        m, x, g = case["scores"]
+        cons, pol, st = api.consensus(ws, m, x, g, trim=case["trim"])
+        assert [c.decode() for c in cons] == case["consensus"], case["name"]
+        assert [bool(p) for p in pol] == case["polished"], case["name"]
+
+
+def test_gpu_host_mirror_classes():
+    """createWindow / add_layer / BatchProcessor (the C++ mirror of the reference interface)."""
+    ws = _mk("partial", seed=77)
+    cons, pol = api.mirror_consensus(ws)
+    ora, opol, _ = ob.oracle_consensus(ws, threads=8)
+    assert cons == ora and (pol == opol).all()
+
+
+def test_gpu_full_size_properties():
+    """BASELINE config 2 size (10k windows): determinism, batch-composition independence, and a
+    checksum-of-checksums against the oracle on a strided sample (the oracle is too slow for all 10k)."""
+    n = 10000
+    ws, _ = windows.synth_windows(n, err=0.12)
+    cons, pol, st = api.consensus(ws)
+    assert (st == 0).all() and pol.all()
+    cons2, _, _ = api.consensus(ws)
+    assert cons == cons2, "two runs of the same batch differ"
+    idx = np.arange(0, n, 40)
+    sub = ws.subset(idx)
+    cons_sub, _, _ = api.consensus(sub)
+    assert cons_sub == [cons[i] for i in idx], "result depends on batch composition"
+    ora, _, _ = ob.oracle_consensus(sub, threads=os.cpu_count() or 4)
+    assert windows.fnv1a64(cons_sub) == windows.fnv1a64(ora)
+    lens = np.array([len(c) for c in cons])
+    assert 480 < lens.mean() < 520
+
+
+def test_gpu_batch_object_protocol():
+    """add-until-full / run / fetch / reset, state errors, per-window status."""
+    ws = _mk("shallow", seed=3)
+    b = api.PoaBatch()
+    with pytest.raises(api.RaconB200Error):
+        b.launch()  # launch before upload
+    took = b.add_window_set(ws)
+    assert took == ws.n_windows == b.size()
+    b.run()
+    b.sync()
+    c0, cov0, p0 = b.fetch(0)
+    ora, opol, _ = ob.oracle_consensus(ws)
+    assert c0 == ora[0] and p0 == bool(opol[0])
+    with pytest.raises(api.RaconB200Error):
+        b.add_window_set(ws)  # uploaded batch must be reset first
+    b.reset()
+    assert b.size() == 0
+    assert b.add_window(ws.window(1)) == api.RP_OK
+    b.run()
+    assert b.fetch(0)[0] == ora[1]
+    info = b.info()
+    assert info["launches"] >= 2 and info["workers"] >= 32
+    b.close()
