@@ -35,8 +35,10 @@ namespace rp {
 
 constexpr uint16_t kNone = 0xffffu;
 constexpr int kChunkCols = 512;          // columns per register-resident row chunk (32 lanes x 16)
-constexpr int32_t kNeg16 = -31744;       // INT16_MIN + 1024, the reference's kNegativeInfinity (simd impl :541)
+constexpr int32_t kNegDiag = -32640;     // "column -1" sentinel: + any int8 profile value stays >= INT16_MIN and
+                                         // below every legal score (legal >= INT16_MIN + 1024, the int16 criterion)
 constexpr int32_t kNeg32 = -(1 << 28);
+constexpr int32_t kMaxGapInt16 = 64;     // |gap| bound of the packed-int16 path (sentinel + 16*gap must not wrap)
 
 /* window status codes (soft, per window; mirrored in include/racon_b200.h) */
 enum : uint32_t {
@@ -138,12 +140,20 @@ struct PoaParams {
     PoaLimits lim;
     SlotLayout lay;
     uint32_t smem_per_warp;       // bytes of shared memory owned by each warp
+    uint32_t tile_rows;           // traceback tile height in ranks (0 = default 96)
 };
 
-RP_DEV uint32_t swz(uint32_t e) {  // element index -> swizzled element index (16 B granules, LDS.128 conflict-free)
+/* Row layout.  A lane owns 16 consecutive columns; inside that 32-byte block register r (0..7) packs
+ * column r in its low half and column 8+r in its high half, so the in-row gap recurrence runs as two
+ * packed 8-long chains and the diagonal operand of register r is simply register r-1 of the predecessor.
+ * perm(): logical column -> element index in a row stored in that register order (HBM copy);
+ * swz(): additionally XOR-swizzles 16-byte granules so the two LDS.128 of a lane are bank-conflict free. */
+RP_DEV uint32_t perm(uint32_t c) { return (c & ~15u) | ((c & 7u) << 1) | ((c >> 3) & 1u); }
+RP_DEV uint32_t swz_e(uint32_t e) {
     uint32_t q = e >> 3;
     return ((q ^ ((q >> 3) & 1u)) << 3) | (e & 7u);
 }
+RP_DEV uint32_t swz(uint32_t c) { return swz_e(perm(c)); }
 
 struct Row8 {
     uint32_t r[8];
@@ -348,26 +358,62 @@ struct PoaWarp {
         const uint16_t* ord = sub ? dp_order : order;
         const uint16_t* rk = sub ? dp_rank : rank_of;
         uint32_t pred_rows = 0;
-        for (uint32_t r = 1 + lane; r <= nrows; r += 32) {
-            uint32_t v = ord[r];
-            uint32_t ni = in_cnt[v];
-            uint32_t np = 0;
-            uint64_t preds = 0;
-            for (uint32_t k = 0; k < ni; ++k) {
-                uint32_t t = in_tail[v * ki + k];
-                if (sub && !member[t]) continue;
-                uint32_t pr = rk[t];
-                if (np < 3)
-                    preds |= static_cast<uint64_t>(pr) << (16 * np);
-                else
-                    pred_ovf[r * ki + np] = static_cast<uint16_t>(pr);
-                ++np;
+        /* The graph lives in HBM, so every level of the chain row -> node -> in-edges -> ranks costs a full
+         * memory latency.  Rows are handled kU per lane at a time with all loads of one level issued together. */
+        constexpr int kU = 4;
+        for (uint32_t r0 = 1; r0 <= nrows; r0 += 32 * kU) {
+            uint32_t r[kU], v[kU], ni[kU], cd[kU], fl[kU];
+            uint64_t t4[kU];
+            uint32_t pk[kU][3];
+            bool use[kU][3];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                r[u] = r0 + u * 32 + lane;
+                v[u] = r[u] <= nrows ? ord[r[u]] : ord[1];
             }
-            bool sink = sub ? !has_out_sub[v] : !(flags[v] & 1);
-            uint64_t rc = static_cast<uint64_t>(code_index(code[v])) | (static_cast<uint64_t>(np & 0x7f) << 8) |
-                          (static_cast<uint64_t>(sink ? 1 : 0) << 15) | (preds << 16);
-            rec[r] = rc;
-            pred_rows += np ? np : 1;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                ni[u] = in_cnt[v[u]];
+                cd[u] = code[v[u]];
+                fl[u] = sub ? has_out_sub[v[u]] : (flags[v[u]] & 1u);
+                t4[u] = *reinterpret_cast<const uint64_t*>(in_tail + v[u] * ki);  // first four in-edge tails
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    uint32_t t = static_cast<uint32_t>(t4[u] >> (16 * k)) & 0xffffu;
+                    use[u][k] = static_cast<uint32_t>(k) < ni[u] && (!sub || member[t]);
+                    pk[u][k] = t;
+                }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pk[u][k] = use[u][k] ? rk[pk[u][k]] : 0u;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (r[u] > nrows) continue;
+                uint32_t np = 0;
+                uint64_t preds = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (use[u][k]) preds |= static_cast<uint64_t>(pk[u][k]) << (16 * np++);
+                for (uint32_t k = 3; k < ni[u]; ++k) {  // rare: in-degree > 3
+                    uint32_t t = in_tail[v[u] * ki + k];
+                    if (sub && !member[t]) continue;
+                    uint32_t pr = rk[t];
+                    if (np < 3)
+                        preds |= static_cast<uint64_t>(pr) << (16 * np);
+                    else
+                        pred_ovf[r[u] * ki + np] = static_cast<uint16_t>(pr);
+                    ++np;
+                }
+                bool sink = !fl[u];
+                rec[r[u]] = static_cast<uint64_t>(code_index(static_cast<uint8_t>(cd[u]))) |
+                            (static_cast<uint64_t>(np & 0x7f) << 8) | (static_cast<uint64_t>(sink ? 1 : 0) << 15) |
+                            (preds << 16);
+                pred_rows += np ? np : 1;
+            }
         }
         if (lane == 0) rec[0] = 0;
         syncwarp();
@@ -398,12 +444,21 @@ struct PoaWarp {
                    int32_t* best_score, uint32_t* n_best) {
         const int32_t g = P->gap;
         const uint32_t g2 = pack16(g, g);
-        const uint32_t neg2 = pack16(kNeg16, kNeg16);
         const uint32_t nch = lpa / kChunkCols;
+        const uint32_t rmask = ring_rows - 1;  // ring_rows is a power of two
+        /* carry sentinel of the packed path: negsafe + 16*g >= INT16_MIN and every value derived from it
+         * stays below INT16_MIN + 1024 <= any legal score (needs |g| <= kMaxGapInt16) */
+        const int32_t negsafe = -32768 - 16 * g;
+        uint32_t gb[8], gc[8];  // bridge / carry offsets per register
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            gb[r] = pack16(0, (r + 1) * g);
+            gc[r] = pack16((r + 1) * g, (r + 9) * g);
+        }
         /* root row: H[0][c] = c * g */
         for (uint32_t col = lane; col < lpa; col += 32) {
             int16_t v = static_cast<int16_t>(static_cast<int32_t>(col) * g);
-            H[col] = v;
+            H[perm(col)] = v;
             ring[swz(col)] = v;  // ring slot 0 <- rank 0
         }
         syncwarp();
@@ -416,86 +471,84 @@ struct PoaWarp {
                 rec_lo = static_cast<uint32_t>(t);
                 rec_hi = static_cast<uint32_t>(t >> 32);
             }
-            uint32_t lo = shfl(rec_lo, (i - 1) & 31), hi = shfl(rec_hi, (i - 1) & 31);
-            uint32_t cidx = lo & 0xff;
-            uint32_t np = (lo >> 8) & 0x7f;
-            bool sink = (lo >> 15) & 1;
-            uint32_t npe = np ? np : 1;
-            int16_t* myrow_s = ring + (i % ring_rows) * lpa;
+            const uint32_t lo = shfl(rec_lo, (i - 1) & 31);
+            const uint32_t cidx = lo & 0xff;
+            const uint32_t np = (lo >> 8) & 0x7f;
+            const bool sink = (lo >> 15) & 1;
+            uint32_t hi = 0;
+            if (np > 1) hi = shfl(rec_hi, (i - 1) & 31);  // warp-uniform branch
+            int16_t* myrow_s = ring + (i & rmask) * lpa;
             int16_t* myrow_g = H + static_cast<uint64_t>(i) * lpa;
             int32_t chunk_carry = kNeg32;
             for (uint32_t ch = 0; ch < nch; ++ch) {
                 uint32_t acc[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) acc[r] = neg2;
-                Row8 pf = load_row_smem(prof + cidx * lpa, ch, lane);
-                for (uint32_t k = 0; k < npe; ++k) {
-                    uint32_t p;
-                    if (np == 0)
-                        p = 0;
-                    else if (k == 0)
-                        p = lo >> 16;
-                    else if (k == 1)
-                        p = hi & 0xffff;
-                    else if (k == 2)
-                        p = hi >> 16;
-                    else
-                        p = pred_ovf[i * ki + k];
-                    bool near = (i - p) < ring_rows;
-                    const int16_t* prow_s = ring + (p % ring_rows) * lpa;
+                for (int r = 0; r < 8; ++r) acc[r] = 0x80008000u;  // max identity; never an addend
+                const Row8 pf = load_row_smem(prof + cidx * lpa, ch, lane);
+                auto pred = [&](uint32_t p) {
+                    const bool near = (i - p) < ring_rows;
+                    const int16_t* prow_s = ring + (p & rmask) * lpa;
                     const int16_t* prow_g = H + static_cast<uint64_t>(p) * lpa;
-                    Row8 pr = near ? load_row_smem(prow_s, ch, lane) : load_row_gmem(prow_g, ch, lane);
-                    uint32_t left = shfl_up(pr.r[7], 1);
-                    if (lane == 0) {
-                        int32_t lv = kNeg16;
-                        if (ch > 0) lv = near ? prow_s[swz(ch * kChunkCols - 1)] : prow_g[ch * kChunkCols - 1];
-                        left = pack16(0, lv);
-                    }
-                    uint32_t d = byte_perm(left, pr.r[0], 0x5432);
-                    acc[0] = viaddmax_s16x2(d, pf.r[0], acc[0]);
+                    const Row8 pr = near ? load_row_smem(prow_s, ch, lane) : load_row_gmem(prow_g, ch, lane);
+                    uint32_t left = shfl_up(pr.r[7], 1);  // hi half = previous lane's last column
+                    int32_t lv = kNegDiag;
+                    if (ch > 0) lv = near ? prow_s[swz(ch * kChunkCols - 1)] : prow_g[perm(ch * kChunkCols - 1)];
+                    left = lane == 0 ? (static_cast<uint32_t>(lv) << 16) : left;
+                    /* diagonal operand of register 0 = (column -1 of the block, column 7) */
+                    uint32_t d0 = byte_perm(left, pr.r[7], 0x5432);
+                    acc[0] = viaddmax_s16x2(d0, pf.r[0], acc[0]);
                     acc[0] = viaddmax_s16x2(pr.r[0], g2, acc[0]);
 #pragma unroll
                     for (int r = 1; r < 8; ++r) {
-                        d = byte_perm(pr.r[r - 1], pr.r[r], 0x5432);
-                        acc[r] = viaddmax_s16x2(d, pf.r[r], acc[r]);
+                        acc[r] = viaddmax_s16x2(pr.r[r - 1], pf.r[r], acc[r]);
                         acc[r] = viaddmax_s16x2(pr.r[r], g2, acc[r]);
                     }
+                };
+                if (np == 0) {
+                    pred(0);
+                } else {
+                    pred(lo >> 16);
+                    if (np > 1) pred(hi & 0xffff);
+                    if (np > 2) pred(hi >> 16);
+                    for (uint32_t k = 3; k < np; ++k) pred(pred_ovf[i * ki + k]);
                 }
-                /* in-row gap recurrence H[c] = max(H[c], H[c-1] + g): lane-local chain + warp max-plus scan */
-                int32_t y[16];
+                /* in-row gap recurrence H[c] = max(H[c], H[c-1] + g), all in packed int16:
+                 * two 8-long chains (low halves = columns 0..7, high halves = columns 8..15 of the block) */
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    y[2 * r] = lo16(acc[r]);
-                    y[2 * r + 1] = hi16(acc[r]);
-                }
+                for (int r = 1; r < 8; ++r) acc[r] = viaddmax_s16x2(acc[r - 1], g2, acc[r]);
+                /* bridge: column 7 feeds columns 8..15 */
+                const uint32_t bridge = byte_perm(acc[7], 0x80008000u, 0x1076);  // lo = INT16_MIN, hi = acc[7].lo
 #pragma unroll
-                for (int k = 1; k < 16; ++k) y[k] = viaddmax_s32(y[k - 1], g, y[k]);
-                int32_t t = y[15];
-                if (lane == 0) t = viaddmax_s32(chunk_carry, 16 * g, t);
+                for (int r = 0; r < 8; ++r) acc[r] = viaddmax_s16x2(bridge, gb[r], acc[r]);
+                /* warp max-plus scan of the lane totals (column 15 of each block), decay 16*g per lane */
+                int32_t t = hi16(acc[7]);
+                t = viaddmax_s32(lane == 0 ? chunk_carry : kNeg32, 16 * g, t);
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
                     int32_t o = shfl_up(t, dd);
-                    if (lane >= dd) t = viaddmax_s32(o, dd * 16 * g, t);
+                    t = viaddmax_s32(lane >= dd ? o : kNeg32, dd * 16 * g, t);
                 }
                 int32_t carry = shfl_up(t, 1);
-                if (lane == 0) carry = chunk_carry;
+                carry = lane == 0 ? chunk_carry : carry;
+                carry = carry < negsafe ? negsafe : carry;
+                const uint32_t c2 = pack16(carry, carry);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) y[k] = viaddmax_s32(carry, (k + 1) * g, y[k]);
-                chunk_carry = shfl(y[15], 31);
+                for (int r = 0; r < 8; ++r) acc[r] = viaddmax_s16x2(c2, gc[r], acc[r]);
+                chunk_carry = shfl(static_cast<int32_t>(hi16(acc[7])), 31);
                 Row8 out;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) out.r[r] = pack16(y[2 * r], y[2 * r + 1]);
+                for (int r = 0; r < 8; ++r) out.r[r] = acc[r];
                 store_row_smem(myrow_s, ch, lane, out);
                 store_row_gmem(myrow_g, ch, lane, out);
             }
             syncwarp();
             if (sink) {
-                int32_t s = myrow_s[swz(len)];
-                if (s > best) {
-                    best = s;
+                int32_t sc = myrow_s[swz(len)];
+                if (sc > best) {
+                    best = sc;
                     bi = i;
                     nb = 1;
-                } else if (s == best) {
+                } else if (sc == best) {
                     ++nb;
                 }
             }
@@ -580,7 +633,7 @@ struct PoaWarp {
         for (uint32_t r = 1 + lane; r <= nrows; r += 32) {
             uint64_t rc = rec[r];
             if (!((rc >> 15) & 1)) continue;
-            if (H[static_cast<uint64_t>(r) * lpa + len] != best) continue;
+            if (H[static_cast<uint64_t>(r) * lpa + perm(len)] != best) continue;
             uint32_t key = (static_cast<uint32_t>(srank[ord[r]]) << 16) | r;
             if (key < bestkey) bestkey = key;
         }
@@ -595,55 +648,116 @@ struct PoaWarp {
     /* ---------------------------------------------------------------- traceback (sisd :366-459)
      * Priority: diagonal over predecessors in in-edge order, then vertical in the same order, then
      * horizontal.  Lanes test predecessors in parallel; the lowest lane that matches wins.
+     * The walk is a chain of dependent reads of H, so it runs out of a shared-memory TILE: the warp
+     * copies kTileRows ranks x 32 columns of H (plus those rows' program records) from HBM with one
+     * coalesced burst, walks until the path leaves the tile (about 30-40 steps), and re-anchors.
+     * Predecessors below the tile (rare long edges) are read from HBM directly.
      * Output: aln[j] = node aligned to read position j, or kNone (new node). */
+    static constexpr uint32_t kTileCols = 32;
+
     RP_DEV void traceback(uint32_t best_row, uint32_t len, uint32_t lpa, const uint8_t* seq, bool sub) {
         const int32_t g = P->gap, m = P->match, x = P->mismatch;
         const uint16_t* ord = sub ? dp_order : order;
+        const uint32_t kTileRows = P->tile_rows ? P->tile_rows : 96;
+        int16_t* tile = reinterpret_cast<int16_t*>(smem);                                        // [kTileRows][32]
+        uint64_t* trec = reinterpret_cast<uint64_t*>(smem + kTileRows * kTileCols * 2);            // [kTileRows]
+        uint16_t* tnode = reinterpret_cast<uint16_t*>(smem + kTileRows * kTileCols * 2 + kTileRows * 8);
+        uint8_t* tseq = smem + kTileRows * kTileCols * 2 + kTileRows * 8 + ((kTileRows * 2 + 15) & ~15u);
+        for (uint32_t c = lane; c < len; c += 32) tseq[c] = seq[c];  // the walk reads seq[j-1] every step
         uint32_t i = best_row, j = len;
-        uint32_t tile_base = 0xffffffffu;
-        uint32_t t_lo = 0, t_hi = 0, t_node = 0;
+        uint32_t t_top = 0, t_rows = 0, t_col0 = 0;  // tile covers ranks (t_top - t_rows, t_top], cols [t_col0, t_col0+32)
+        bool have_tile = false;
         while (i != 0) {
-            if ((i & ~31u) != tile_base) {
-                tile_base = i & ~31u;
-                uint64_t t = rec[tile_base + lane];
-                t_lo = static_cast<uint32_t>(t);
-                t_hi = static_cast<uint32_t>(t >> 32);
-                t_node = ord[tile_base + lane];  // dp_order/order arrays are padded past nmax
+            if (!have_tile || i + t_rows <= t_top || (j > 0 && j - 1 < t_col0)) {
+                syncwarp();
+                t_top = i;
+                t_rows = i + 1 < kTileRows ? i + 1 : kTileRows;  // down to rank 0 at most
+                uint32_t cb = j >> 4;
+                t_col0 = (cb ? cb - 1 : 0) << 4;
+                for (uint32_t q = lane; q < t_rows; q += 32) {
+                    uint32_t rk = t_top - q;
+                    const U4* src = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0);
+                    U4* dst = reinterpret_cast<U4*>(tile + q * kTileCols);
+                    U4 a = src[0], b = src[1], c = src[2], d = src[3];
+                    dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+                    trec[q] = rec[rk];
+                    tnode[q] = ord[rk];
+                }
+                have_tile = true;
+                syncwarp();
             }
-            uint32_t lo = shfl(t_lo, i & 31), hi = shfl(t_hi, i & 31);
-            uint32_t node = shfl(t_node, i & 31);
-            uint32_t cidx = lo & 0xff, np = (lo >> 8) & 0x7f;
-            uint32_t npe = np ? np : 1;
-            int32_t hij = H[static_cast<uint64_t>(i) * lpa + j];
+            const uint32_t q = t_top - i;
+            const uint64_t rc = trec[q];
+            const uint32_t lo = static_cast<uint32_t>(rc), hi = static_cast<uint32_t>(rc >> 32);
+            const uint32_t node = tnode[q];
+            const uint32_t cidx = lo & 0xff, np = (lo >> 8) & 0x7f;
+            const uint32_t npe = np ? np : 1;
+            const uint32_t ej = perm(j) - t_col0;                      // element of column j inside a tile row
+            const uint32_t ejm = j > 0 ? perm(j - 1) - t_col0 : 0;     // column j-1
+            const int32_t hij = tile[q * kTileCols + ej];
             int32_t mc = 0;
-            if (j > 0) mc = (static_cast<uint8_t>(alpha >> (8 * cidx)) == seq[j - 1]) ? m : x;
+            if (j > 0) mc = (static_cast<uint8_t>(alpha >> (8 * cidx)) == tseq[j - 1]) ? m : x;
             uint32_t found_p = 0;
             int move = 0;  // 1 diag, 2 vert, 3 horiz
-            /* pass 1: diagonal, pass 2: vertical */
-            for (int pass = 1; pass <= 2 && !move; ++pass) {
-                if (pass == 1 && j == 0) continue;
-                for (uint32_t k0 = 0; k0 < npe && !move; k0 += 32) {
-                    uint32_t k = k0 + lane;
-                    uint32_t p = 0;
-                    bool ok = false;
-                    if (k < npe) {
-                        if (np == 0)
-                            p = 0;
-                        else if (k == 0)
-                            p = lo >> 16;
-                        else if (k == 1)
-                            p = hi & 0xffff;
-                        else if (k == 2)
-                            p = hi >> 16;
-                        else
-                            p = pred_ovf[i * ki + k];
+            for (uint32_t k0 = 0; k0 < npe && !move; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                uint32_t p = 0;
+                bool okd = false, okv = false;
+                if (k < npe) {
+                    if (np == 0)
+                        p = 0;
+                    else if (k == 0)
+                        p = lo >> 16;
+                    else if (k == 1)
+                        p = hi & 0xffff;
+                    else if (k == 2)
+                        p = hi >> 16;
+                    else
+                        p = pred_ovf[i * ki + k];
+                    int32_t a = 0, b;
+                    if (p + t_rows > t_top) {  // predecessor row is inside the tile
+                        const int16_t* pr = tile + (t_top - p) * kTileCols;
+                        if (j > 0) a = pr[ejm];
+                        b = pr[ej];
+                    } else {
                         const int16_t* pr = H + static_cast<uint64_t>(p) * lpa;
-                        ok = (pass == 1) ? (hij == pr[j - 1] + mc) : (hij == pr[j] + g);
+                        if (j > 0) a = pr[perm(j - 1)];
+                        b = pr[perm(j)];
                     }
-                    uint32_t msk = ballot(ok);
-                    if (msk) {
-                        found_p = shfl(p, ffs_(msk) - 1);
-                        move = pass;
+                    okd = j > 0 && hij == a + mc;
+                    okv = hij == b + g;
+                }
+                /* all diagonal candidates of ALL predecessors outrank any vertical one (sisd :392-442) */
+                uint32_t md = ballot(okd);
+                uint32_t mv = ballot(okv);
+                if (md) {
+                    found_p = shfl(p, ffs_(md) - 1);
+                    move = 1;
+                } else if (mv && k0 + 32 >= npe) {
+                    found_p = shfl(p, ffs_(mv) - 1);
+                    move = 2;
+                } else if (mv) {
+                    /* > 32 predecessors: a later group may still hold a diagonal match; remember the first vertical */
+                    uint32_t vp = shfl(p, ffs_(mv) - 1);
+                    bool later_diag = false;
+                    for (uint32_t k1 = k0 + 32; k1 < npe && !later_diag; k1 += 32) {
+                        uint32_t kk = k1 + lane;
+                        bool od = false;
+                        if (kk < npe && j > 0) {
+                            uint32_t pp = pred_ovf[i * ki + kk];
+                            od = hij == H[static_cast<uint64_t>(pp) * lpa + perm(j - 1)] + mc;
+                            if (od) p = pp;
+                        }
+                        uint32_t m2 = ballot(od);
+                        if (m2) {
+                            found_p = shfl(p, ffs_(m2) - 1);
+                            move = 1;
+                            later_diag = true;
+                        }
+                    }
+                    if (!later_diag) {
+                        found_p = vp;
+                        move = 2;
                     }
                 }
             }
@@ -673,59 +787,72 @@ struct PoaWarp {
     RP_DEV void add_alignment(const uint8_t* seq, const uint8_t* w, uint32_t len) {
         const uint32_t n_old = N;
         uint16_t* delta = reinterpret_cast<uint16_t*>(smem);  // n_old + 2 counters (ring is idle now)
+        /* All phases handle kU positions per lane at a time with the loads of one dependency level issued
+         * together (the graph is in HBM: every level costs a full memory latency). */
+        constexpr int kU = 4;
         /* Phase A: target node per position (existing node, aligned sibling with the same character, or new) */
         uint32_t n_new = 0;
-        for (uint32_t j0 = 0; j0 < len; j0 += 32) {
-            uint32_t j = j0 + lane;
-            bool is_new = false;
-            uint32_t tgt = kNone, anchor = kNone;
-            if (j < len) {
-                uint32_t a = aln[j];
-                uint8_t c = seq[j];
-                if (a == kNone) {
-                    is_new = true;
-                } else if (code[a] == c) {
-                    tgt = a;
-                } else {
-                    uint32_t na = al_cnt[a];
-                    for (uint32_t k = 0; k < na; ++k) {
-                        uint32_t s = al[a * ka + k];
-                        if (code[s] == c) {
-                            tgt = s;
-                            break;
+        for (uint32_t j0 = 0; j0 < len; j0 += 32 * kU) {
+            uint32_t a[kU], c[kU], ca[kU], na[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                uint32_t j = j0 + u * 32 + lane;
+                a[u] = j < len ? aln[j] : kNone;
+                c[u] = j < len ? seq[j] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                ca[u] = a[u] != kNone ? code[a[u]] : 0;
+                na[u] = a[u] != kNone ? al_cnt[a[u]] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                uint32_t j = j0 + u * 32 + lane;
+                bool is_new = false;
+                uint32_t tgt = kNone, anchor = kNone;
+                if (j < len) {
+                    if (a[u] == kNone) {
+                        is_new = true;
+                    } else if (ca[u] == c[u]) {
+                        tgt = a[u];
+                    } else {
+                        for (uint32_t k = 0; k < na[u]; ++k) {
+                            uint32_t sb = al[a[u] * ka + k];
+                            if (code[sb] == c[u]) {
+                                tgt = sb;
+                                break;
+                            }
+                        }
+                        if (tgt == kNone) {
+                            is_new = true;
+                            anchor = a[u];
                         }
                     }
-                    if (tgt == kNone) {
-                        is_new = true;
-                        anchor = a;
+                }
+                uint32_t tot;
+                uint32_t pos = warp_rank(is_new, &tot);
+                if (is_new) {
+                    uint32_t id = n_old + n_new + pos;
+                    tgt = id;
+                    if (id < nmax) {
+                        code[id] = static_cast<uint8_t>(c[u]);
+                        flags[id] = 0;
+                        in_cnt[id] = 0;
+                        cov[id] = 0;
+                        al_cnt[id] = 0;
                     }
+                    newlist[n_new + pos] = (j << 16) | anchor;  // anchor kNone => unaligned insertion
                 }
+                if (j < len) cur[j] = static_cast<uint16_t>(tgt);
+                n_new += tot;
             }
-            uint32_t tot;
-            uint32_t pos = warp_rank(is_new, &tot);
-            if (is_new) {
-                uint32_t id = n_old + n_new + pos;
-                tgt = id;
-                if (id < nmax) {
-                    code[id] = seq[j];
-                    flags[id] = 0;
-                    in_cnt[id] = 0;
-                    cov[id] = 0;
-                    al_cnt[id] = 0;
-                }
-                newlist[n_new + pos] = (j << 16) | anchor;  // anchor kNone => unaligned insertion
-            }
-            if (j < len) cur[j] = static_cast<uint16_t>(tgt);
-            n_new += tot;
         }
         if (n_old + n_new > nmax) {
             fail(kWinNodeLimit);
             return;
         }
         syncwarp();
-        /* K_j: rank after which position j's node sits / is inserted (non-decreasing along the read) */
-        /* Phase B: aligned-cluster membership of new nodes + per-position order keys */
-        /* keys are kept in cur-parallel scratch: reuse `aln` as uint16 key array after reading it */
+        /* Phase B: aligned-cluster membership of new nodes (graph.cpp:221-229) */
         bool lim_a = false;
         for (uint32_t k0 = 0; k0 < n_new; k0 += 32) {
             uint32_t k = k0 + lane;
@@ -739,11 +866,11 @@ struct PoaWarp {
                         lim_a = true;
                     } else {
                         for (uint32_t q = 0; q < na; ++q) {
-                            uint32_t s = al[anchor * ka + q];
-                            al[id * ka + q] = static_cast<uint16_t>(s);
-                            uint32_t ns = al_cnt[s];
-                            al[s * ka + ns] = static_cast<uint16_t>(id);
-                            al_cnt[s] = static_cast<uint8_t>(ns + 1);
+                            uint32_t sb = al[anchor * ka + q];
+                            al[id * ka + q] = static_cast<uint16_t>(sb);
+                            uint32_t ns = al_cnt[sb];
+                            al[sb * ka + ns] = static_cast<uint16_t>(id);
+                            al_cnt[sb] = static_cast<uint8_t>(ns + 1);
                         }
                         al[id * ka + na] = static_cast<uint16_t>(anchor);
                         al_cnt[id] = static_cast<uint8_t>(na + 1);
@@ -758,63 +885,80 @@ struct PoaWarp {
             return;
         }
         syncwarp();
-        /* order keys: for an old target (or the anchor of an aligned new node) the end of its cluster block */
-        int32_t run = 0;  // running max of keys over previous positions (K_{-1} = 0: right after the root)
-        for (uint32_t j0 = 0; j0 < len; j0 += 32) {
-            uint32_t j = j0 + lane;
-            int32_t own = 0;
-            if (j < len) {
-                uint32_t t = cur[j];
-                uint32_t base_node = kNone;
-                if (t < n_old) {
-                    base_node = t;
-                } else {
-                    uint32_t anchor = newlist[t - n_old] & 0xffffu;
-                    if (anchor != kNone) base_node = anchor;
-                }
-                if (base_node != kNone) {
-                    uint32_t r = rank_of[base_node];
-                    uint32_t na = al_cnt[base_node];
-                    for (uint32_t q = 0; q < na; ++q) {
-                        uint32_t s = al[base_node * ka + q];
-                        if (s < n_old) {
-                            uint32_t rs = rank_of[s];
-                            if (rs > r) r = rs;
-                        }
-                    }
-                    own = static_cast<int32_t>(r);
-                }
+        /* order keys K_j (non-decreasing along the read): for an old target, or the anchor of an aligned new
+         * node, the last rank of its aligned-cluster block; an unaligned insertion inherits K_{j-1} */
+        int32_t run = 0;  // K_{-1} = 0: right after the root
+        for (uint32_t j0 = 0; j0 < len; j0 += 32 * kU) {
+            uint32_t bn[kU], rk0[kU], nal[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                uint32_t j = j0 + u * 32 + lane;
+                bn[u] = j < len ? cur[j] : kNone;
             }
-            int32_t inc = warp_incl_max(own);
-            if (inc < run) inc = run;
-            if (j < len) aln[j] = static_cast<uint16_t>(inc);  // aln now holds K_j
-            run = shfl(inc, 31);
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (bn[u] != kNone && bn[u] >= n_old) bn[u] = newlist[bn[u] - n_old] & 0xffffu;  // anchor or kNone
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                rk0[u] = bn[u] != kNone ? rank_of[bn[u]] : 0;
+                nal[u] = bn[u] != kNone ? al_cnt[bn[u]] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                uint32_t j = j0 + u * 32 + lane;
+                uint32_t rmax = rk0[u];
+                for (uint32_t q = 0; q < nal[u]; ++q) {
+                    uint32_t sb = al[bn[u] * ka + q];
+                    if (sb < n_old) {
+                        uint32_t rs = rank_of[sb];
+                        if (rs > rmax) rmax = rs;
+                    }
+                }
+                int32_t inc = warp_incl_max(static_cast<int32_t>(rmax));
+                if (inc < run) inc = run;
+                if (j < len) aln[j] = static_cast<uint16_t>(inc);  // aln now holds K_j
+                run = shfl(inc, 31);
+            }
         }
         syncwarp();
         /* Phase C: edges (graph.cpp:81-91,236-243) + per-node sequence counters (Node::Coverage, :32-47) */
         bool lim_e = false;
-        for (uint32_t j0 = 0; j0 < len; j0 += 32) {
-            uint32_t j = j0 + lane;
-            if (j < len) {
-                uint32_t c = cur[j];
-                if (len >= 2) cov[c] = static_cast<uint16_t>(cov[c] + 1);
-                if (j > 0) {
-                    uint32_t pv = cur[j - 1];
-                    int32_t wt = static_cast<int32_t>(w[j - 1]) + static_cast<int32_t>(w[j]);
-                    uint32_t ni = in_cnt[c];
-                    uint32_t q = 0;
-                    for (; q < ni; ++q)
-                        if (in_tail[c * ki + q] == pv) break;
-                    if (q < ni) {
-                        in_w[c * ki + q] += wt;
-                    } else if (ni < ki && ni < 127) {
-                        in_tail[c * ki + ni] = static_cast<uint16_t>(pv);
-                        in_w[c * ki + ni] = wt;
-                        in_cnt[c] = static_cast<uint8_t>(ni + 1);
-                        flags[pv] |= 1;  // several lanes may set different nodes' flags; each pv is unique per lane
-                    } else {
-                        lim_e = true;
-                    }
+        for (uint32_t j0 = 0; j0 < len; j0 += 32 * kU) {
+            uint32_t c[kU], pv[kU], ni[kU], cv[kU];
+            int32_t wt[kU];
+            uint64_t t4[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                uint32_t j = j0 + u * 32 + lane;
+                c[u] = j < len ? cur[j] : kNone;
+                pv[u] = (j < len && j > 0) ? cur[j - 1] : kNone;
+                wt[u] = (j < len && j > 0) ? static_cast<int32_t>(w[j - 1]) + static_cast<int32_t>(w[j]) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                ni[u] = c[u] != kNone ? in_cnt[c[u]] : 0;
+                cv[u] = c[u] != kNone ? cov[c[u]] : 0;
+                t4[u] = c[u] != kNone ? *reinterpret_cast<const uint64_t*>(in_tail + c[u] * ki) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (c[u] == kNone) continue;
+                if (len >= 2) cov[c[u]] = static_cast<uint16_t>(cv[u] + 1);
+                if (pv[u] == kNone) continue;
+                uint32_t q = 0;
+                for (; q < ni[u]; ++q) {
+                    uint32_t t = q < 4 ? (static_cast<uint32_t>(t4[u] >> (16 * q)) & 0xffffu) : in_tail[c[u] * ki + q];
+                    if (t == pv[u]) break;
+                }
+                if (q < ni[u]) {
+                    in_w[c[u] * ki + q] += wt[u];
+                } else if (ni[u] < ki && ni[u] < 127) {
+                    in_tail[c[u] * ki + ni[u]] = static_cast<uint16_t>(pv[u]);
+                    in_w[c[u] * ki + ni[u]] = wt[u];
+                    in_cnt[c[u]] = static_cast<uint8_t>(ni[u] + 1);
+                    flags[pv[u]] |= 1;  // every pv is a distinct node, so lanes never touch the same byte
+                } else {
+                    lim_e = true;
                 }
             }
         }
@@ -998,6 +1142,7 @@ struct PoaWarp {
 
 /* int16 is safe iff spoa's own criterion holds (alignment_engine.cpp:101-110, simd impl :699-745) */
 RP_DEV bool fits_int16(int32_t m, int32_t g, int64_t len, int64_t nodes) {
+    if (g < -kMaxGapInt16) return false;
     int64_t i = len + 8, j = nodes;
     int64_t mn = i < j ? i : j;
     int64_t df = i > j ? i - j : j - i;
@@ -1055,11 +1200,12 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         uint32_t lpa = (len + 1 + kChunkCols - 1) / kChunkCols * kChunkCols;
         /* shared memory split: profile rows first, the rest is the ring of recent DP rows */
         uint32_t prof_bytes = W.ncodes * lpa * 2;
-        uint32_t ring_rows = (P.smem_per_warp - prof_bytes) / (lpa * 2);
         if (prof_bytes + 2 * lpa * 2 > P.smem_per_warp) {
             W.fail(kWinSeqTooLong);
             break;
         }
+        uint32_t ring_rows = (P.smem_per_warp - prof_bytes) / (lpa * 2);
+        while (ring_rows & (ring_rows - 1)) ring_rows &= ring_rows - 1;  // largest power of two that fits
         W.prof = reinterpret_cast<int16_t*>(smem);
         W.ring = reinterpret_cast<int16_t*>(smem + prof_bytes);
         uint32_t pred_rows = W.build_program(nrows, sub);

@@ -37,7 +37,7 @@ void warp_entry(void* arg) {
 
 extern "C" {
 
-/* Flat window set in, consensus out.  limits: {nmax, lmax, ki, ka, smem_per_warp}.  Returns 0 or <0. */
+/* Flat window set in, consensus out.  limits: {nmax, lmax, ki, ka, smem_per_warp, tile_rows}.  Returns 0 or <0. */
 int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
                const uint8_t* seq_has_qual, const uint32_t* seq_begin, const uint32_t* seq_end,
                const uint32_t* win_first, const uint8_t* win_type, int8_t match, int8_t mismatch, int8_t gap,
@@ -97,6 +97,7 @@ int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const u
     P.lim.stack_cap = limits[0] * 4 + 64;
     P.lay = rp::make_layout(P.lim);
     P.smem_per_warp = limits[4];
+    P.tile_rows = limits[5];
     std::vector<uint8_t> slot(P.lay.bytes + 64);
     std::vector<uint8_t> smem(P.smem_per_warp + 64);
     uint8_t* slot_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slot.data()) + 15) & ~uintptr_t(15));

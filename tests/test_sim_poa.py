@@ -58,6 +58,12 @@ def test_sim_tiny_ring_forces_far_predecessor_path():
     _check(ws, smem=5 * 512 * 2 + 2 * 512 * 2)
 
 
+def test_sim_tiny_traceback_tile_forces_out_of_tile_predecessors():
+    # 3-rank tiles: most predecessor rows fall below the tile and are read from the HBM copy
+    _check(_mk("fullspan_small", seed=8), tile_rows=3)
+    _check(_mk("partial", seed=8), tile_rows=2)
+
+
 def test_sim_no_trim_and_trivial():
     _check(_mk("partial", seed=9), trim=False)
     from racon_b200 import windows

@@ -34,7 +34,8 @@ data = rows[2:]
 base = int(data[0][ia], 16)
 byoff = {int(r[ia], 16) - base: (int(r[ii] or 0), int(r[isamp] or 0), r[1]) for r in data if r[ia].startswith("0x")}
 # function ranges in poa_core.cuh
-src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "racon_b200", "csrc", "poa_core.cuh")).read().splitlines()
+srcpath = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "racon_b200", "csrc", "poa_core.cuh")
+src = open(srcpath).read().splitlines()
 funcs = []
 for n, l in enumerate(src, 1):
     m = re.match(r"\s*RP_DEV\s+[\w:<>\*&\s]+?\s+(\w+)\(", l)
