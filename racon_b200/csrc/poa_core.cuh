@@ -65,7 +65,7 @@ struct PoaLimits {
 struct SlotLayout {
     uint64_t code, flags, in_cnt, al_cnt, cov, in_tail, in_w, al, order_a, order_b, rank_of, dp_order, dp_rank,
         rec, pred_ovf, H, aln, cur, wts_unused, member, has_out_sub, score, cpred, sorder, srank, marks, stack,
-        newlist, bytes;
+        newlist, ccarry, bytes;
 };
 
 RP_HD uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -92,7 +92,7 @@ RP_HD SlotLayout make_layout(const PoaLimits& L) {
     s.rank_of = take(n * 2);
     s.dp_order = take((n + 2 + 64) * 2);
     s.dp_rank = take(n * 2);
-    s.rec = take((n + 1 + 64) * 8);
+    s.rec = take((n + 1 + 160) * 16);
     s.pred_ovf = take((n + 1) * L.ki * 2);
     s.H = take((n + 1) * static_cast<uint64_t>(L.lp) * 2);
     s.aln = take((static_cast<uint64_t>(L.lmax) + 1) * 2);
@@ -107,6 +107,7 @@ RP_HD SlotLayout make_layout(const PoaLimits& L) {
     s.marks = take(n);
     s.stack = take(static_cast<uint64_t>(L.stack_cap) * 2);
     s.newlist = take((static_cast<uint64_t>(L.lmax) + 1) * 4);
+    s.ccarry = take((n + 2) * 2 * 2);
     s.bytes = align_up(o, 4096);
     return s;
 }
@@ -159,6 +160,16 @@ struct Row8 {
     uint32_t r[8];
 };
 
+/* One DP program record per row: a = code index (8) | in-degree (7) | sink (1) | pred0 | pred1 | pred2,
+ * b = pred3..pred6 (DP ranks, 0 = virtual root row).  In-degrees above 7 spill to pred_ovf. */
+struct alignas(16) Rec {
+    uint64_t a, b;
+};
+RP_DEV uint32_t rec_pred(const Rec& r, uint32_t k) {  // k < 7
+    return k < 3 ? (static_cast<uint32_t>(r.a >> (16 + 16 * k)) & 0xffffu)
+                 : (static_cast<uint32_t>(r.b >> (16 * (k - 3))) & 0xffffu);
+}
+
 struct alignas(16) U4 {
     uint32_t x, y, z, w;
 };
@@ -205,10 +216,11 @@ struct PoaWarp {
     uint16_t *cov, *in_tail, *al, *order, *order_nxt, *rank_of, *dp_order, *dp_rank, *pred_ovf, *aln, *cur, *cpred,
         *sorder, *srank, *stack;
     int32_t* in_w;
-    uint64_t* rec;
+    Rec* rec;
     int16_t* H;
     int64_t* score;
     uint32_t* newlist;
+    int16_t* ccarry;
     /* shared memory */
     int16_t* ring;       // ring_rows x lp_a
     int16_t* prof;       // ncodes x lp_a
@@ -239,7 +251,7 @@ struct PoaWarp {
         rank_of = reinterpret_cast<uint16_t*>(slot + y.rank_of);
         dp_order = reinterpret_cast<uint16_t*>(slot + y.dp_order);
         dp_rank = reinterpret_cast<uint16_t*>(slot + y.dp_rank);
-        rec = reinterpret_cast<uint64_t*>(slot + y.rec);
+        rec = reinterpret_cast<Rec*>(slot + y.rec);
         pred_ovf = reinterpret_cast<uint16_t*>(slot + y.pred_ovf);
         H = reinterpret_cast<int16_t*>(slot + y.H);
         aln = reinterpret_cast<uint16_t*>(slot + y.aln);
@@ -253,6 +265,7 @@ struct PoaWarp {
         marks = slot + y.marks;
         stack = reinterpret_cast<uint16_t*>(slot + y.stack);
         newlist = reinterpret_cast<uint32_t*>(slot + y.newlist);
+        ccarry = reinterpret_cast<int16_t*>(slot + y.ccarry);
         smem = sm;
         smem_bytes = sm_bytes;
         ki = p->lim.ki;
@@ -394,45 +407,36 @@ struct PoaWarp {
             for (int u = 0; u < kU; ++u) {
                 if (r[u] > nrows) continue;
                 uint32_t np = 0;
-                uint64_t preds = 0;
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (use[u][k]) preds |= static_cast<uint64_t>(pk[u][k]) << (16 * np++);
-                for (uint32_t k = 3; k < ni[u]; ++k) {  // rare: in-degree > 3
-                    uint32_t t = in_tail[v[u] * ki + k];
-                    if (sub && !member[t]) continue;
-                    uint32_t pr = rk[t];
+                uint64_t pa = 0, pb = 0;
+                auto put = [&](uint32_t pr) {
                     if (np < 3)
-                        preds |= static_cast<uint64_t>(pr) << (16 * np);
+                        pa |= static_cast<uint64_t>(pr) << (16 + 16 * np);
+                    else if (np < 7)
+                        pb |= static_cast<uint64_t>(pr) << (16 * (np - 3));
                     else
                         pred_ovf[r[u] * ki + np] = static_cast<uint16_t>(pr);
                     ++np;
+                };
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (use[u][k]) put(pk[u][k]);
+                for (uint32_t k = 3; k < ni[u]; ++k) {  // less common: in-degree > 3
+                    uint32_t t = in_tail[v[u] * ki + k];
+                    if (sub && !member[t]) continue;
+                    put(rk[t]);
                 }
                 bool sink = !fl[u];
-                rec[r[u]] = static_cast<uint64_t>(code_index(static_cast<uint8_t>(cd[u]))) |
-                            (static_cast<uint64_t>(np & 0x7f) << 8) | (static_cast<uint64_t>(sink ? 1 : 0) << 15) |
-                            (preds << 16);
+                Rec rc;
+                rc.a = static_cast<uint64_t>(code_index(static_cast<uint8_t>(cd[u]))) |
+                       (static_cast<uint64_t>(np & 0x7f) << 8) | (static_cast<uint64_t>(sink ? 1 : 0) << 15) | pa;
+                rc.b = pb;
+                rec[r[u]] = rc;
                 pred_rows += np ? np : 1;
             }
         }
-        if (lane == 0) rec[0] = 0;
+        if (lane == 0) rec[0] = Rec{0, 0};
         syncwarp();
         return pred_rows;  // per-lane partial sum (only summed when the device counters are on)
-    }
-
-    /* ---------------------------------------------------------------- profile (sisd :123-131) */
-    RP_DEV void build_profile(const uint8_t* seq, uint32_t len, uint32_t lpa) {
-        int32_t m = P->match, x = P->mismatch;
-        for (uint32_t k = 0; k < ncodes; ++k) {
-            uint8_t c = static_cast<uint8_t>(alpha >> (8 * k));
-            int16_t* row = prof + k * lpa;
-            for (uint32_t col = lane; col < lpa; col += 32) {
-                int16_t v = static_cast<int16_t>(x);
-                if (col >= 1 && col <= len && seq[col - 1] == c) v = static_cast<int16_t>(m);
-                row[swz(col)] = v;
-            }
-        }
-        syncwarp();
     }
 
     /* ---------------------------------------------------------------- the DP (sisd :292-360, simd :760-906)
@@ -440,60 +444,80 @@ struct PoaWarp {
      * -infinity, which makes column 0 follow the general recurrence.  Returns the best sink row
      * (first strictly greater in processing order) in *best_row, its score, and the number of sink rows
      * that reach that score. */
-    RP_DEV void dp(uint32_t nrows, uint32_t len, uint32_t lpa, uint32_t ring_rows, uint32_t* best_row,
-                   int32_t* best_score, uint32_t* n_best) {
+    /* one 512-column chunk of the match/mismatch profile (sisd :123-131) into shared memory */
+    RP_DEV void build_profile(const uint8_t* seq, uint32_t len, uint32_t ch) {
+        int32_t m = P->match, x = P->mismatch;
+        for (uint32_t k = 0; k < ncodes; ++k) {
+            uint8_t c = static_cast<uint8_t>(alpha >> (8 * k));
+            int16_t* row = prof + k * kChunkCols;
+            for (uint32_t cc = lane; cc < kChunkCols; cc += 32) {
+                uint32_t col = ch * kChunkCols + cc;
+                int16_t v = static_cast<int16_t>(x);
+                if (col >= 1 && col <= len && seq[col - 1] == c) v = static_cast<int16_t>(m);
+                row[swz(cc)] = v;
+            }
+        }
+    }
+
+    RP_DEV void dp(const uint8_t* seq, uint32_t nrows, uint32_t len, uint32_t lpa, uint32_t ring_rows,
+                   uint32_t* best_row, int32_t* best_score, uint32_t* n_best) {
+        /* Row-synchronous: the whole warp computes one row (512-column chunk) at a time; lane l owns columns
+         * 16l..16l+15.  Rows longer than 512 columns are done chunk by chunk (one pass over all rows per chunk,
+         * the carry between chunks goes through a small per-row array), so shared memory only ever holds one
+         * chunk: the profile chunk and a ring of the last `ring_rows` rows (power of two). */
         const int32_t g = P->gap;
         const uint32_t g2 = pack16(g, g);
         const uint32_t nch = lpa / kChunkCols;
-        const uint32_t rmask = ring_rows - 1;  // ring_rows is a power of two
-        /* carry sentinel of the packed path: negsafe + 16*g >= INT16_MIN and every value derived from it
-         * stays below INT16_MIN + 1024 <= any legal score (needs |g| <= kMaxGapInt16) */
-        const int32_t negsafe = -32768 - 16 * g;
+        const uint32_t rmask = ring_rows - 1;
+        const int32_t negsafe = -32768 - 16 * g;  // see kMaxGapInt16
         uint32_t gb[8], gc[8];  // bridge / carry offsets per register
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             gb[r] = pack16(0, (r + 1) * g);
             gc[r] = pack16((r + 1) * g, (r + 9) * g);
         }
-        /* root row: H[0][c] = c * g */
-        for (uint32_t col = lane; col < lpa; col += 32) {
-            int16_t v = static_cast<int16_t>(static_cast<int32_t>(col) * g);
-            H[perm(col)] = v;
-            ring[swz(col)] = v;  // ring slot 0 <- rank 0
-        }
-        syncwarp();
+        for (uint32_t col = lane; col < lpa; col += 32) H[perm(col)] = static_cast<int16_t>(static_cast<int32_t>(col) * g);
+        const uint32_t sink_ch = len / kChunkCols, sink_e = swz(len % kChunkCols);
         int32_t best = kNeg32;
         uint32_t bi = 0, nb = 0;
-        uint32_t rec_lo = 0, rec_hi = 0;
-        for (uint32_t i = 1; i <= nrows; ++i) {
-            if (((i - 1) & 31u) == 0) {
-                uint64_t t = rec[i + lane];  // rec[] is padded
-                rec_lo = static_cast<uint32_t>(t);
-                rec_hi = static_cast<uint32_t>(t >> 32);
-            }
-            const uint32_t lo = shfl(rec_lo, (i - 1) & 31);
-            const uint32_t cidx = lo & 0xff;
-            const uint32_t np = (lo >> 8) & 0x7f;
-            const bool sink = (lo >> 15) & 1;
-            uint32_t hi = 0;
-            if (np > 1) hi = shfl(rec_hi, (i - 1) & 31);  // warp-uniform branch
-            int16_t* myrow_s = ring + (i & rmask) * lpa;
-            int16_t* myrow_g = H + static_cast<uint64_t>(i) * lpa;
-            int32_t chunk_carry = kNeg32;
-            for (uint32_t ch = 0; ch < nch; ++ch) {
+        int16_t* cc_prev = ccarry;        // last column of the previous chunk, per row (multi-chunk rows only)
+        int16_t* cc_cur = ccarry + (nmax + 2);
+        const uint32_t lanem = static_cast<uint32_t>(lane);
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            build_profile(seq, len, ch);
+            for (uint32_t c = lane; c < kChunkCols; c += 32)  // root row (rank 0) -> ring slot 0
+                ring[swz(c)] = static_cast<int16_t>(static_cast<int32_t>(ch * kChunkCols + c) * g);
+            syncwarp();
+            const bool multi = ch > 0;
+            uint32_t rec_a_lo = 0, rec_a_hi = 0, rec_b_lo = 0, rec_b_hi = 0;
+            int16_t* hrow = H + static_cast<uint64_t>(ch) * kChunkCols;  // row i of this chunk = hrow + i*lpa
+            for (uint32_t i = 1; i <= nrows; ++i) {
+                const uint32_t ti = (i - 1) & 31u;
+                if (ti == 0) {
+                    Rec t = rec[i + lane];  // rec[] is padded
+                    rec_a_lo = static_cast<uint32_t>(t.a);
+                    rec_a_hi = static_cast<uint32_t>(t.a >> 32);
+                    rec_b_lo = static_cast<uint32_t>(t.b);
+                    rec_b_hi = static_cast<uint32_t>(t.b >> 32);
+                }
+                const uint32_t lo = shfl(rec_a_lo, ti);
+                const uint32_t cidx = lo & 0xff;
+                const uint32_t np = (lo >> 8) & 0x7f;
+                const bool sink = (lo >> 15) & 1;
                 uint32_t acc[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) acc[r] = 0x80008000u;  // max identity; never an addend
-                const Row8 pf = load_row_smem(prof + cidx * lpa, ch, lane);
+                const Row8 pf = load_row_smem(prof + cidx * kChunkCols, 0, lane);
                 auto pred = [&](uint32_t p) {
-                    const bool near = (i - p) < ring_rows;
-                    const int16_t* prow_s = ring + (p & rmask) * lpa;
-                    const int16_t* prow_g = H + static_cast<uint64_t>(p) * lpa;
-                    const Row8 pr = near ? load_row_smem(prow_s, ch, lane) : load_row_gmem(prow_g, ch, lane);
+                    Row8 pr;
+                    if (i - p < ring_rows)  // warp-uniform
+                        pr = load_row_smem(ring + (p & rmask) * kChunkCols, 0, lane);
+                    else
+                        pr = load_row_gmem(hrow + static_cast<uint64_t>(p) * lpa, 0, lane);
                     uint32_t left = shfl_up(pr.r[7], 1);  // hi half = previous lane's last column
                     int32_t lv = kNegDiag;
-                    if (ch > 0) lv = near ? prow_s[swz(ch * kChunkCols - 1)] : prow_g[perm(ch * kChunkCols - 1)];
-                    left = lane == 0 ? (static_cast<uint32_t>(lv) << 16) : left;
+                    if (multi) lv = cc_prev[p];
+                    left = lanem == 0 ? (static_cast<uint32_t>(lv) << 16) : left;
                     /* diagonal operand of register 0 = (column -1 of the block, column 7) */
                     uint32_t d0 = byte_perm(left, pr.r[7], 0x5432);
                     acc[0] = viaddmax_s16x2(d0, pf.r[0], acc[0]);
@@ -504,13 +528,21 @@ struct PoaWarp {
                         acc[r] = viaddmax_s16x2(pr.r[r], g2, acc[r]);
                     }
                 };
-                if (np == 0) {
-                    pred(0);
+                if (np <= 1) {
+                    pred(np ? (lo >> 16) : 0u);
                 } else {
+                    const uint32_t hi = shfl(rec_a_hi, ti);
                     pred(lo >> 16);
-                    if (np > 1) pred(hi & 0xffff);
+                    pred(hi & 0xffff);
                     if (np > 2) pred(hi >> 16);
-                    for (uint32_t k = 3; k < np; ++k) pred(pred_ovf[i * ki + k]);
+                    if (np > 3) {
+                        const uint32_t blo = shfl(rec_b_lo, ti), bhi = shfl(rec_b_hi, ti);
+                        pred(blo & 0xffff);
+                        if (np > 4) pred(blo >> 16);
+                        if (np > 5) pred(bhi & 0xffff);
+                        if (np > 6) pred(bhi >> 16);
+                        for (uint32_t k = 7; k < np; ++k) pred(pred_ovf[i * ki + k]);
+                    }
                 }
                 /* in-row gap recurrence H[c] = max(H[c], H[c-1] + g), all in packed int16:
                  * two 8-long chains (low halves = columns 0..7, high halves = columns 8..15 of the block) */
@@ -521,36 +553,46 @@ struct PoaWarp {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) acc[r] = viaddmax_s16x2(bridge, gb[r], acc[r]);
                 /* warp max-plus scan of the lane totals (column 15 of each block), decay 16*g per lane */
+                int32_t chunk_carry = kNeg32;
+                if (multi) chunk_carry = cc_prev[i];
                 int32_t t = hi16(acc[7]);
-                t = viaddmax_s32(lane == 0 ? chunk_carry : kNeg32, 16 * g, t);
+                t = viaddmax_s32(lanem == 0 ? chunk_carry : kNeg32, 16 * g, t);
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) {
                     int32_t o = shfl_up(t, dd);
-                    t = viaddmax_s32(lane >= dd ? o : kNeg32, dd * 16 * g, t);
+                    t = viaddmax_s32(lanem >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * 16 * g, t);
                 }
                 int32_t carry = shfl_up(t, 1);
-                carry = lane == 0 ? chunk_carry : carry;
+                carry = lanem == 0 ? chunk_carry : carry;
                 carry = carry < negsafe ? negsafe : carry;
                 const uint32_t c2 = pack16(carry, carry);
 #pragma unroll
                 for (int r = 0; r < 8; ++r) acc[r] = viaddmax_s16x2(c2, gc[r], acc[r]);
-                chunk_carry = shfl(static_cast<int32_t>(hi16(acc[7])), 31);
                 Row8 out;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) out.r[r] = acc[r];
-                store_row_smem(myrow_s, ch, lane, out);
-                store_row_gmem(myrow_g, ch, lane, out);
-            }
-            syncwarp();
-            if (sink) {
-                int32_t sc = myrow_s[swz(len)];
-                if (sc > best) {
-                    best = sc;
-                    bi = i;
-                    nb = 1;
-                } else if (sc == best) {
-                    ++nb;
+                int16_t* myrow_s = ring + (i & rmask) * kChunkCols;
+                store_row_smem(myrow_s, 0, lane, out);
+                store_row_gmem(hrow + static_cast<uint64_t>(i) * lpa, 0, lane, out);
+                if (nch > 1 && lanem == 31) cc_cur[i] = static_cast<int16_t>(hi16(acc[7]));
+                syncwarp();
+                if (sink && ch == sink_ch) {  // warp-uniform
+                    int32_t sc = myrow_s[sink_e];
+                    if (sc > best) {
+                        best = sc;
+                        bi = i;
+                        nb = 1;
+                    } else if (sc == best) {
+                        ++nb;
+                    }
                 }
+            }
+            if (nch > 1) {
+                if (lane == 0) cc_cur[0] = static_cast<int16_t>((ch + 1) * kChunkCols * g - g);  // root row, last column
+                int16_t* tmp = cc_prev;
+                cc_prev = cc_cur;
+                cc_cur = tmp;
+                syncwarp();
             }
         }
         *best_row = bi;
@@ -631,7 +673,7 @@ struct PoaWarp {
         const uint16_t* ord = sub ? dp_order : order;
         uint32_t bestkey = 0xffffffffu;
         for (uint32_t r = 1 + lane; r <= nrows; r += 32) {
-            uint64_t rc = rec[r];
+            uint64_t rc = rec[r].a;
             if (!((rc >> 15) & 1)) continue;
             if (H[static_cast<uint64_t>(r) * lpa + perm(len)] != best) continue;
             uint32_t key = (static_cast<uint32_t>(srank[ord[r]]) << 16) | r;
@@ -660,9 +702,9 @@ struct PoaWarp {
         const uint16_t* ord = sub ? dp_order : order;
         const uint32_t kTileRows = P->tile_rows ? P->tile_rows : 96;
         int16_t* tile = reinterpret_cast<int16_t*>(smem);                                        // [kTileRows][32]
-        uint64_t* trec = reinterpret_cast<uint64_t*>(smem + kTileRows * kTileCols * 2);            // [kTileRows]
-        uint16_t* tnode = reinterpret_cast<uint16_t*>(smem + kTileRows * kTileCols * 2 + kTileRows * 8);
-        uint8_t* tseq = smem + kTileRows * kTileCols * 2 + kTileRows * 8 + ((kTileRows * 2 + 15) & ~15u);
+        Rec* trec = reinterpret_cast<Rec*>(smem + kTileRows * kTileCols * 2);                      // [kTileRows]
+        uint16_t* tnode = reinterpret_cast<uint16_t*>(smem + kTileRows * kTileCols * 2 + kTileRows * 16);
+        uint8_t* tseq = smem + kTileRows * kTileCols * 2 + kTileRows * 16 + ((kTileRows * 2 + 15) & ~15u);
         for (uint32_t c = lane; c < len; c += 32) tseq[c] = seq[c];  // the walk reads seq[j-1] every step
         uint32_t i = best_row, j = len;
         uint32_t t_top = 0, t_rows = 0, t_col0 = 0;  // tile covers ranks (t_top - t_rows, t_top], cols [t_col0, t_col0+32)
@@ -687,8 +729,8 @@ struct PoaWarp {
                 syncwarp();
             }
             const uint32_t q = t_top - i;
-            const uint64_t rc = trec[q];
-            const uint32_t lo = static_cast<uint32_t>(rc), hi = static_cast<uint32_t>(rc >> 32);
+            const Rec rc = trec[q];
+            const uint32_t lo = static_cast<uint32_t>(rc.a);
             const uint32_t node = tnode[q];
             const uint32_t cidx = lo & 0xff, np = (lo >> 8) & 0x7f;
             const uint32_t npe = np ? np : 1;
@@ -706,12 +748,8 @@ struct PoaWarp {
                 if (k < npe) {
                     if (np == 0)
                         p = 0;
-                    else if (k == 0)
-                        p = lo >> 16;
-                    else if (k == 1)
-                        p = hi & 0xffff;
-                    else if (k == 2)
-                        p = hi >> 16;
+                    else if (k < 7)
+                        p = rec_pred(rc, k);
                     else
                         p = pred_ovf[i * ki + k];
                     int32_t a = 0, b;
@@ -1199,20 +1237,22 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         }
         uint32_t lpa = (len + 1 + kChunkCols - 1) / kChunkCols * kChunkCols;
         /* shared memory split: profile rows first, the rest is the ring of recent DP rows */
-        uint32_t prof_bytes = W.ncodes * lpa * 2;
-        if (prof_bytes + 2 * lpa * 2 > P.smem_per_warp) {
+        /* shared memory (chunk-local): profile chunk | ring of the last R DP rows (R = power of two) */
+        const uint32_t prof_bytes = W.ncodes * kChunkCols * 2;
+        const uint32_t tile_rows = P.tile_rows ? P.tile_rows : 96;
+        const uint32_t tb_bytes = tile_rows * (64 + 16 + 2) + 16 + len;  // traceback: H tile | records | nodes | read
+        if (prof_bytes + 2 * kChunkCols * 2 > P.smem_per_warp || tb_bytes > P.smem_per_warp) {
             W.fail(kWinSeqTooLong);
             break;
         }
-        uint32_t ring_rows = (P.smem_per_warp - prof_bytes) / (lpa * 2);
+        uint32_t ring_rows = (P.smem_per_warp - prof_bytes) / (kChunkCols * 2);
         while (ring_rows & (ring_rows - 1)) ring_rows &= ring_rows - 1;  // largest power of two that fits
         W.prof = reinterpret_cast<int16_t*>(smem);
         W.ring = reinterpret_cast<int16_t*>(smem + prof_bytes);
         uint32_t pred_rows = W.build_program(nrows, sub);
-        W.build_profile(seq, len, lpa);
         uint32_t best_row, n_best;
         int32_t best;
-        W.dp(nrows, len, lpa, ring_rows, &best_row, &best, &n_best);
+        W.dp(seq, nrows, len, lpa, ring_rows, &best_row, &best, &n_best);
         if (n_best > 1) {
             best_row = W.resolve_sink_tie(nrows, len, lpa, best, sub);
             if (W.status != kWinOk) break;

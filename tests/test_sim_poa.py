@@ -15,6 +15,7 @@ CASES = {
     "shallow": dict(n=10, wlen=60, depth=3, err=0.2, partial_frac=0.3),
     "higherr_ties": dict(n=8, wlen=80, depth=14, err=0.3),
     "multichunk": dict(n=1, wlen=560, depth=4, err=0.08),
+    "threechunks": dict(n=1, wlen=1060, depth=3, err=0.05, partial_frac=0.3),
 }
 
 
@@ -55,7 +56,7 @@ def test_sim_scores(scores):
 def test_sim_tiny_ring_forces_far_predecessor_path():
     # 2 ring rows only: almost every predecessor that is not the previous row is fetched from the HBM copy
     ws = _mk("fullspan_small", seed=3)
-    _check(ws, smem=5 * 512 * 2 + 2 * 512 * 2)
+    _check(ws, smem=4 * 1024 + 2 * 1024, tile_rows=8)  # profile chunk | 2 ring rows
 
 
 def test_sim_tiny_traceback_tile_forces_out_of_tile_predecessors():
