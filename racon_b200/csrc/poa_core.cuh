@@ -464,11 +464,10 @@ struct PoaWarp {
         /* Row-synchronous: the whole warp computes one row (512-column chunk) at a time; lane l owns columns
          * 16l..16l+15.  Rows longer than 512 columns are done chunk by chunk (one pass over all rows per chunk,
          * the carry between chunks goes through a small per-row array), so shared memory only ever holds one
-         * chunk: the profile chunk and a ring of the last `ring_rows` rows (power of two). */
+         * chunk: the profile chunk and a ring of the last `ring_rows` rows. */
         const int32_t g = P->gap;
         const uint32_t g2 = pack16(g, g);
         const uint32_t nch = lpa / kChunkCols;
-        const uint32_t rmask = ring_rows - 1;
         const int32_t negsafe = -32768 - 16 * g;  // see kMaxGapInt16
         uint32_t gb[8], gc[8];  // bridge / carry offsets per register
 #pragma unroll
@@ -491,7 +490,9 @@ struct PoaWarp {
             const bool multi = ch > 0;
             uint32_t rec_a_lo = 0, rec_a_hi = 0, rec_b_lo = 0, rec_b_hi = 0;
             int16_t* hrow = H + static_cast<uint64_t>(ch) * kChunkCols;  // row i of this chunk = hrow + i*lpa
+            uint32_t myslot = 0;  // i % ring_rows, kept incrementally (any ring size, no division)
             for (uint32_t i = 1; i <= nrows; ++i) {
+                myslot = myslot + 1 == ring_rows ? 0u : myslot + 1;
                 const uint32_t ti = (i - 1) & 31u;
                 if (ti == 0) {
                     Rec t = rec[i + lane];  // rec[] is padded
@@ -510,9 +511,11 @@ struct PoaWarp {
                 const Row8 pf = load_row_smem(prof + cidx * kChunkCols, 0, lane);
                 auto pred = [&](uint32_t p) {
                     Row8 pr;
-                    if (i - p < ring_rows)  // warp-uniform
-                        pr = load_row_smem(ring + (p & rmask) * kChunkCols, 0, lane);
-                    else
+                    const uint32_t dist = i - p;
+                    if (dist < ring_rows) {  // warp-uniform
+                        const uint32_t slot = myslot >= dist ? myslot - dist : myslot + ring_rows - dist;
+                        pr = load_row_smem(ring + slot * kChunkCols, 0, lane);
+                    } else
                         pr = load_row_gmem(hrow + static_cast<uint64_t>(p) * lpa, 0, lane);
                     uint32_t left = shfl_up(pr.r[7], 1);  // hi half = previous lane's last column
                     int32_t lv = kNegDiag;
@@ -571,7 +574,7 @@ struct PoaWarp {
                 Row8 out;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) out.r[r] = acc[r];
-                int16_t* myrow_s = ring + (i & rmask) * kChunkCols;
+                int16_t* myrow_s = ring + myslot * kChunkCols;
                 store_row_smem(myrow_s, 0, lane, out);
                 store_row_gmem(hrow + static_cast<uint64_t>(i) * lpa, 0, lane, out);
                 if (nch > 1 && lanem == 31) cc_cur[i] = static_cast<int16_t>(hi16(acc[7]));
@@ -604,7 +607,7 @@ struct PoaWarp {
     /* ---------------------------------------------------------------- spoa's DFS order (graph.cpp:249-303)
      * Serial (lane 0).  With `sub`, runs on the subgraph exactly as spoa would on Graph::Subgraph():
      * nodes in ascending id, in-edges/aligned nodes filtered to members, original list orders kept. */
-    RP_DEV void spoa_sort(bool sub) {
+    RP_DEV void spoa_sort_hbm(bool sub) {
         for (uint32_t v = lane; v < N; v += 32) marks[v] = 0;  // bits0-1 mark, bit2 ignored
         syncwarp();
         if (lane == 0) {
@@ -657,6 +660,93 @@ struct PoaWarp {
                             }
                         } else {
                             marks[c] = static_cast<uint8_t>((marks[c] & 4) | 1);
+                        }
+                    }
+                    if (valid) --sp;
+                }
+            }
+        }
+        status = shfl(status, 0);
+        syncwarp();
+    }
+
+    /* Same DFS with the per-node state the walk touches on every step (marks, in-degree, aligned count) and
+     * the stack staged in shared memory (idle outside the DP): one HBM round trip per examined node (its
+     * in-edge tails and aligned list are fetched together) instead of five dependent ones. */
+    RP_DEV void spoa_sort(bool sub) {
+        const uint32_t npad = (N + 15) & ~15u;
+        if (ki > 31 || ka != 8 || 2 * npad + 512 > smem_bytes) {
+            spoa_sort_hbm(sub);
+            return;
+        }
+        uint8_t* smk = smem;          // bits0-1 mark, bit2 ignored, bit3 member
+        uint8_t* sme = smem + npad;   // in_cnt | al_cnt << 5
+        uint16_t* sst = reinterpret_cast<uint16_t*>(smem + 2 * npad);
+        const uint32_t cap = (smem_bytes - 2 * npad) / 2;
+        for (uint32_t v = lane; v < N; v += 32) {
+            smk[v] = (!sub || member[v]) ? 8 : 0;
+            sme[v] = static_cast<uint8_t>(in_cnt[v] | (al_cnt[v] << 5));
+        }
+        syncwarp();
+        if (lane == 0) {
+            uint32_t out = 0, sp = 0;
+            for (uint32_t root = 0; root < N && status == kWinOk; ++root) {
+                if (smk[root] != 8) continue;  // not a member, or already marked
+                sst[sp++] = static_cast<uint16_t>(root);
+                while (sp > 0) {
+                    const uint32_t c = sst[sp - 1];
+                    bool valid = true;
+                    const uint8_t mk = smk[c];
+                    if ((mk & 3) != 2) {
+                        const uint32_t ni = sme[c] & 31u, na = sme[c] >> 5;
+                        const uint64_t t4 = *reinterpret_cast<const uint64_t*>(in_tail + c * ki);
+                        uint64_t a_lo = 0, a_hi = 0;
+                        if (na) {
+                            const U4 a8 = *reinterpret_cast<const U4*>(al + c * ka);
+                            a_lo = a8.x | (static_cast<uint64_t>(a8.y) << 32);
+                            a_hi = a8.z | (static_cast<uint64_t>(a8.w) << 32);
+                        }
+                        if (sp + ni + na > cap) {
+                            fail(kWinStackLimit);
+                            break;
+                        }
+                        for (uint32_t k = 0; k < ni; ++k) {
+                            const uint32_t t = k < 4 ? (static_cast<uint32_t>(t4 >> (16 * k)) & 0xffffu)
+                                                     : in_tail[c * ki + k];
+                            const uint8_t mt = smk[t];
+                            if (!(mt & 8)) continue;
+                            if ((mt & 3) != 2) {
+                                sst[sp++] = static_cast<uint16_t>(t);
+                                valid = false;
+                            }
+                        }
+                        if (!(mk & 4)) {
+                            for (uint32_t k = 0; k < na; ++k) {
+                                const uint32_t a = static_cast<uint32_t>((k < 4 ? a_lo : a_hi) >> (16 * (k & 3))) & 0xffffu;
+                                const uint8_t ma = smk[a];
+                                if (!(ma & 8)) continue;
+                                if ((ma & 3) != 2) {
+                                    sst[sp++] = static_cast<uint16_t>(a);
+                                    smk[a] = ma | 4;
+                                    valid = false;
+                                }
+                            }
+                        }
+                        if (valid) {
+                            const uint8_t now = smk[c];
+                            smk[c] = static_cast<uint8_t>((now & 12) | 2);
+                            if (!(now & 4)) {
+                                srank[c] = static_cast<uint16_t>(out);
+                                sorder[out++] = static_cast<uint16_t>(c);
+                                for (uint32_t k = 0; k < na; ++k) {
+                                    const uint32_t a = static_cast<uint32_t>((k < 4 ? a_lo : a_hi) >> (16 * (k & 3))) & 0xffffu;
+                                    if (!(smk[a] & 8)) continue;
+                                    srank[a] = static_cast<uint16_t>(out);
+                                    sorder[out++] = static_cast<uint16_t>(a);
+                                }
+                            }
+                        } else {
+                            smk[c] = static_cast<uint8_t>((smk[c] & 12) | 1);
                         }
                     }
                     if (valid) --sp;
@@ -1237,7 +1327,7 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         }
         uint32_t lpa = (len + 1 + kChunkCols - 1) / kChunkCols * kChunkCols;
         /* shared memory split: profile rows first, the rest is the ring of recent DP rows */
-        /* shared memory (chunk-local): profile chunk | ring of the last R DP rows (R = power of two) */
+        /* shared memory (chunk-local): profile chunk | ring of the last R DP rows */
         const uint32_t prof_bytes = W.ncodes * kChunkCols * 2;
         const uint32_t tile_rows = P.tile_rows ? P.tile_rows : 96;
         const uint32_t tb_bytes = tile_rows * (64 + 16 + 2) + 16 + len;  // traceback: H tile | records | nodes | read
@@ -1246,7 +1336,7 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
             break;
         }
         uint32_t ring_rows = (P.smem_per_warp - prof_bytes) / (kChunkCols * 2);
-        while (ring_rows & (ring_rows - 1)) ring_rows &= ring_rows - 1;  // largest power of two that fits
+        if (ring_rows > 32) ring_rows = 32;
         W.prof = reinterpret_cast<int16_t*>(smem);
         W.ring = reinterpret_cast<int16_t*>(smem + prof_bytes);
         uint32_t pred_rows = W.build_program(nrows, sub);

@@ -102,27 +102,47 @@ struct PackedBatch {
     uint32_t n_added() const { return static_cast<uint32_t>(gpu_index.size()); }
     uint32_t n_gpu() const { return static_cast<uint32_t>(win_flags.size); }
 
-    /* One window; same argument meaning as rp_poa_add_window (include/racon_b200.h). */
-    int add(uint32_t n_seq, const char* const* seq, const uint32_t* len, const char* const* qual,
-            const uint32_t* begin, const uint32_t* end, int window_type, int trim) {
-        if (n_seq == 0 || !seq || !len || !seq[0] || len[0] == 0) return kPackInvalid;  // window.cpp:19-23
+    /* A window is packed in three steps so that the bulk path can run the byte-heavy ones on many host
+     * threads: prepare() (validation, layer order, alphabet — no shared state), commit() (serial: reserves
+     * space and writes the per-sequence / per-window metadata), fill() (copies bases and weights). */
+    struct Prep {
+        int status = kPackOk;          // kPackOk or kPackInvalid
+        int kind = 0;                  // 0 GPU window, -1 trivial (< 3 sequences), -2 alphabet limit
+        uint32_t blen = 0;
+        uint64_t tot = 0;
+        uint64_t alpha = 0;
+        std::vector<uint32_t> order;   // caller's sequence indices in processing order (backbone first)
+        std::vector<uint8_t> full;     // per entry of `order`: full-span flag
+        uint64_t base_off = 0;         // set by commit(): where fill() writes
+    };
+
+    static void prepare(Prep& pr, uint32_t n_seq, const char* const* seq, const uint32_t* len, const uint32_t* begin,
+                        const uint32_t* end, uint32_t max_seq_len) {
+        pr = Prep();
+        if (n_seq == 0 || !seq || !len || !seq[0] || len[0] == 0 || len[0] > max_seq_len) {  // window.cpp:19-23
+            pr.status = kPackInvalid;
+            return;
+        }
         const uint32_t blen = len[0];
-        if (blen > max_seq_len) return kPackInvalid;
+        pr.blen = blen;
         /* Window::add_layer, window.cpp:42-63 */
         std::vector<uint32_t> kept;
+        kept.reserve(n_seq);
         kept.push_back(0);
         uint64_t tot = blen;
         for (uint32_t k = 1; k < n_seq; ++k) {
             if (len[k] == 0 || begin[k] == end[k]) continue;
-            if (!seq[k] || begin[k] >= end[k] || begin[k] > blen || end[k] > blen) return kPackInvalid;
-            if (len[k] > max_seq_len) return kPackInvalid;
+            if (!seq[k] || begin[k] >= end[k] || begin[k] > blen || end[k] > blen || len[k] > max_seq_len) {
+                pr.status = kPackInvalid;
+                return;
+            }
             kept.push_back(k);
             tot += len[k];
         }
+        pr.tot = tot;
         if (kept.size() < 3) {  // window.cpp:68-71
-            gpu_index.push_back(-1);
-            trivial.emplace_back(seq[0], blen);
-            return kPackOk;
+            pr.kind = -1;
+            return;
         }
         /* layer order, window.cpp:79-86 — the same std::sort call on the same element type */
         std::vector<uint32_t> rank(kept.size());
@@ -130,70 +150,105 @@ struct PackedBatch {
         std::sort(rank.begin() + 1, rank.end(),
                   [&](uint32_t l, uint32_t r) { return begin[kept[l]] < begin[kept[r]]; });
         const uint32_t offset = static_cast<uint32_t>(0.01 * blen);  // window.cpp:88
-        for (uint32_t i = 1; i < rank.size(); ++i) {
+        pr.order.resize(rank.size());
+        pr.full.resize(rank.size());
+        for (uint32_t i = 0; i < rank.size(); ++i) {
             uint32_t k = kept[rank[i]];
-            bool full = begin[k] < offset && end[k] > blen - offset;
-            if (!full && end[k] >= blen) return kPackInvalid;  // Subgraph(begin, end) needs backbone node `end`
-        }
-        if (bases.size + tot > max_bases || n_gpu() >= max_windows) return kPackFull;
-
-        /* alphabet: distinct characters in first-seen order */
-        uint64_t alpha = 0;
-        uint32_t ncodes = 0;
-        bool seen[256] = {false};
-        bool too_many = false;
-        for (uint32_t i = 0; i < rank.size() && !too_many; ++i) {
-            uint32_t k = kept[rank[i]];
-            for (uint32_t j = 0; j < len[k]; ++j) {
-                uint8_t c = static_cast<uint8_t>(seq[k][j]);
-                if (c == 0) return kPackInvalid;
-                if (!seen[c]) {
-                    seen[c] = true;
-                    if (ncodes == 8) {
-                        too_many = true;
-                        break;
-                    }
-                    alpha |= static_cast<uint64_t>(c) << (8 * ncodes++);
-                }
+            bool full = i > 0 && begin[k] < offset && end[k] > blen - offset;
+            if (i > 0 && !full && end[k] >= blen) {  // Subgraph(begin, end) needs backbone node `end`
+                pr.status = kPackInvalid;
+                return;
             }
+            pr.order[i] = k;
+            pr.full[i] = full ? 1 : 0;
         }
-        if (too_many) {
+        /* alphabet: the distinct characters of the window (any order: only equality matters on the device) */
+        uint8_t seen[256];
+        std::memset(seen, 0, sizeof(seen));
+        for (uint32_t i = 0; i < pr.order.size(); ++i) {
+            const uint8_t* sq = reinterpret_cast<const uint8_t*>(seq[pr.order[i]]);
+            const uint32_t n = len[pr.order[i]];
+            for (uint32_t j = 0; j < n; ++j) seen[sq[j]] = 1;
+        }
+        if (seen[0]) {
+            pr.status = kPackInvalid;
+            return;
+        }
+        uint32_t ncodes = 0;
+        for (uint32_t c = 1; c < 256; ++c) {
+            if (!seen[c]) continue;
+            if (ncodes == 8) {
+                pr.kind = -2;
+                return;
+            }
+            pr.alpha |= static_cast<uint64_t>(c) << (8 * ncodes++);
+        }
+    }
+
+    /* serial; returns kPackOk / kPackFull / kPackNoMem (or pr.status when the window is malformed) */
+    int commit(Prep& pr, const char* const* seq, const uint32_t* len, const uint32_t* begin, const uint32_t* end,
+               int window_type, int trim) {
+        if (pr.status != kPackOk) return pr.status;
+        if (pr.kind == -1) {
+            gpu_index.push_back(-1);
+            trivial.emplace_back(seq[0], pr.blen);
+            return kPackOk;
+        }
+        if (pr.kind == -2) {
             gpu_index.push_back(-2);
             trivial.emplace_back();
             return kPackOk;
         }
-
-        uint8_t* b = bases.extend(tot);
-        uint8_t* w = weights.extend(tot);
-        if (!b || !w) return kPackNoMem;
+        if (bases.size + pr.tot > max_bases || n_gpu() >= max_windows) return kPackFull;
+        pr.base_off = bases.size;
+        if (!bases.extend(pr.tot) || !weights.extend(pr.tot)) return kPackNoMem;
         uint32_t off = seq_off.data[seq_off.size - 1];
-        for (uint32_t i = 0; i < rank.size(); ++i) {
-            uint32_t k = kept[rank[i]];
-            std::memcpy(b, seq[k], len[k]);
-            const char* q = qual ? qual[k] : nullptr;
-            if (q) {
-                for (uint32_t j = 0; j < len[k]; ++j) w[j] = static_cast<uint8_t>(q[j] - 33);
-            } else {
-                std::memset(w, i == 0 ? 0 : 1, len[k]);  // dummy '!' backbone => 0; layer without quality => 1
-            }
-            b += len[k];
-            w += len[k];
+        for (uint32_t i = 0; i < pr.order.size(); ++i) {
+            uint32_t k = pr.order[i];
             off += len[k];
-            bool full = i > 0 && begin[k] < offset && end[k] > blen - offset;
             if (!seq_off.push(off) || !seq_begin.push(i ? begin[k] : 0) || !seq_end.push(i ? end[k] : 0) ||
-                !seq_flags.push(full ? 1 : 0))
+                !seq_flags.push(pr.full[i]))
                 return kPackNoMem;
         }
-        uint32_t cap = 2 * blen + 64;
+        uint32_t cap = 2 * pr.blen + 64;
         if (!win_first.push(static_cast<uint32_t>(seq_off.size - 1)) ||
-            !win_flags.push((window_type == 1 && trim) ? 1 : 0) || !win_alpha.push(alpha) ||
+            !win_flags.push((window_type == 1 && trim) ? 1 : 0) || !win_alpha.push(pr.alpha) ||
             !out_off.push(static_cast<uint32_t>(out_total)) || !out_cap.push(cap))
             return kPackNoMem;
         out_total += cap;
         gpu_index.push_back(static_cast<int32_t>(n_gpu() - 1));
         trivial.emplace_back();
-        cost.push_back(static_cast<uint32_t>(tot));
+        cost.push_back(static_cast<uint32_t>(pr.tot));
         return kPackOk;
+    }
+
+    /* thread-safe for distinct windows once every commit() of the batch is done (buffers no longer move) */
+    void fill(const Prep& pr, const char* const* seq, const uint32_t* len, const char* const* qual) {
+        if (pr.status != kPackOk || pr.kind != 0) return;
+        uint8_t* b = bases.data + pr.base_off;
+        uint8_t* w = weights.data + pr.base_off;
+        for (uint32_t i = 0; i < pr.order.size(); ++i) {
+            uint32_t k = pr.order[i];
+            std::memcpy(b, seq[k], len[k]);
+            const char* q = qual ? qual[k] : nullptr;
+            if (q) {
+                for (uint32_t j = 0; j < len[k]; ++j) w[j] = static_cast<uint8_t>(q[j] - 33);  // graph.cpp:141-143
+            } else {
+                std::memset(w, i == 0 ? 0 : 1, len[k]);  // dummy '!' backbone => 0; layer without quality => 1
+            }
+            b += len[k];
+            w += len[k];
+        }
+    }
+
+    /* One window; same argument meaning as rp_poa_add_window (include/racon_b200.h). */
+    int add(uint32_t n_seq, const char* const* seq, const uint32_t* len, const char* const* qual,
+            const uint32_t* begin, const uint32_t* end, int window_type, int trim) {
+        Prep pr;
+        prepare(pr, n_seq, seq, len, begin, end, max_seq_len);
+        int r = commit(pr, seq, len, begin, end, window_type, trim);
+        if (r == kPackOk) fill(pr, seq, len, qual);
+        return r;
     }
 
     /* processing order: most expensive windows first (persistent warps pull from this queue) */

@@ -8,9 +8,13 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <functional>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "poa_core.cuh"
@@ -63,8 +67,10 @@ struct DevBuf {
 };
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kBlocksPerSm = 4;
 
+/* Persistent kernel: each warp is an independent worker that pulls windows from an atomic queue.
+ * Compiled for several occupancy points (blocks per SM -> register cap); RP_BLOCKS_PER_SM selects one. */
+template <int kBlocksPerSm>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kernel(rp::PoaParams P) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int warp = threadIdx.x >> 5;
@@ -77,6 +83,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kern
         q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= P.n_windows) break;
         rp::poa_window(P, P.queue[q], slot, smem);
+    }
+}
+
+typedef void (*PoaKernel)(rp::PoaParams);
+PoaKernel pick_kernel(int blocks_per_sm) {
+    switch (blocks_per_sm) {
+        case 3: return rp_poa_kernel<3>;
+        case 5: return rp_poa_kernel<5>;
+        case 6: return rp_poa_kernel<6>;
+        case 8: return rp_poa_kernel<8>;
+        default: return rp_poa_kernel<4>;
     }
 }
 
@@ -99,6 +116,8 @@ struct rp_poa {
     uint32_t workers = 0;
     int grid = 0;
     uint32_t smem_block = 0;
+    PoaKernel kernel = nullptr;
+    int blocks_per_sm = 4;
     bool uploaded = false, launched = false, downloaded = false, synced = false;
     bool counters = false;
     uint64_t launches = 0, last_h2d = 0, last_d2h = 0;
@@ -173,17 +192,22 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     p->P.mismatch = mismatch;
     p->P.gap = gap;
 
-    /* launch shape: persistent blocks of 4 independent warps, 4 blocks per SM (16 windows in flight per SM) */
+    /* launch shape: persistent blocks of 4 independent warps, kBlocksPerSm blocks per SM */
+    int bps = 4;
+    if (const char* e_bps = getenv("RP_BLOCKS_PER_SM")) bps = atoi(e_bps);
+    if (bps != 3 && bps != 5 && bps != 6 && bps != 8) bps = 4;
+    p->blocks_per_sm = bps;
+    p->kernel = pick_kernel(bps);
     uint32_t smem_per_sm = static_cast<uint32_t>(prop.sharedMemPerMultiprocessor);
-    uint32_t per_block = smem_per_sm / kBlocksPerSm - 1024;                     // 1 KB reserved per block
+    uint32_t per_block = smem_per_sm / bps - 1024;                              // 1 KB reserved per block
     if (per_block > prop.sharedMemPerBlockOptin) per_block = static_cast<uint32_t>(prop.sharedMemPerBlockOptin);
-    uint32_t per_warp = (per_block / kWarpsPerBlock) & ~1023u;
+    uint32_t per_warp = (per_block / kWarpsPerBlock) & ~255u;
     p->P.smem_per_warp = per_warp;
     p->smem_block = per_warp * kWarpsPerBlock;
-    e = cudaFuncSetAttribute(rp_poa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_block));
+    e = cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_block));
     int occ = 0;
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp_poa_kernel, kWarpsPerBlock * 32, p->smem_block);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->kernel, kWarpsPerBlock * 32, p->smem_block);
     if (e != cudaSuccess || occ < 1) {
         rp_poa_destroy(p);
         return fail(RP_ERR_CUDA, std::string("kernel configuration: ") + cudaGetErrorString(e));
@@ -258,26 +282,57 @@ rp_status rp_poa_add_window_set(rp_poa* p, uint32_t first, uint32_t count, const
     if (!p || !bases || !seq_off || !win_first || !seq_begin || !seq_end)
         return fail(RP_ERR_INVALID, "null argument");
     if (p->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
-    std::vector<const char*> sp, qp;
-    std::vector<uint32_t> ln;
+    if (added) *added = 0;
+    if (count == 0) return RP_OK;
+    /* per-window pointer tables (the flat set stores offsets) */
+    const uint32_t sbase = win_first[first];
+    const uint32_t nseq = win_first[first + count] - sbase;
+    std::vector<const char*> sp(nseq), qp(nseq);
+    std::vector<uint32_t> ln(nseq);
+    const bool any_q = quals && seq_has_qual;
+    unsigned hw = std::thread::hardware_concurrency();
+    const unsigned nthreads = std::max(1u, std::min(hw ? hw : 1u, std::min(32u, count / 64 + 1)));
+    std::vector<rp::PackedBatch::Prep> preps(count);
+    const uint32_t max_len = p->batch.max_seq_len;
+    auto prep_range = [&](uint32_t a, uint32_t b) {
+        for (uint32_t w = a; w < b; ++w) {
+            const uint32_t s0 = win_first[first + w], s1 = win_first[first + w + 1];
+            for (uint32_t s = s0; s < s1; ++s) {
+                sp[s - sbase] = bases + seq_off[s];
+                qp[s - sbase] = (any_q && seq_has_qual[s]) ? quals + seq_off[s] : nullptr;
+                ln[s - sbase] = static_cast<uint32_t>(seq_off[s + 1] - seq_off[s]);
+            }
+            rp::PackedBatch::prepare(preps[w], s1 - s0, sp.data() + (s0 - sbase), ln.data() + (s0 - sbase),
+                                     seq_begin + s0, seq_end + s0, max_len);
+        }
+    };
+    auto run_parallel = [&](const std::function<void(uint32_t, uint32_t)>& fn, uint32_t n) {
+        if (nthreads <= 1 || n < 128) {
+            fn(0, n);
+            return;
+        }
+        std::vector<std::thread> pool;
+        const uint32_t step = (n + nthreads - 1) / nthreads;
+        for (uint32_t a = 0; a < n; a += step) pool.emplace_back(fn, a, std::min(n, a + step));
+        for (auto& t : pool) t.join();
+    };
+    run_parallel(prep_range, count);
+    /* serial commit: reserves space, writes metadata; stops at the first window that does not fit */
     uint32_t n = 0;
     rp_status st = RP_OK;
-    for (uint32_t w = first; w < first + count; ++w) {
-        uint32_t s0 = win_first[w], s1 = win_first[w + 1];
-        sp.clear();
-        qp.clear();
-        ln.clear();
-        for (uint32_t s = s0; s < s1; ++s) {
-            sp.push_back(bases + seq_off[s]);
-            bool q = quals && seq_has_qual && seq_has_qual[s];
-            qp.push_back(q ? quals + seq_off[s] : nullptr);
-            ln.push_back(static_cast<uint32_t>(seq_off[s + 1] - seq_off[s]));
-        }
-        st = map_pack(p->batch.add(s1 - s0, sp.data(), ln.data(), qp.data(), seq_begin + s0, seq_end + s0,
-                                   win_type ? win_type[w] : 1, trim));
+    for (; n < count; ++n) {
+        const uint32_t s0 = win_first[first + n];
+        st = map_pack(p->batch.commit(preps[n], sp.data() + (s0 - sbase), ln.data() + (s0 - sbase), seq_begin + s0,
+                                      seq_end + s0, win_type ? win_type[first + n] : 1, trim));
         if (st != RP_OK) break;
-        ++n;
     }
+    auto fill_range = [&](uint32_t a, uint32_t b) {
+        for (uint32_t w = a; w < b; ++w) {
+            const uint32_t s0 = win_first[first + w];
+            p->batch.fill(preps[w], sp.data() + (s0 - sbase), ln.data() + (s0 - sbase), qp.data() + (s0 - sbase));
+        }
+    };
+    run_parallel(fill_range, n);
     if (added) *added = n;
     return st == RP_BATCH_FULL && n > 0 ? RP_OK : st;
 }
@@ -350,7 +405,7 @@ rp_status rp_poa_launch(rp_poa* p) {
     if (p->P.n_windows > 0) {
         RP_CUDA(cudaMemsetAsync(p->d_head.p, 0, 4, p->stream));
         p->P.stats = p->counters ? static_cast<uint64_t*>(p->d_stats.p) : nullptr;
-        rp_poa_kernel<<<p->grid, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(p->P);
+        p->kernel<<<p->grid, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(p->P);
         RP_CUDA(cudaGetLastError());
         p->launches += 1;
     }

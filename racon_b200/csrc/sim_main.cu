@@ -37,6 +37,29 @@ void warp_entry(void* arg) {
 
 extern "C" {
 
+/* packing only (host-side cost of rp_poa_add_window): returns number of GPU windows packed */
+int rp_sim_pack_only(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
+                     const uint8_t* seq_has_qual, const uint32_t* seq_begin, const uint32_t* seq_end,
+                     const uint32_t* win_first, const uint8_t* win_type, int trim) {
+    rp::PackedBatch pb(&kSimAlloc);
+    std::vector<const char*> sp, qp;
+    std::vector<uint32_t> ln;
+    for (uint32_t w = 0; w < n_windows; ++w) {
+        uint32_t s0 = win_first[w], s1 = win_first[w + 1];
+        sp.clear(); qp.clear(); ln.clear();
+        for (uint32_t s = s0; s < s1; ++s) {
+            sp.push_back(bases + seq_off[s]);
+            bool q = quals && seq_has_qual && seq_has_qual[s];
+            qp.push_back(q ? quals + seq_off[s] : nullptr);
+            ln.push_back(static_cast<uint32_t>(seq_off[s + 1] - seq_off[s]));
+        }
+        int r = pb.add(s1 - s0, sp.data(), ln.data(), qp.data(), seq_begin + s0, seq_end + s0, win_type[w], trim);
+        if (r != rp::kPackOk) return -100 + r;
+    }
+    pb.build_queue();
+    return static_cast<int>(pb.n_gpu());
+}
+
 /* Flat window set in, consensus out.  limits: {nmax, lmax, ki, ka, smem_per_warp, tile_rows}.  Returns 0 or <0. */
 int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
                const uint8_t* seq_has_qual, const uint32_t* seq_begin, const uint32_t* seq_end,

@@ -65,6 +65,12 @@ def test_sim_tiny_traceback_tile_forces_out_of_tile_predecessors():
     _check(_mk("partial", seed=8), tile_rows=2)
 
 
+def test_sim_hbm_fallback_of_the_order_dfs():
+    # ka != 8 selects the HBM-resident variant of the spoa-order DFS
+    _check(_mk("higherr_ties", seed=21), ka=7)
+    _check(_mk("partial", seed=4), ka=9)
+
+
 def test_sim_no_trim_and_trivial():
     _check(_mk("partial", seed=9), trim=False)
     from racon_b200 import windows
