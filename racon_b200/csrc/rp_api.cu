@@ -122,6 +122,13 @@ struct rp_poa {
     bool counters = false;
     uint64_t launches = 0, last_h2d = 0, last_d2h = 0;
     int banded = 0;
+    /* escalation pass for windows that exceeded a device limit (never a CPU re-run) */
+    DevBuf d_scratch_big, d_queue_big;
+    rp::PoaLimits lim_big;
+    rp::SlotLayout lay_big;
+    uint32_t workers_big = 0;
+    uint64_t escalated = 0;
+    size_t mem_budget = 0;
 
     rp_poa() : batch(&kPinned), h_cons(&kPinned), h_cov(&kPinned), h_len(&kPinned), h_status(&kPinned) {
         std::memset(&P, 0, sizeof(P));
@@ -230,7 +237,16 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
         return fail(RP_ERR_NOMEM, std::string("scratch allocation: ") + cudaGetErrorString(e));
     }
     cudaMemsetAsync(p->d_stats.p, 0, 256, p->stream);
-    p->batch.max_seq_len = lim.lmax > lim.nmax ? lim.nmax : 65000;
+    p->batch.max_seq_len = 65000;
+    p->mem_budget = mem_bytes;
+    p->lim_big = lim;
+    p->lim_big.nmax = std::min<uint32_t>(65000, lim.nmax * 8);
+    p->lim_big.lmax = std::min<uint32_t>(16000, lim.lmax * 4);
+    p->lim_big.lp = (p->lim_big.lmax + 1 + rp::kChunkCols - 1) / rp::kChunkCols * rp::kChunkCols;
+    p->lim_big.ki = 96;
+    p->lim_big.ka = 8;
+    p->lim_big.stack_cap = p->lim_big.nmax * 6 + 64;
+    p->lay_big = rp::make_layout(p->lim_big);
     *out = p;
     return RP_OK;
 }
@@ -241,7 +257,8 @@ void rp_poa_destroy(rp_poa* p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     DevBuf* bufs[] = {&p->d_bases, &p->d_weights, &p->d_seq_flags, &p->d_win_flags, &p->d_seq_off, &p->d_seq_begin,
                       &p->d_seq_end, &p->d_win_first, &p->d_out_off, &p->d_out_cap, &p->d_queue, &p->d_win_alpha,
-                      &p->d_cons, &p->d_cov, &p->d_len, &p->d_status, &p->d_head, &p->d_stats, &p->d_scratch};
+                      &p->d_cons, &p->d_cov, &p->d_len, &p->d_status, &p->d_head, &p->d_stats, &p->d_scratch,
+                      &p->d_scratch_big, &p->d_queue_big};
     for (DevBuf* b : bufs) b->release();
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -444,11 +461,63 @@ rp_status rp_poa_run(rp_poa* p) {
     return rp_poa_download(p);
 }
 
+/* Windows whose graph outgrew the default per-window limits (very deep coverage, very long layers) are run
+ * again ON THE GPU with 8x the node budget, 4x the layer length and 96 in-edge slots, on a smaller set of
+ * workers (the reference hands such windows to the CPU, cudapolisher.cpp:354-370; this library has no CPU path). */
+static rp_status escalate(rp_poa* p) {
+    const uint32_t n = p->P.n_windows;
+    std::vector<uint32_t> redo;
+    for (uint32_t w = 0; w < n; ++w) {
+        uint32_t st = p->h_status.data[w];
+        if (st == rp::kWinNodeLimit || st == rp::kWinEdgeLimit || st == rp::kWinSeqTooLong || st == rp::kWinStackLimit)
+            redo.push_back(w);
+    }
+    if (redo.empty()) return RP_OK;
+    if (p->workers_big == 0) {
+        uint64_t fit = (p->mem_budget / 4) / p->lay_big.bytes;
+        uint64_t workers = std::min<uint64_t>(p->workers, fit) / kWarpsPerBlock * kWarpsPerBlock;
+        if (workers < kWarpsPerBlock) return RP_OK;  // no room: the soft status stays
+        cudaError_t e = p->d_scratch_big.reserve(workers * p->lay_big.bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return RP_OK;
+        }
+        p->workers_big = static_cast<uint32_t>(workers);
+    }
+    RP_CUDA(p->d_queue_big.reserve(redo.size() * 4));
+    RP_CUDA(cudaMemcpyAsync(p->d_queue_big.p, redo.data(), redo.size() * 4, cudaMemcpyHostToDevice, p->stream));
+    RP_CUDA(cudaMemsetAsync(p->d_head.p, 0, 4, p->stream));
+    rp::PoaParams P = p->P;
+    P.n_windows = static_cast<uint32_t>(redo.size());
+    P.queue = static_cast<const uint32_t*>(p->d_queue_big.p);
+    P.scratch = static_cast<uint8_t*>(p->d_scratch_big.p);
+    P.lim = p->lim_big;
+    P.lay = p->lay_big;
+    P.stats = nullptr;
+    uint32_t blocks = std::min<uint32_t>(p->workers_big / kWarpsPerBlock,
+                                         (static_cast<uint32_t>(redo.size()) + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    p->kernel<<<blocks, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(P);
+    RP_CUDA(cudaGetLastError());
+    p->launches += 1;
+    p->escalated += redo.size();
+    size_t tot = p->batch.out_total;
+    RP_CUDA(cudaMemcpyAsync(p->h_cons.data, p->d_cons.p, tot, cudaMemcpyDeviceToHost, p->stream));
+    RP_CUDA(cudaMemcpyAsync(p->h_cov.data, p->d_cov.p, tot * 2, cudaMemcpyDeviceToHost, p->stream));
+    RP_CUDA(cudaMemcpyAsync(p->h_len.data, p->d_len.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    RP_CUDA(cudaMemcpyAsync(p->h_status.data, p->d_status.p, n * 4, cudaMemcpyDeviceToHost, p->stream));
+    RP_CUDA(cudaStreamSynchronize(p->stream));
+    return RP_OK;
+}
+
 rp_status rp_poa_sync(rp_poa* p) {
     if (!p) return fail(RP_ERR_INVALID, "null object");
     RP_CUDA(cudaSetDevice(p->device));
     RP_CUDA(cudaStreamSynchronize(p->stream));
-    if (p->downloaded) p->synced = true;
+    if (p->downloaded && !p->synced) {
+        rp_status s = escalate(p);
+        if (s != RP_OK) return s;
+        p->synced = true;
+    }
     return RP_OK;
 }
 

@@ -114,6 +114,25 @@ def test_gpu_full_size_properties():
     assert 480 < lens.mean() < 520
 
 
+def test_gpu_escalation_of_deep_and_long_windows():
+    """Windows that outgrow the default per-window limits (3064 nodes / 1023-base layers at w=500) are re-run on
+    the GPU with larger limits — never on the CPU — and still match the oracle."""
+    deep = util.make_set(5, 3, wlen=500, depth=150, err=0.15)          # > 3064 graph nodes
+    long_layers = util.make_set(6, 3, wlen=500, depth=12, err=0.05)
+    wins = [deep.window(i) for i in range(3)]
+    # one layer much longer than the window (e.g. a large insertion): 1400 bases over a 500-base backbone
+    rng = np.random.default_rng(1)
+    w0 = long_layers.window(0)
+    big = bytes(b"ACGT"[i] for i in rng.integers(4, size=1400))
+    w0.append((big, None, 0, len(w0[0][0]) - 1))
+    wins.append(w0)
+    ws = windows.from_lists(wins)
+    cons, pol, st = api.consensus(ws)
+    ora, opol, _ = ob.oracle_consensus(ws, threads=os.cpu_count() or 4)
+    assert (st == 0).all(), st
+    assert cons == ora and (pol == opol).all()
+
+
 def test_gpu_batch_object_protocol():
     """add-until-full / run / fetch / reset, state errors, per-window status."""
     ws = _mk("shallow", seed=3)

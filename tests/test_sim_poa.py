@@ -71,6 +71,12 @@ def test_sim_hbm_fallback_of_the_order_dfs():
     _check(_mk("partial", seed=4), ka=9)
 
 
+def test_sim_escalation_limits_configuration():
+    # the limits of the GPU escalation pass (96 in-edge slots, large node budget) on ordinary windows
+    _check(_mk("higherr_ties", seed=2), nmax=20000, lmax=4095, ki=96)
+    _check(_mk("partial_qual", seed=2), nmax=20000, lmax=4095, ki=96)
+
+
 def test_sim_no_trim_and_trivial():
     _check(_mk("partial", seed=9), trim=False)
     from racon_b200 import windows
