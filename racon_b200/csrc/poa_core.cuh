@@ -505,47 +505,57 @@ struct PoaWarp {
                 const uint32_t cidx = lo & 0xff;
                 const uint32_t np = (lo >> 8) & 0x7f;
                 const bool sink = (lo >> 15) & 1;
-                uint32_t acc[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) acc[r] = 0x80008000u;  // max identity; never an addend
                 const Row8 pf = load_row_smem(prof + cidx * kChunkCols, 0, lane);
-                auto pred = [&](uint32_t p) {
-                    Row8 pr;
+                /* max over predecessors distributes over both terms of the recurrence:
+                 *   max_p(H[p][c-1] + s(c), H[p][c] + g) = max(max_p H[p][c-1] + s(c), max_p H[p][c] + g),
+                 * so predecessor rows are first combined with a packed max (8 ops per extra predecessor) and the
+                 * diagonal/vertical update (16 DPX ops, one shuffle) runs once per row */
+                Row8 pm;
+                int32_t lvm = kNegDiag;
+                auto load_pred = [&](uint32_t p, Row8& pr) {
                     const uint32_t dist = i - p;
                     if (dist < ring_rows) {  // warp-uniform
                         const uint32_t slot = myslot >= dist ? myslot - dist : myslot + ring_rows - dist;
                         pr = load_row_smem(ring + slot * kChunkCols, 0, lane);
                     } else
                         pr = load_row_gmem(hrow + static_cast<uint64_t>(p) * lpa, 0, lane);
-                    uint32_t left = shfl_up(pr.r[7], 1);  // hi half = previous lane's last column
-                    int32_t lv = kNegDiag;
-                    if (multi) lv = cc_prev[p];
-                    left = lanem == 0 ? (static_cast<uint32_t>(lv) << 16) : left;
-                    /* diagonal operand of register 0 = (column -1 of the block, column 7) */
-                    uint32_t d0 = byte_perm(left, pr.r[7], 0x5432);
-                    acc[0] = viaddmax_s16x2(d0, pf.r[0], acc[0]);
-                    acc[0] = viaddmax_s16x2(pr.r[0], g2, acc[0]);
-#pragma unroll
-                    for (int r = 1; r < 8; ++r) {
-                        acc[r] = viaddmax_s16x2(pr.r[r - 1], pf.r[r], acc[r]);
-                        acc[r] = viaddmax_s16x2(pr.r[r], g2, acc[r]);
+                    if (multi) {
+                        int32_t lv = cc_prev[p];
+                        lvm = lv > lvm ? lv : lvm;
                     }
                 };
+                auto more = [&](uint32_t p) {
+                    Row8 pr;
+                    load_pred(p, pr);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) pm.r[r] = vmax_s16x2(pm.r[r], pr.r[r]);
+                };
                 if (np <= 1) {
-                    pred(np ? (lo >> 16) : 0u);
+                    load_pred(np ? (lo >> 16) : 0u, pm);
                 } else {
                     const uint32_t hi = shfl(rec_a_hi, ti);
-                    pred(lo >> 16);
-                    pred(hi & 0xffff);
-                    if (np > 2) pred(hi >> 16);
+                    load_pred(lo >> 16, pm);
+                    more(hi & 0xffff);
+                    if (np > 2) more(hi >> 16);
                     if (np > 3) {
                         const uint32_t blo = shfl(rec_b_lo, ti), bhi = shfl(rec_b_hi, ti);
-                        pred(blo & 0xffff);
-                        if (np > 4) pred(blo >> 16);
-                        if (np > 5) pred(bhi & 0xffff);
-                        if (np > 6) pred(bhi >> 16);
-                        for (uint32_t k = 7; k < np; ++k) pred(pred_ovf[i * ki + k]);
+                        more(blo & 0xffff);
+                        if (np > 4) more(blo >> 16);
+                        if (np > 5) more(bhi & 0xffff);
+                        if (np > 6) more(bhi >> 16);
+                        for (uint32_t k = 7; k < np; ++k) more(pred_ovf[i * ki + k]);
                     }
+                }
+                uint32_t acc[8];
+                {
+                    uint32_t left = shfl_up(pm.r[7], 1);  // hi half = previous lane's last column
+                    left = lanem == 0 ? (static_cast<uint32_t>(lvm) << 16) : left;
+                    /* diagonal operand of register 0 = (column -1 of the block, column 7) */
+                    const uint32_t d0 = byte_perm(left, pm.r[7], 0x5432);
+                    acc[0] = viaddmax_s16x2(pm.r[0], g2, viaddmax_s16x2(d0, pf.r[0], 0x80008000u));
+#pragma unroll
+                    for (int r = 1; r < 8; ++r)
+                        acc[r] = viaddmax_s16x2(pm.r[r], g2, viaddmax_s16x2(pm.r[r - 1], pf.r[r], 0x80008000u));
                 }
                 /* in-row gap recurrence H[c] = max(H[c], H[c-1] + g), all in packed int16:
                  * two 8-long chains (low halves = columns 0..7, high halves = columns 8..15 of the block) */
@@ -785,6 +795,32 @@ struct PoaWarp {
      * coalesced burst, walks until the path leaves the tile (about 30-40 steps), and re-anchors.
      * Predecessors below the tile (rare long edges) are read from HBM directly.
      * Output: aln[j] = node aligned to read position j, or kNone (new node). */
+    /* > 32 predecessors (escalated windows only): every diagonal candidate of every group outranks any
+     * vertical one.  Reads straight from the HBM copy; kept out of line so the common loop stays small. */
+    static RP_DEV_NOINLINE int traceback_step_wide(const int16_t* H, const Rec* rec, const uint16_t* pred_ovf, uint32_t ki,
+                                                   int lane, int32_t g, uint32_t i, uint32_t j, uint32_t npe,
+                                                   int32_t hij, int32_t mc, uint32_t lpa, uint32_t* found) {
+        for (int pass = 1; pass <= 2; ++pass) {
+            if (pass == 1 && j == 0) continue;
+            for (uint32_t k0 = 0; k0 < npe; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                uint32_t p = 0;
+                bool ok = false;
+                if (k < npe) {
+                    p = k < 7 ? rec_pred(rec[i], k) : pred_ovf[i * ki + k];
+                    const int16_t* pr = H + static_cast<uint64_t>(p) * lpa;
+                    ok = pass == 1 ? (hij == pr[perm(j - 1)] + mc) : (hij == pr[perm(j)] + g);
+                }
+                const uint32_t msk = ballot(ok);
+                if (msk) {
+                    *found = shfl(p, ffs_(msk) - 1);
+                    return pass;
+                }
+            }
+        }
+        return 0;
+    }
+
     static constexpr uint32_t kTileCols = 32;
 
     RP_DEV void traceback(uint32_t best_row, uint32_t len, uint32_t lpa, const uint8_t* seq, bool sub) {
@@ -831,63 +867,34 @@ struct PoaWarp {
             if (j > 0) mc = (static_cast<uint8_t>(alpha >> (8 * cidx)) == tseq[j - 1]) ? m : x;
             uint32_t found_p = 0;
             int move = 0;  // 1 diag, 2 vert, 3 horiz
-            for (uint32_t k0 = 0; k0 < npe && !move; k0 += 32) {
-                const uint32_t k = k0 + lane;
+            if (npe <= 32) {
+                /* one predecessor per lane; all diagonal candidates outrank any vertical one (sisd :392-442) */
                 uint32_t p = 0;
                 bool okd = false, okv = false;
-                if (k < npe) {
-                    if (np == 0)
-                        p = 0;
-                    else if (k < 7)
-                        p = rec_pred(rc, k);
-                    else
-                        p = pred_ovf[i * ki + k];
+                if (static_cast<uint32_t>(lane) < npe) {
+                    if (np) p = static_cast<uint32_t>(lane) < 7 ? rec_pred(rc, lane) : pred_ovf[i * ki + lane];
                     int32_t a = 0, b;
                     if (p + t_rows > t_top) {  // predecessor row is inside the tile
                         const int16_t* pr = tile + (t_top - p) * kTileCols;
-                        if (j > 0) a = pr[ejm];
+                        a = pr[ejm];
                         b = pr[ej];
                     } else {
                         const int16_t* pr = H + static_cast<uint64_t>(p) * lpa;
-                        if (j > 0) a = pr[perm(j - 1)];
+                        a = pr[perm(j > 0 ? j - 1 : 0)];
                         b = pr[perm(j)];
                     }
                     okd = j > 0 && hij == a + mc;
                     okv = hij == b + g;
                 }
-                /* all diagonal candidates of ALL predecessors outrank any vertical one (sisd :392-442) */
-                uint32_t md = ballot(okd);
-                uint32_t mv = ballot(okv);
-                if (md) {
-                    found_p = shfl(p, ffs_(md) - 1);
-                    move = 1;
-                } else if (mv && k0 + 32 >= npe) {
-                    found_p = shfl(p, ffs_(mv) - 1);
-                    move = 2;
-                } else if (mv) {
-                    /* > 32 predecessors: a later group may still hold a diagonal match; remember the first vertical */
-                    uint32_t vp = shfl(p, ffs_(mv) - 1);
-                    bool later_diag = false;
-                    for (uint32_t k1 = k0 + 32; k1 < npe && !later_diag; k1 += 32) {
-                        uint32_t kk = k1 + lane;
-                        bool od = false;
-                        if (kk < npe && j > 0) {
-                            uint32_t pp = pred_ovf[i * ki + kk];
-                            od = hij == H[static_cast<uint64_t>(pp) * lpa + perm(j - 1)] + mc;
-                            if (od) p = pp;
-                        }
-                        uint32_t m2 = ballot(od);
-                        if (m2) {
-                            found_p = shfl(p, ffs_(m2) - 1);
-                            move = 1;
-                            later_diag = true;
-                        }
-                    }
-                    if (!later_diag) {
-                        found_p = vp;
-                        move = 2;
-                    }
+                const uint32_t md = ballot(okd);
+                const uint32_t mv = ballot(okv);
+                const uint32_t sel = md ? md : mv;
+                if (sel) {
+                    found_p = shfl(p, ffs_(sel) - 1);
+                    move = md ? 1 : 2;
                 }
+            } else {
+                move = traceback_step_wide(H, rec, pred_ovf, ki, lane, g, i, j, npe, hij, mc, lpa, &found_p);
             }
             if (!move) move = 3;
             if (move == 1) {

@@ -19,11 +19,13 @@
 #include <cstdlib>
 #include <cstring>
 #define RP_DEV inline
+#define RP_DEV_NOINLINE
 #define RP_HD inline
 #define RP_GLOBAL
 #else
 #include <cuda_runtime.h>
 #define RP_DEV __device__ __forceinline__
+#define RP_DEV_NOINLINE __device__ __noinline__
 #define RP_HD __host__ __device__ __forceinline__
 #endif
 
@@ -174,6 +176,9 @@ inline int32_t viaddmax_s32(int32_t a, int32_t b, int32_t c) {
     int32_t s = a + b;
     return s > c ? s : c;
 }
+inline uint32_t vmax_s16x2(uint32_t a, uint32_t b) {
+    return pack16(lo16(a) > lo16(b) ? lo16(a) : lo16(b), hi16(a) > hi16(b) ? hi16(a) : hi16(b));
+}
 inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
     uint64_t all = (static_cast<uint64_t>(b) << 32) | a;
     uint32_t r = 0;
@@ -212,6 +217,7 @@ RP_DEV uint32_t pack16(int32_t lo, int32_t hi) {
 /* DPX: per-halfword max(a + b, c) — one VIADDMNMX.S16x2 on sm_90+ */
 RP_DEV uint32_t viaddmax_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
 RP_DEV int32_t viaddmax_s32(int32_t a, int32_t b, int32_t c) { return __viaddmax_s32(a, b, c); }
+RP_DEV uint32_t vmax_s16x2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }  // VIMNMX.S16x2
 RP_DEV uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 #endif
 
