@@ -142,6 +142,7 @@ struct PoaParams {
     SlotLayout lay;
     uint32_t smem_per_warp;       // bytes of shared memory owned by each warp
     uint32_t tile_rows;           // traceback tile height in ranks (0 = default 96)
+    uint32_t debug_flags;         // tests only: bit0 = use the HBM-resident variants of the order DFS / bundle
 };
 
 /* Row layout.  A lane owns 16 consecutive columns; inside that 32-byte block register r (0..7) packs
@@ -685,7 +686,7 @@ struct PoaWarp {
      * in-edge tails and aligned list are fetched together) instead of five dependent ones. */
     RP_DEV void spoa_sort(bool sub) {
         const uint32_t npad = (N + 15) & ~15u;
-        if (ki > 31 || ka != 8 || 2 * npad + 512 > smem_bytes) {
+        if (ki > 31 || ka != 8 || 2 * npad + 512 > smem_bytes || (P->debug_flags & 1)) {
             spoa_sort_hbm(sub);
             return;
         }
@@ -1125,17 +1126,33 @@ struct PoaWarp {
 #endif
             }
             syncwarp();
+            /* inclusive prefix of the counters in shared memory, then a remap pass whose HBM loads are batched */
             uint32_t carry = 0;
             for (uint32_t q0 = 1; q0 <= n_old; q0 += 32) {
                 uint32_t q = q0 + lane;
                 uint32_t d = q <= n_old ? delta[q] : 0;
                 uint32_t inc = warp_incl_sum(d) + carry;
-                if (q <= n_old) {
-                    uint32_t v = order[q];
-                    order_nxt[q + inc] = static_cast<uint16_t>(v);
-                    rank_of[v] = static_cast<uint16_t>(q + inc);
-                }
+                if (q <= n_old) delta[q] = static_cast<uint16_t>(inc);
                 carry = shfl(inc, 31);
+            }
+            syncwarp();
+            constexpr int kV = 8;
+            for (uint32_t q0 = 1; q0 <= n_old; q0 += 32 * kV) {
+                uint32_t v[kV];
+#pragma unroll
+                for (int u = 0; u < kV; ++u) {
+                    uint32_t q = q0 + u * 32 + lane;
+                    v[u] = q <= n_old ? order[q] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < kV; ++u) {
+                    uint32_t q = q0 + u * 32 + lane;
+                    if (q <= n_old) {
+                        uint32_t nr = q + delta[q];
+                        order_nxt[nr] = static_cast<uint16_t>(v[u]);
+                        rank_of[v[u]] = static_cast<uint16_t>(nr);
+                    }
+                }
             }
             if (lane == 0) order_nxt[0] = kNone;
             uint16_t* t = order;
@@ -1147,35 +1164,82 @@ struct PoaWarp {
         syncwarp();
     }
 
-    /* ---------------------------------------------------------------- consensus (graph.cpp:433-516, 377-398) */
-    RP_DEV void better(uint32_t it, uint32_t t, int64_t wgt) {
-        int64_t si = score[it];
-        if (si < wgt || (si == wgt && cpred[it] != kNone && score[cpred[it]] <= score[t])) {
-            score[it] = wgt;
-            cpred[it] = static_cast<uint16_t>(t);
+    /* ---------------------------------------------------------------- consensus (graph.cpp:433-516, 377-398)
+     * Heaviest bundle.  The pass over the nodes in spoa's rank order is inherently serial (lane 0), but what it
+     * reads is not: the warp stages 32 nodes at a time (id, in-degree, first four in-edge tails and weights)
+     * into shared memory with coalesced gathers, and scores / best predecessors live in shared memory too
+     * when the graph is small enough (int32 scores are exact while the sum of all edge weights < 2^31). */
+    struct CStage {
+        uint32_t w[4];
+        uint16_t t[4];
+        uint16_t it;
+        uint16_t ni;
+        uint32_t pad;
+    };
+
+    template <typename ScoreT>
+    RP_DEV void better_t(ScoreT* sc, uint16_t* cp, uint32_t it, uint32_t t, int64_t wgt) {
+        int64_t si = sc[it];
+        if (si < wgt || (si == wgt && cp[it] != kNone && sc[cp[it]] <= sc[t])) {
+            sc[it] = static_cast<ScoreT>(wgt);
+            cp[it] = static_cast<uint16_t>(t);
         }
     }
 
-    RP_DEV uint32_t consensus(uint8_t* out, uint16_t* out_cov, uint32_t out_cap, bool trim, uint32_t n_seq) {
-        spoa_sort(false);
-        if (status != kWinOk) return 0;
-        for (uint32_t v = lane; v < N; v += 32) {
-            score[v] = -1;
-            cpred[v] = kNone;
-        }
-        syncwarp();
+    /* one pass over ranks [r_begin, N): graph.cpp:442-456 (skip_dead = false) or :493-513 (true) */
+    template <typename ScoreT>
+    RP_DEV uint32_t bundle_pass(ScoreT* sc, uint16_t* cp, CStage* stg, uint32_t r_begin, bool skip_dead) {
         uint32_t mx = kNone;
-        if (lane == 0) {
-            for (uint32_t r = 0; r < N; ++r) {
-                uint32_t it = sorder[r];
-                uint32_t ni = in_cnt[it];
-                for (uint32_t k = 0; k < ni; ++k) better(it, in_tail[it * ki + k], in_w[it * ki + k]);
-                if (cpred[it] != kNone) score[it] += score[cpred[it]];
-                if (mx == kNone || score[mx] < score[it]) mx = it;
+        for (uint32_t r0 = r_begin; r0 < N; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            if (r < N) {
+                const uint32_t it = sorder[r];
+                CStage e;
+                e.it = static_cast<uint16_t>(it);
+                e.ni = in_cnt[it];
+                const uint64_t t4 = *reinterpret_cast<const uint64_t*>(in_tail + it * ki);
+                const U4 w4 = *reinterpret_cast<const U4*>(in_w + it * ki);
+                e.t[0] = static_cast<uint16_t>(t4);
+                e.t[1] = static_cast<uint16_t>(t4 >> 16);
+                e.t[2] = static_cast<uint16_t>(t4 >> 32);
+                e.t[3] = static_cast<uint16_t>(t4 >> 48);
+                e.w[0] = w4.x; e.w[1] = w4.y; e.w[2] = w4.z; e.w[3] = w4.w;
+                e.pad = 0;
+                stg[lane] = e;
             }
+            syncwarp();
+            if (lane == 0) {
+                const uint32_t cnt = N - r0 < 32 ? N - r0 : 32;
+                for (uint32_t q = 0; q < cnt; ++q) {
+                    const CStage& e = stg[q];
+                    const uint32_t it = e.it;
+                    if (skip_dead) {
+                        sc[it] = -1;
+                        cp[it] = kNone;
+                    }
+                    for (uint32_t k = 0; k < e.ni; ++k) {
+                        const uint32_t t = k < 4 ? e.t[k] : in_tail[it * ki + k];
+                        if (skip_dead && sc[t] == -1) continue;
+                        const int64_t wgt = k < 4 ? static_cast<int32_t>(e.w[k]) : in_w[it * ki + k];
+                        better_t(sc, cp, it, t, wgt);
+                    }
+                    if (cp[it] != kNone) sc[it] = static_cast<ScoreT>(sc[it] + sc[cp[it]]);
+                    if (mx == kNone || sc[mx] < sc[it]) mx = it;
+                }
+            }
+            syncwarp();
         }
-        mx = shfl(mx, 0);
+        return shfl(mx, 0);
+    }
+
+    template <typename ScoreT>
+    RP_DEV uint32_t bundle(ScoreT* sc, uint16_t* cp, CStage* stg) {
+        for (uint32_t v = lane; v < N; v += 32) {
+            sc[v] = -1;
+            cp[v] = kNone;
+        }
         syncwarp();
+        uint32_t mx = bundle_pass(sc, cp, stg, 0, false);
         /* branch completion (graph.cpp:478-516) while the best node still has out-edges */
         while (flags[mx] & 1) {
             /* heads of mx's out-edges = nodes with an in-edge from mx; their other tails are invalidated */
@@ -1186,30 +1250,41 @@ struct PoaWarp {
                 if (hit)
                     for (uint32_t k = 0; k < ni; ++k) {
                         uint32_t t = in_tail[v * ki + k];
-                        if (t != mx) score[t] = -1;
+                        if (t != mx) sc[t] = -1;
                     }
             }
             syncwarp();
-            uint32_t nm = kNone;
-            if (lane == 0) {
-                for (uint32_t r = static_cast<uint32_t>(srank[mx]) + 1; r < N; ++r) {
-                    uint32_t it = sorder[r];
-                    score[it] = -1;
-                    cpred[it] = kNone;
-                    uint32_t ni = in_cnt[it];
-                    for (uint32_t k = 0; k < ni; ++k) {
-                        uint32_t t = in_tail[it * ki + k];
-                        if (score[t] == -1) continue;
-                        better(it, t, in_w[it * ki + k]);
-                    }
-                    if (cpred[it] != kNone) score[it] += score[cpred[it]];
-                    if (nm == kNone || score[nm] < score[it]) nm = it;
-                }
-            }
-            nm = shfl(nm, 0);
-            syncwarp();
+            uint32_t nm = bundle_pass(sc, cp, stg, static_cast<uint32_t>(srank[mx]) + 1, true);
             if (nm == kNone) break;  // cannot happen: a node with out-edges has successors of higher rank
             mx = nm;
+        }
+        /* hand the predecessor chain over in the HBM array the emitter reads */
+        if (cp != cpred)
+            for (uint32_t v = lane; v < N; v += 32) cpred[v] = cp[v];
+        syncwarp();
+        return mx;
+    }
+
+    RP_DEV uint32_t consensus(uint8_t* out, uint16_t* out_cov, uint32_t out_cap, bool trim, uint32_t n_seq) {
+        spoa_sort(false);
+        if (status != kWinOk) return 0;
+        /* int32 scores in shared memory are exact iff the total edge weight fits */
+        uint64_t wsum = 0;
+        for (uint32_t v = lane; v < N; v += 32) {
+            uint32_t ni = in_cnt[v];
+            for (uint32_t k = 0; k < ni; ++k) wsum += static_cast<uint32_t>(in_w[v * ki + k]);
+        }
+        for (int d = 16; d > 0; d >>= 1) wsum += shfl_down(wsum, d);
+        wsum = shfl(wsum, 0);
+        const uint32_t npad = (N + 7) & ~7u;
+        uint32_t mx;
+        if (wsum < 0x7fffffffull && npad * 6 + sizeof(CStage) * 32 <= smem_bytes && !(P->debug_flags & 1)) {
+            int32_t* sc = reinterpret_cast<int32_t*>(smem);
+            uint16_t* cp = reinterpret_cast<uint16_t*>(smem + npad * 4);
+            CStage* stg = reinterpret_cast<CStage*>(smem + npad * 6);
+            mx = bundle(sc, cp, stg);
+        } else {
+            mx = bundle(score, cpred, reinterpret_cast<CStage*>(smem));
         }
         /* walk predecessors back; the path is stored reversed in `stack`, then emitted forward */
         uint32_t clen = 0;

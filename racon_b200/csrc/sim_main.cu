@@ -60,7 +60,7 @@ int rp_sim_pack_only(uint32_t n_windows, const char* bases, const char* quals, c
     return static_cast<int>(pb.n_gpu());
 }
 
-/* Flat window set in, consensus out.  limits: {nmax, lmax, ki, ka, smem_per_warp, tile_rows}.  Returns 0 or <0. */
+/* Flat window set in, consensus out.  limits: {nmax, lmax, ki, ka, smem_per_warp, tile_rows, debug_flags}.  Returns 0 or <0. */
 int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
                const uint8_t* seq_has_qual, const uint32_t* seq_begin, const uint32_t* seq_end,
                const uint32_t* win_first, const uint8_t* win_type, int8_t match, int8_t mismatch, int8_t gap,
@@ -121,6 +121,7 @@ int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const u
     P.lay = rp::make_layout(P.lim);
     P.smem_per_warp = limits[4];
     P.tile_rows = limits[5];
+    P.debug_flags = limits[6];
     std::vector<uint8_t> slot(P.lay.bytes + 64);
     std::vector<uint8_t> smem(P.smem_per_warp + 64);
     uint8_t* slot_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slot.data()) + 15) & ~uintptr_t(15));

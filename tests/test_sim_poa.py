@@ -77,6 +77,13 @@ def test_sim_escalation_limits_configuration():
     _check(_mk("partial_qual", seed=2), nmax=20000, lmax=4095, ki=96)
 
 
+def test_sim_branch_completion_is_exercised():
+    # seeds chosen with the oracle's counters: the heaviest-bundle maximum is not a sink => BranchCompletion
+    for seed in (48, 61, 78):
+        _check(util.make_set(seed, 6, wlen=80, depth=14, err=0.3))
+        _check(util.make_set(seed, 6, wlen=80, depth=14, err=0.3), debug_flags=1)  # HBM-resident variants
+
+
 def test_sim_no_trim_and_trivial():
     _check(_mk("partial", seed=9), trim=False)
     from racon_b200 import windows

@@ -13,25 +13,26 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin") and "host_mirror" not in f][0]
 dis = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cubin)], stdout=subprocess.PIPE, text=True).stdout
-lines = []  # (offset, file, line, text)
-cur = ("?", 0)
-in_kernel = False
+funcs_dis, cur, cur_fn = {}, ("?", 0), None
 for ln in dis.splitlines():
-    if ln.startswith("\t.section") or ".text." in ln and ln.strip().endswith(":"):
-        in_kernel = "rp_poa_kernel" in ln or in_kernel
+    m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+    if m:
+        cur_fn = m.group(1); funcs_dis[cur_fn] = []; continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
-    if m:
-        lines.append((int(m.group(1), 16), cur[0], cur[1], m.group(2).strip()))
+    if m and cur_fn:
+        funcs_dis[cur_fn].append((int(m.group(1), 16), cur[0], cur[1], m.group(2).strip()))
 csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(csvtxt.splitlines()))
 hdr = rows[1]
 ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 data = rows[2:]
 base = int(data[0][ia], 16)
+ninst = sum(1 for r in data if r[ia].startswith("0x"))
+lines = min(funcs_dis.values(), key=lambda v: abs(len(v) - ninst))
 byoff = {int(r[ia], 16) - base: (int(r[ii] or 0), int(r[isamp] or 0), r[1]) for r in data if r[ia].startswith("0x")}
 # function ranges in poa_core.cuh
 srcpath = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "racon_b200", "csrc", "poa_core.cuh")

@@ -7,18 +7,23 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin") and "host_mirror" not in f][0]
 dis = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cubin)], stdout=subprocess.PIPE, text=True).stdout
-lines, cur = [], ("?", 0)
+funcs_dis, cur, cur_fn = {}, ("?", 0), None
 for ln in dis.splitlines():
+    m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
+    if m:
+        cur_fn = m.group(1); funcs_dis[cur_fn] = []; continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
-    if m: lines.append((int(m.group(1), 16), cur[0], cur[1], m.group(2).strip()))
+    if m and cur_fn: funcs_dis[cur_fn].append((int(m.group(1), 16), cur[0], cur[1], m.group(2).strip()))
 rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout.splitlines()))
 hdr = rows[1]; data = rows[2:]
 ia = hdr.index("Address")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 base = int(data[0][ia], 16)
+ninst = sum(1 for r in data if r[ia].startswith("0x"))
+lines = min(funcs_dis.values(), key=lambda v: abs(len(v) - ninst))
 byoff = {int(r[ia], 16) - base: r for r in data if r[ia].startswith("0x")}
 src = open(srcpath).read().splitlines()
 funcs = [(n, m.group(1)) for n, l in enumerate(src, 1) for m in [re.match(r"\s*RP_DEV\s+[\w:<>\*&\s]+?\s+(\w+)\(", l)] if m]
