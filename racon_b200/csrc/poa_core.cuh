@@ -312,26 +312,75 @@ struct PoaWarp {
     /* Backward DFS from backbone node `end` over in-edges and aligned nodes, keeping ids >= begin.
      * Serial (lane 0); only partial-span layers take this path. */
     RP_DEV void mark_subgraph(uint32_t begin, uint32_t end) {
-        for (uint32_t v = lane; v < N; v += 32) member[v] = 0;
+        const uint32_t npad = (N + 15) & ~15u;
+        const bool staged = ki <= 31 && ka == 8 && 2 * npad + 512 <= smem_bytes && !(P->debug_flags & 1);
+        if (!staged) {  /* HBM-resident variant */
+            for (uint32_t v = lane; v < N; v += 32) member[v] = 0;
+            syncwarp();
+            if (lane == 0) {
+                uint32_t sp = 0;
+                const uint32_t cap = P->lim.stack_cap;
+                stack[sp++] = static_cast<uint16_t>(end);
+                while (sp > 0) {
+                    uint32_t c = stack[--sp];
+                    if (member[c] || c < begin) continue;
+                    uint32_t ni = in_cnt[c], na = al_cnt[c];
+                    if (sp + ni + na > cap) {
+                        fail(kWinStackLimit);
+                        break;
+                    }
+                    for (uint32_t k = 0; k < ni; ++k) stack[sp++] = in_tail[c * ki + k];
+                    for (uint32_t k = 0; k < na; ++k) stack[sp++] = al[c * ka + k];
+                    member[c] = 1;
+                }
+            }
+            status = shfl(status, 0);
+            syncwarp();
+            return;
+        }
+        /* membership bytes, per-node degrees and the stack in shared memory; one HBM round trip per node
+         * (in-edge tails and aligned list fetched together) */
+        uint8_t* smb = smem;
+        uint8_t* sme = smem + npad;
+        uint16_t* sst = reinterpret_cast<uint16_t*>(smem + 2 * npad);
+        const uint32_t cap = (smem_bytes - 2 * npad) / 2;
+        for (uint32_t v = lane; v < N; v += 32) {
+            smb[v] = 0;
+            sme[v] = static_cast<uint8_t>(in_cnt[v] | (al_cnt[v] << 5));
+        }
         syncwarp();
         if (lane == 0) {
             uint32_t sp = 0;
-            const uint32_t cap = P->lim.stack_cap;
-            stack[sp++] = static_cast<uint16_t>(end);
+            sst[sp++] = static_cast<uint16_t>(end);
             while (sp > 0) {
-                uint32_t c = stack[--sp];
-                if (member[c] || c < begin) continue;
-                uint32_t ni = in_cnt[c], na = al_cnt[c];
+                const uint32_t c = sst[--sp];
+                if (smb[c] || c < begin) continue;
+                const uint32_t ni = sme[c] & 31u, na = sme[c] >> 5;
+                const uint64_t t4 = *reinterpret_cast<const uint64_t*>(in_tail + c * ki);
+                uint64_t a_lo = 0, a_hi = 0;
+                if (na) {
+                    const U4 a8 = *reinterpret_cast<const U4*>(al + c * ka);
+                    a_lo = a8.x | (static_cast<uint64_t>(a8.y) << 32);
+                    a_hi = a8.z | (static_cast<uint64_t>(a8.w) << 32);
+                }
                 if (sp + ni + na > cap) {
                     fail(kWinStackLimit);
                     break;
                 }
-                for (uint32_t k = 0; k < ni; ++k) stack[sp++] = in_tail[c * ki + k];
-                for (uint32_t k = 0; k < na; ++k) stack[sp++] = al[c * ka + k];
-                member[c] = 1;
+                for (uint32_t k = 0; k < ni; ++k) {
+                    const uint32_t t = k < 4 ? (static_cast<uint32_t>(t4 >> (16 * k)) & 0xffffu) : in_tail[c * ki + k];
+                    if (!smb[t] && t >= begin) sst[sp++] = static_cast<uint16_t>(t);
+                }
+                for (uint32_t k = 0; k < na; ++k) {
+                    const uint32_t a = static_cast<uint32_t>((k < 4 ? a_lo : a_hi) >> (16 * (k & 3))) & 0xffffu;
+                    if (!smb[a] && a >= begin) sst[sp++] = static_cast<uint16_t>(a);
+                }
+                smb[c] = 1;
             }
         }
         status = shfl(status, 0);
+        syncwarp();
+        for (uint32_t v = lane; v < N; v += 32) member[v] = smb[v];
         syncwarp();
     }
 

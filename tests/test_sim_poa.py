@@ -69,6 +69,7 @@ def test_sim_hbm_fallback_of_the_order_dfs():
     # ka != 8 selects the HBM-resident variant of the spoa-order DFS
     _check(_mk("higherr_ties", seed=21), ka=7)
     _check(_mk("partial", seed=4), ka=9)
+    _check(_mk("partial_qual", seed=4), debug_flags=1)
 
 
 def test_sim_escalation_limits_configuration():
