@@ -338,15 +338,19 @@ struct PoaWarp {
             syncwarp();
             return;
         }
-        /* membership bytes, per-node degrees and the stack in shared memory; one HBM round trip per node
-         * (in-edge tails and aligned list fetched together) */
+        /* membership bytes, per-node degrees, the first two in-edge tails of every node and the stack live in
+         * shared memory: a node costs an HBM round trip only if it has more than two in-edges or aligned nodes */
         uint8_t* smb = smem;
         uint8_t* sme = smem + npad;
-        uint16_t* sst = reinterpret_cast<uint16_t*>(smem + 2 * npad);
-        const uint32_t cap = (smem_bytes - 2 * npad) / 2;
+        const bool have_t2 = 6 * npad + 1024 <= smem_bytes;
+        uint32_t* st2 = reinterpret_cast<uint32_t*>(smem + 2 * npad);
+        const uint32_t fixed = have_t2 ? 6 * npad : 2 * npad;
+        uint16_t* sst = reinterpret_cast<uint16_t*>(smem + fixed);
+        const uint32_t cap = (smem_bytes - fixed) / 2;
         for (uint32_t v = lane; v < N; v += 32) {
             smb[v] = 0;
             sme[v] = static_cast<uint8_t>(in_cnt[v] | (al_cnt[v] << 5));
+            if (have_t2) st2[v] = *reinterpret_cast<const uint32_t*>(in_tail + v * ki);
         }
         syncwarp();
         if (lane == 0) {
@@ -356,7 +360,8 @@ struct PoaWarp {
                 const uint32_t c = sst[--sp];
                 if (smb[c] || c < begin) continue;
                 const uint32_t ni = sme[c] & 31u, na = sme[c] >> 5;
-                const uint64_t t4 = *reinterpret_cast<const uint64_t*>(in_tail + c * ki);
+                uint64_t t4 = have_t2 ? st2[c] : 0;
+                if (!have_t2 || ni > 2) t4 = *reinterpret_cast<const uint64_t*>(in_tail + c * ki);
                 uint64_t a_lo = 0, a_hi = 0;
                 if (na) {
                     const U4 a8 = *reinterpret_cast<const U4*>(al + c * ka);
@@ -741,11 +746,17 @@ struct PoaWarp {
         }
         uint8_t* smk = smem;          // bits0-1 mark, bit2 ignored, bit3 member
         uint8_t* sme = smem + npad;   // in_cnt | al_cnt << 5
-        uint16_t* sst = reinterpret_cast<uint16_t*>(smem + 2 * npad);
-        const uint32_t cap = (smem_bytes - 2 * npad) / 2;
+        /* the first two in-edge tails of every node too, when they fit: a node then costs an HBM round trip
+         * only if it has more than two in-edges or aligned nodes */
+        const bool have_t2 = 6 * npad + 1536 <= smem_bytes;
+        uint32_t* st2 = reinterpret_cast<uint32_t*>(smem + 2 * npad);
+        const uint32_t fixed = have_t2 ? 6 * npad : 2 * npad;
+        uint16_t* sst = reinterpret_cast<uint16_t*>(smem + fixed);
+        const uint32_t cap = (smem_bytes - fixed) / 2;
         for (uint32_t v = lane; v < N; v += 32) {
             smk[v] = (!sub || member[v]) ? 8 : 0;
             sme[v] = static_cast<uint8_t>(in_cnt[v] | (al_cnt[v] << 5));
+            if (have_t2) st2[v] = *reinterpret_cast<const uint32_t*>(in_tail + v * ki);
         }
         syncwarp();
         if (lane == 0) {
@@ -759,7 +770,8 @@ struct PoaWarp {
                     const uint8_t mk = smk[c];
                     if ((mk & 3) != 2) {
                         const uint32_t ni = sme[c] & 31u, na = sme[c] >> 5;
-                        const uint64_t t4 = *reinterpret_cast<const uint64_t*>(in_tail + c * ki);
+                        uint64_t t4 = have_t2 ? st2[c] : 0;
+                        if (!have_t2 || ni > 2) t4 = *reinterpret_cast<const uint64_t*>(in_tail + c * ki);
                         uint64_t a_lo = 0, a_hi = 0;
                         if (na) {
                             const U4 a8 = *reinterpret_cast<const U4*>(al + c * ka);
