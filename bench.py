@@ -178,7 +178,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from racon_b200 import api, windows
+    from racon_b200 import api, shard, windows
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the POA hot path has no CPU fallback")
@@ -243,9 +243,6 @@ def main():
     gpu_launches = batch.info()["launches"] - launches0
 
     # ---- end-to-end arm: C-ABI call with host buffers (H2D + kernel + D2H + fetch) ------------------
-    gather_buf = None
-    if distributed:
-        gather_buf = torch.empty(world * n * 640, dtype=torch.uint8, device="cuda")
     def plugin_step():
         # exactly what racon's CUDABatchProcessor does per batch: reset, addWindow x n (host buffers are copied
         # into pinned staging), generateConsensus (H2D + kernel + D2H), read the consensus strings back
@@ -261,9 +258,9 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         out, lens, pol, st = plugin_step()
-        if distributed:  # the one exchange step of the path: final consensus gather over NCCL
-            mine = torch.from_numpy(np.ascontiguousarray(out[:, :640]).reshape(-1)).cuda(non_blocking=True)
-            dist.all_gather_into_tensor(gather_buf, mine)
+        if distributed:  # the one exchange step of the path: final consensus gather over NCCL (SURVEY.md §8e)
+            mask = np.arange(out.shape[1], dtype=np.uint32)[None, :] < lens[:, None]
+            gathered = shard.gather_packed(out[mask], lens, device="cuda")
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     io = batch.info()

@@ -1,0 +1,58 @@
+"""Multi-GPU plumbing: windows are independent (src/polisher.cpp:495-503), so each rank owns a contiguous shard
+of the window stream and the only exchange is the final gather of the consensus bytes.
+Works with any torch.distributed backend: "nccl" on the GPU box, "gloo" in the CPU tests."""
+import numpy as np
+
+
+def shard_bounds(n_windows, rank, world):
+    """Contiguous, count-balanced window range [lo, hi) of `rank` (output order = window order)."""
+    base, rem = divmod(n_windows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_consensus(cons):
+    """list of bytes -> (flat uint8 array, uint32 lengths)"""
+    lens = np.asarray([len(c) for c in cons], dtype=np.uint32)
+    flat = np.frombuffer(b"".join(cons), dtype=np.uint8).copy() if len(cons) else np.zeros(0, np.uint8)
+    return flat, lens
+
+
+def gather_packed(flat, lens, device=None, group=None):
+    """Array form of the gather: every rank contributes (flat uint8 bytes, uint32 lengths) of its shard and gets
+    back the per-rank lists [(flat_r, lens_r)] in rank (= window) order.  Three collectives: counts, lengths, bytes."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    dev = device if device is not None else "cpu"
+    n = int(len(lens))
+    counts = torch.tensor([n, int(flat.size)], dtype=torch.int64, device=dev)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    max_n = int(max(int(c[0]) for c in all_counts))
+    max_b = int(max(int(c[1]) for c in all_counts))
+    lbuf = torch.zeros(max(max_n, 1), dtype=torch.int32, device=dev)
+    lbuf[:n] = torch.from_numpy(np.asarray(lens).astype(np.int32)).to(dev)
+    bbuf = torch.zeros(max(max_b, 1), dtype=torch.uint8, device=dev)
+    bbuf[:flat.size] = torch.from_numpy(np.ascontiguousarray(flat)).to(dev)
+    all_l = [torch.zeros_like(lbuf) for _ in range(world)]
+    all_b = [torch.zeros_like(bbuf) for _ in range(world)]
+    dist.all_gather(all_l, lbuf, group=group)
+    dist.all_gather(all_b, bbuf, group=group)
+    out = []
+    for r in range(world):
+        nr, br = int(all_counts[r][0]), int(all_counts[r][1])
+        out.append((all_b[r][:br].cpu().numpy(), all_l[r][:nr].cpu().numpy().astype(np.uint32)))
+    return out
+
+
+def gather_consensus(cons, device=None, group=None):
+    """All ranks call this with their shard's consensus list; every rank gets the full list in window order."""
+    flat, lens = pack_consensus(cons)
+    out = []
+    for bb, ll in gather_packed(flat, lens, device, group):
+        off = 0
+        for k in range(len(ll)):
+            out.append(bb[off:off + int(ll[k])].tobytes())
+            off += int(ll[k])
+    return out
