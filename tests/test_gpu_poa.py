@@ -133,6 +133,26 @@ def test_gpu_escalation_of_deep_and_long_windows():
     assert cons == ora and (pol == opol).all()
 
 
+def test_gpu_edge_cases_ragged_and_degenerate():
+    bb = b"ACGTTGCAACGTAGCTAGCTAGGATCGATCGATCGTAGCTAGCTAGCATCGATCGTAGCATGCATGCAA"
+    wins = [
+        [(bb, None, 0, 0), (bb[:40], None, 0, 39), (b"", None, 0, 10), (bb[5:60], None, 5, 59), (b"ACG", None, 7, 7),
+         (bb, None, 0, len(bb) - 1)],
+        [(bb, None, 0, 0), (b"A", None, 0, 1), (b"T", None, 3, 4), (bb[10:50], b"5" * 40, 10, 49),
+         (bb, None, 0, len(bb) - 1)],
+        [(bb, None, 0, 0), (b"", None, 0, 5), (bb, None, 0, len(bb) - 1), (b"AC", None, 9, 9)],
+        [(b"AC", None, 0, 0), (b"AC", None, 0, 1), (b"AG", None, 0, 1), (b"AC", None, 0, 1)],
+        [(b"A", None, 0, 0)],
+    ]
+    ws = windows.from_lists(wins)
+    cons, pol, st = api.consensus(ws)
+    ora, opol, _ = ob.oracle_consensus(ws)
+    assert cons == ora and (pol == opol).all() and (st == 0).all()
+    bad = windows.from_lists([[(bb, None, 0, 0), (bb, None, 12, 5), (bb, None, 0, 60), (bb, None, 0, 60)]])
+    with pytest.raises(api.RaconB200Error):
+        api.consensus(bad)  # begin > end: RP_ERR_INVALID (the reference exit(1)s, window.cpp:53-58)
+
+
 def test_gpu_batch_object_protocol():
     """add-until-full / run / fetch / reset, state errors, per-window status."""
     ws = _mk("shallow", seed=3)

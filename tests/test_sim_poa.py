@@ -104,3 +104,40 @@ def test_sim_limits_are_reported_not_crashed():
     assert (st == 1).all() and not pol.any()  # RP_WIN_NODE_LIMIT
     cons, pol, st, _, _ = simlib.sim_consensus(ws, ki=2)
     assert ((st == 2) | (st == 0)).all() and (st == 2).any()  # RP_WIN_EDGE_LIMIT
+
+
+def test_sim_edge_cases_ragged_and_degenerate():
+    """Empty / ragged inputs as the reference accepts them: skipped layers (len 0, begin == end), 1-base layers,
+    a 1-base backbone, windows where everything but two layers is skipped (=> backbone copy, not polished)."""
+    from racon_b200 import windows
+    bb = b"ACGTTGCAACGTAGCTAGCTAGGATCGATCGATCGTAGCTAGCTAGCATCGATCGTAGCATGCATGCAA"
+    wins = [
+        # two real layers + skipped ones (zero length / begin == end)
+        [(bb, None, 0, 0), (bb[:40], None, 0, 39), (b"", None, 0, 10), (bb[5:60], None, 5, 59), (b"ACG", None, 7, 7),
+         (bb, None, 0, len(bb) - 1)],
+        # 1-base layers and a quality-weighted one
+        [(bb, None, 0, 0), (b"A", None, 0, 1), (b"T", None, 3, 4), (bb[10:50], b"5" * 40, 10, 49),
+         (bb, None, 0, len(bb) - 1)],
+        # everything skipped but one layer -> < 3 sequences
+        [(bb, None, 0, 0), (b"", None, 0, 5), (bb, None, 0, len(bb) - 1), (b"AC", None, 9, 9)],
+        # very short backbone
+        [(b"AC", None, 0, 0), (b"AC", None, 0, 1), (b"AG", None, 0, 1), (b"AC", None, 0, 1)],
+        [(b"A", None, 0, 0)],
+    ]
+    ws = windows.from_lists(wins)
+    cons, pol, st, covs, _ = simlib.sim_consensus(ws)
+    ora, opol, _, ocov = ob.oracle_consensus(ws, want_coverage=True)
+    assert cons == ora and (pol == opol).all() and (st == 0).all()
+    if ob.have_ref():
+        ref, rpol, _ = ob.ref_consensus(ws)
+        assert ref == cons and (rpol == pol).all()
+
+
+def test_sim_malformed_windows_are_rejected_not_crashed():
+    """The reference exit(1)s on these (window.cpp:19-23,49-58); the ABI returns RP_ERR_INVALID instead."""
+    from racon_b200 import windows
+    bb = b"ACGTACGTACGTACGTACGT"
+    for bad in ([(bb, None, 0, 0), (bb, None, 12, 5), (bb, None, 0, 19), (bb, None, 0, 19)],      # begin > end
+                [(bb, None, 0, 0), (bb, None, 0, 25), (bb, None, 0, 19), (bb, None, 0, 19)]):     # end > backbone
+        with pytest.raises(RuntimeError):
+            simlib.sim_consensus(windows.from_lists([bad]))
