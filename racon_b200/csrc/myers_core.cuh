@@ -1,0 +1,592 @@
+/*
+ * myers_core.cuh — batched global pairwise alignment with edlib-identical CIGARs (device code).
+ *
+ * Replaces, per overlap, what racon asks of edlib in Overlap::align_overlaps
+ * (/root/reference/src/overlap.cpp:205-224): edlibAlign(query, target, NW, k=-1, TASK_PATH) + standard CIGAR.
+ * The alignment edlib returns is a function of EXACT edit distances only (see oracle/myers_oracle.cpp, pinned
+ * against the unmodified edlib): priority traceback up > left > diagonal below 1 MiB of alignment data,
+ * Hirschberg with the smallest-split-row rule above (vendor/edlib/edlib/src/edlib.cpp:987-1097, 1128-1180,
+ * 1198-1363).  Any exact banded method therefore reproduces it; this one is built for a warp:
+ *
+ *   * one warp per overlap, lanes = 64-bit words of the Myers/Hyyro bit-vector column (word w of the band lives
+ *     in lane w % 32, slot (w / 32) % kSlots), Ukkonen band of the diagonals that a path of cost <= k can touch;
+ *   * the horizontal carry between the words of a column is resolved iteratively with one SHFL per round
+ *     (it converges in 2-3 rounds in practice) instead of a 32-step serial chain;
+ *   * distance by k doubling from 64 (any k that succeeds gives the exact distance); Hirschberg columns with
+ *     k = the known score of the sub-problem; base cases store the vertical-(+1) and horizontal-(+1) bit-vectors
+ *     of every band word and are walked back with edlib's move priority;
+ *   * operations are written backwards into one buffer (right sub-problem first), then run-length encoded.
+ */
+#pragma once
+#include "rp_warp.cuh"
+
+namespace rp {
+
+constexpr int kAlnSlots = 4;                  // band words per lane -> band of up to 128 words = 8192 rows
+constexpr uint32_t kAlnMaxSyms = 8;
+constexpr int32_t kAlnInf = 1 << 28;
+
+enum : uint32_t {
+    kAlnOk = 0,
+    kAlnBandLimit = 1,
+    kAlnAlphabetLimit = 2,
+    kAlnStoreLimit = 3,
+    kAlnInternal = 4,
+    kAlnRunLimit = 5,
+    kAlnTooLong = 6
+};
+
+struct AlnLimits {
+    uint32_t max_len;        // longest query / target
+    uint32_t store_words;    // capacity (in 64-bit words) of each of the two base-case bit-vector stores
+};
+
+struct AlnLayout {
+    uint64_t peq_f, peq_r, col_l, col_r, store_pv, store_ph, store_first, ops, stack, bytes;
+};
+
+RP_HD AlnLayout make_aln_layout(const AlnLimits& L) {
+    AlnLayout a;
+    uint64_t o = 0;
+    auto take = [&](uint64_t bytes) {
+        uint64_t r = o;
+        o = (o + bytes + 255) / 256 * 256;
+        return r;
+    };
+    const uint64_t nw = (L.max_len + 63) / 64 + 2;
+    a.peq_f = take(kAlnMaxSyms * nw * 8);
+    a.peq_r = take(kAlnMaxSyms * nw * 8);
+    a.col_l = take((static_cast<uint64_t>(L.max_len) + 2) * 4);
+    a.col_r = take((static_cast<uint64_t>(L.max_len) + 2) * 4);
+    a.store_pv = take(static_cast<uint64_t>(L.store_words) * 8);
+    a.store_ph = take(static_cast<uint64_t>(L.store_words) * 8);
+    a.store_first = take((static_cast<uint64_t>(L.max_len) + 2) * 4);
+    a.ops = take(2ull * L.max_len + 64);
+    a.stack = take(128 * 5 * 4);
+    a.bytes = (o + 4095) / 4096 * 4096;
+    return a;
+}
+
+struct AlnParams {
+    uint32_t n_pairs;
+    const uint8_t* bases;       // all queries and targets, concatenated
+    const uint32_t* q_off;
+    const uint32_t* q_len;
+    const uint32_t* t_off;
+    const uint32_t* t_len;
+    const uint32_t* queue;
+    uint32_t* queue_head;
+    /* outputs: run-length encoded operations ('M','I','D'), pair p at runs + run_off[p], capacity run_cap[p] */
+    uint32_t* runs;             // (count << 8) | op
+    const uint32_t* run_off;
+    const uint32_t* run_cap;
+    uint32_t* n_runs;
+    int32_t* dist;
+    uint32_t* status;
+    uint8_t* scratch;
+    AlnLimits lim;
+    AlnLayout lay;
+};
+
+struct AlnWarp {
+    const AlnParams* P;
+    int lane;
+    uint64_t *peq_f, *peq_r, *store_pv, *store_ph;
+    int32_t *col_l, *col_r;
+    uint32_t* store_first;
+    uint8_t* ops;
+    uint32_t* stack;
+    uint32_t status;
+    uint64_t syms;      // up to 8 distinct characters of the pair
+    uint32_t nsyms;
+
+    RP_DEV void bind(const AlnParams* p, uint8_t* slot) {
+        P = p;
+        lane = lane_id();
+        const AlnLayout& y = p->lay;
+        peq_f = reinterpret_cast<uint64_t*>(slot + y.peq_f);
+        peq_r = reinterpret_cast<uint64_t*>(slot + y.peq_r);
+        col_l = reinterpret_cast<int32_t*>(slot + y.col_l);
+        col_r = reinterpret_cast<int32_t*>(slot + y.col_r);
+        store_pv = reinterpret_cast<uint64_t*>(slot + y.store_pv);
+        store_ph = reinterpret_cast<uint64_t*>(slot + y.store_ph);
+        store_first = reinterpret_cast<uint32_t*>(slot + y.store_first);
+        ops = slot + y.ops;
+        stack = reinterpret_cast<uint32_t*>(slot + y.stack);
+        status = kAlnOk;
+    }
+
+    RP_DEV uint32_t sym_index(uint8_t c) const {
+        uint32_t k = 0;
+        for (; k < nsyms; ++k)
+            if (static_cast<uint8_t>(syms >> (8 * k)) == c) break;
+        return k;
+    }
+
+    /* match masks of the (possibly reversed) query sub-range: peq[s * nw + w] bit b = (q[64w+b] == symbol s) */
+    RP_DEV void build_peq(uint64_t* peq, const uint8_t* q, uint32_t n, bool rev) {
+        const uint32_t nw = (n + 63) / 64;
+        for (uint32_t idx = lane; idx < nsyms * nw; idx += 32) {
+            const uint32_t s = idx / nw, w = idx % nw;
+            const uint8_t c = static_cast<uint8_t>(syms >> (8 * s));
+            uint64_t m = 0;
+            for (uint32_t b = 0; b < 64; ++b) {
+                uint32_t i = w * 64 + b;
+                if (i >= n) break;
+                uint8_t qc = rev ? q[n - 1 - i] : q[i];
+                if (qc == c) m |= 1ull << b;
+            }
+            peq[s * nw + w] = m;
+        }
+        syncwarp();
+    }
+
+    /* One banded pass over columns 0..stop_col of the (n x m) problem with threshold k.
+     * mode 0: returns H[n-1][stop_col] (the distance when stop_col == m-1), kAlnInf if the band misses it;
+     * mode 1: additionally writes col[r+1] = H[r][stop_col] for every row r (kAlnInf outside the band),
+     *         col[0] = stop_col + 1 (the boundary row above the matrix);
+     * mode 2: additionally stores the vertical-(+1) and horizontal-(+1) words of every column (base case). */
+    RP_DEV int32_t band_pass(const uint64_t* peq, uint32_t n, const uint8_t* t, uint32_t m, bool rev_t, int32_t k,
+                             uint32_t stop_col, int mode, int32_t* col) {
+        const int32_t delta = static_cast<int32_t>(n) - static_cast<int32_t>(m);
+        const int32_t dlo = -((k - delta) / 2), dhi = (k + delta) / 2;  // diagonals i - j a cost-<=k path can touch
+        const uint32_t nw = (n + 63) / 64;
+        uint64_t pv[kAlnSlots], mv[kAlnSlots];
+#pragma unroll
+        for (int s = 0; s < kAlnSlots; ++s) {
+            pv[s] = ~0ull;
+            mv[s] = 0;
+        }
+        int32_t whi_prev = -1;   // last active word of the previous column
+        int32_t sb = 0;          // H at the bottom row of word whi_prev (after the previous column)
+        uint64_t store_pos = 0;
+        for (uint32_t j = 0; j <= stop_col; ++j) {
+            int32_t rlo = static_cast<int32_t>(j) + dlo, rhi = static_cast<int32_t>(j) + dhi;
+            if (rlo < 0) rlo = 0;
+            if (rhi > static_cast<int32_t>(n) - 1) rhi = static_cast<int32_t>(n) - 1;
+            if (rhi < rlo) {  // band left the matrix (cannot happen for k >= |delta|)
+                fail(kAlnInternal);
+                return kAlnInf;
+            }
+            const int32_t wlo = rlo >> 6, whi = rhi >> 6;
+            if (whi - wlo + 1 > 32 * kAlnSlots) {
+                fail(kAlnBandLimit);
+                return kAlnInf;
+            }
+            /* words entering the band at the bottom start with vertical +1 everywhere */
+            if (whi_prev < 0) {
+                sb = static_cast<int32_t>(j) + 64 * (whi + 1);  // column j-1 boundary: H[r][j-1] = j + r + 1 for j = 0
+                if (j != 0) sb = kAlnInf;                       // never: the first column is j = 0
+            } else {
+                sb += 64 * (whi - whi_prev);
+            }
+            for (int32_t w = whi_prev + 1; w <= whi; ++w) {
+                if ((w & 31) == lane) {
+                    const int s = (w >> 5) % kAlnSlots;
+#pragma unroll
+                    for (int q = 0; q < kAlnSlots; ++q)
+                        if (q == s) {
+                            pv[q] = ~0ull;
+                            mv[q] = 0;
+                        }
+                }
+            }
+            const uint8_t tc = rev_t ? t[m - 1 - j] : t[j];
+            const uint32_t sidx = sym_index(tc);
+            int32_t carry = 1;  // horizontal delta entering the top word of the band (edlib.cpp:766: hout = 1)
+            int32_t last_hout = 0;
+            if (mode == 2 && lane == 0) store_first[j] = (static_cast<uint32_t>(wlo) << 16) | static_cast<uint32_t>(whi - wlo + 1);
+            /* rounds of 32 consecutive words */
+            for (int32_t w0 = wlo; w0 <= whi; w0 += 32) {
+                const int32_t w = w0 + ((lane - (w0 & 31)) & 31);  // the word of this round that lives in my lane
+                const bool act = w <= whi;
+                const int s = (w >> 5) % kAlnSlots;
+                uint64_t Pv = 0, Mv = 0, Eq = 0;
+#pragma unroll
+                for (int q = 0; q < kAlnSlots; ++q)
+                    if (q == s) {
+                        Pv = pv[q];
+                        Mv = mv[q];
+                    }
+                if (act) Eq = sidx < nsyms ? peq[sidx * nw + w] : 0ull;
+                const int first_lane = w0 & 31;
+                int32_t hin = (lane == first_lane) ? carry : 0;
+                uint64_t Ph = 0, Mh = 0, Xv = 0;
+                int32_t hout = 0;
+                for (int it = 0; it < 34; ++it) {
+                    const uint64_t hneg = hin < 0 ? 1ull : 0ull;
+                    Xv = Eq | Mv;
+                    const uint64_t Eq2 = Eq | hneg;
+                    const uint64_t Xh = (((Eq2 & Pv) + Pv) ^ Pv) | Eq2;
+                    Ph = Mv | ~(Xh | Pv);
+                    Mh = Pv & Xh;
+                    hout = static_cast<int32_t>(Ph >> 63) - static_cast<int32_t>(Mh >> 63);
+                    /* my carry-in is the hout of the previous word: the lane before me (cyclically) */
+                    int32_t nh = shfl(hout, (lane + 31) & 31);
+                    if (lane == first_lane) nh = carry;
+                    const bool changed = act && nh != hin;
+                    hin = nh;
+                    if (!ballot(changed)) break;
+                }
+                /* commit */
+                uint64_t Phs = (Ph << 1) | (hin > 0 ? 1ull : 0ull);
+                uint64_t Mhs = (Mh << 1) | (hin < 0 ? 1ull : 0ull);
+                const uint64_t Pvn = Mhs | ~(Xv | Phs);
+                const uint64_t Mvn = Phs & Xv;
+                if (act) {
+#pragma unroll
+                    for (int q = 0; q < kAlnSlots; ++q)
+                        if (q == s) {
+                            pv[q] = Pvn;
+                            mv[q] = Mvn;
+                        }
+                    if (mode == 2) {
+                        const uint64_t pos = store_pos + static_cast<uint64_t>(w - wlo);
+                        if (pos < P->lim.store_words) {
+                            store_pv[pos] = Pvn;
+                            store_ph[pos] = Ph;
+                        } else {
+                            status = kAlnStoreLimit;
+                        }
+                    }
+                }
+                /* carry into the next round = hout of the last word of this round */
+                const int32_t last_w = (w0 + 31 <= whi) ? w0 + 31 : whi;
+                last_hout = shfl(hout, last_w & 31);
+                carry = last_hout;
+            }
+            if (mode == 2) {
+                store_pos += static_cast<uint64_t>(whi - wlo + 1);
+                if (ballot(status != kAlnOk)) {  // some lane ran out of store space
+                    fail(kAlnStoreLimit);
+                    return kAlnInf;
+                }
+            }
+            sb += last_hout;
+            whi_prev = whi;
+        }
+        /* H at row r of the stop column: bottom score minus the vertical deltas below r */
+        const int32_t j = static_cast<int32_t>(stop_col);
+        int32_t rlo = j + dlo, rhi = j + dhi;
+        if (rlo < 0) rlo = 0;
+        if (rhi > static_cast<int32_t>(n) - 1) rhi = static_cast<int32_t>(n) - 1;
+        const int32_t wlo = rlo >> 6, whi = rhi >> 6;
+        int32_t result = kAlnInf;
+        if (mode == 1)
+            for (uint32_t r = lane; r <= n; r += 32) col[r] = (r == 0) ? j + 1 : kAlnInf;
+        syncwarp();
+        /* walk the words from the bottom of the band up; words of one round are handled together */
+        int32_t below = 0;  // sum of vertical deltas of all words below the current round
+        for (int32_t w1 = whi; w1 >= wlo; w1 -= 32) {
+            /* this round covers words (w1-31 .. w1) clipped to wlo */
+            const int32_t wbot = w1;
+            const int32_t w = wbot - ((wbot - lane) & 31);  // the word <= wbot congruent to my lane
+            const bool act = w >= wlo && w >= wbot - 31;
+            const int s = (w >> 5) % kAlnSlots;
+            uint64_t Pv = 0, Mv = 0;
+#pragma unroll
+            for (int q = 0; q < kAlnSlots; ++q)
+                if (q == s && act) {
+                    Pv = pv[q];
+                    Mv = mv[q];
+                }
+            const int32_t mine = act ? popc64(Pv) - popc64(Mv) : 0;
+            /* suffix sum over the words of this round that lie below mine (larger w) */
+            int32_t suffix = 0;
+            for (int32_t ww = wbot; ww > wbot - 32 && ww >= wlo; --ww) {
+                const int32_t v = shfl(mine, ww & 31);
+                if (ww > w) suffix += v;
+            }
+            if (act) {
+                const int32_t hbot = sb - below - suffix;  // H at row 64w + 63
+                /* rows of my word */
+                if (mode == 1) {
+                    for (int b = 63; b >= 0; --b) {
+                        const int32_t r = w * 64 + b;
+                        if (r < static_cast<int32_t>(n) && r >= rlo && r <= rhi) {
+                            const uint64_t above = b == 63 ? 0ull : (~0ull << (b + 1));
+                            col[r + 1] = hbot - (popc64(Pv & above) - popc64(Mv & above));
+                        }
+                    }
+                }
+                const int32_t rl = static_cast<int32_t>(n) - 1;
+                if ((rl >> 6) == w && rl >= rlo && rl <= rhi) {
+                    const int b = rl & 63;
+                    const uint64_t above = b == 63 ? 0ull : (~0ull << (b + 1));
+                    result = hbot - (popc64(Pv & above) - popc64(Mv & above));
+                }
+            }
+            int32_t round_sum = 0;
+            for (int32_t ww = wbot; ww > wbot - 32 && ww >= wlo; --ww) round_sum += shfl(mine, ww & 31);
+            below += round_sum;
+        }
+        /* the lane that owns row n-1 holds the result */
+        for (int d = 16; d > 0; d >>= 1) {
+            int32_t o = shfl_down(result, d);
+            result = o < result ? o : result;
+        }
+        result = shfl(result, 0);
+        syncwarp();
+        return result;
+    }
+
+    RP_DEV void fail(uint32_t st) {
+        if (status == kAlnOk) status = st;
+    }
+
+    RP_DEV static int popc64(uint64_t x) {
+        return popc(static_cast<uint32_t>(x)) + popc(static_cast<uint32_t>(x >> 32));
+    }
+
+    /* base case: store the band, then walk back with edlib's priority up > left > diagonal (edlib.cpp:987-1097).
+     * Operations are written backwards: ops[--wpos]. */
+    RP_DEV void base_case(const uint8_t* q, uint32_t n, const uint8_t* t, uint32_t m, int32_t best, uint32_t* wpos) {
+        build_peq(peq_f, q, n, false);
+        int32_t d = band_pass(peq_f, n, t, m, false, best, m - 1, 2, nullptr);
+        if (status != kAlnOk) return;
+        if (d != best) {
+            fail(kAlnInternal);
+            return;
+        }
+        /* column offsets of the store: exclusive prefix of the per-column word counts */
+        uint32_t run = 0;
+        for (uint32_t j0 = 0; j0 < m; j0 += 32) {
+            uint32_t j = j0 + lane;
+            uint32_t cnt = j < m ? (store_first[j] & 0xffffu) : 0;
+            uint32_t inc = warp_incl_sum(cnt);
+            if (j < m) col_l[j] = static_cast<int32_t>(run + inc - cnt);  // col_l is idle here: start of column j
+            run += shfl(inc, 31);
+        }
+        syncwarp();
+        int32_t i = static_cast<int32_t>(n) - 1, j = static_cast<int32_t>(m) - 1;
+        uint32_t pos = *wpos;
+        if (lane == 0) {
+            while (i >= 0 && j >= 0) {
+                const uint32_t sf = store_first[j];
+                const int32_t wl = static_cast<int32_t>(sf >> 16), cnt = static_cast<int32_t>(sf & 0xffffu);
+                const int32_t w = i >> 6;
+                uint8_t op;
+                if (w < wl || w >= wl + cnt) {  // cannot happen: optimal paths stay inside the band
+                    status = kAlnInternal;
+                    break;
+                }
+                const uint64_t at = static_cast<uint64_t>(col_l[j]) + static_cast<uint64_t>(w - wl);
+                const uint64_t bit = 1ull << (i & 63);
+                if (store_pv[at] & bit) {
+                    op = 'I';
+                    --i;
+                } else if (store_ph[at] & bit) {
+                    op = 'D';
+                    --j;
+                } else {
+                    op = 'M';
+                    --i;
+                    --j;
+                }
+                ops[--pos] = op;
+            }
+            while (i >= 0) {
+                ops[--pos] = 'I';
+                --i;
+            }
+            while (j >= 0) {
+                ops[--pos] = 'D';
+                --j;
+            }
+        }
+        *wpos = shfl(pos, 0);
+        status = shfl(status, 0);
+        syncwarp();
+    }
+
+    RP_DEV void emit_run(uint8_t op, uint32_t count, uint32_t* wpos) {
+        uint32_t pos = *wpos;
+        for (uint32_t x = lane; x < count; x += 32) ops[pos - 1 - x] = op;
+        *wpos = pos - count;
+        syncwarp();
+    }
+
+    /* whole pair: distance, Hirschberg recursion (explicit stack), run-length encoding */
+    RP_DEV void align_pair(uint32_t p) {
+        const uint8_t* q = P->bases + P->q_off[p];
+        const uint8_t* t = P->bases + P->t_off[p];
+        const uint32_t n = P->q_len[p], m = P->t_len[p];
+        status = kAlnOk;
+        /* alphabet of the pair */
+        syms = 0;
+        nsyms = 0;
+        {
+            uint32_t seen_lo = 0;  // bitmap via repeated ballot: collect distinct bytes cooperatively
+            (void)seen_lo;
+            /* small alphabets: scan with lane 0 only for the first distinct characters (cheap: stops at 8) */
+            if (lane == 0) {
+                uint64_t sy = 0;
+                uint32_t ns = 0;
+                bool over = false;
+                for (uint32_t x = 0; x < n + m && !over; ++x) {
+                    uint8_t c = x < n ? q[x] : t[x - n];
+                    uint32_t k = 0;
+                    for (; k < ns; ++k)
+                        if (static_cast<uint8_t>(sy >> (8 * k)) == c) break;
+                    if (k == ns) {
+                        if (ns == kAlnMaxSyms)
+                            over = true;
+                        else
+                            sy |= static_cast<uint64_t>(c) << (8 * ns++);
+                    }
+                }
+                syms = sy;
+                nsyms = over ? 0xffffffffu : ns;
+            }
+            syms = shfl(syms, 0);
+            nsyms = shfl(nsyms, 0);
+            if (nsyms == 0xffffffffu) {
+                nsyms = 0;
+                fail(kAlnAlphabetLimit);
+            }
+        }
+        int32_t best = -1;
+        uint32_t n_out = 0;
+        if (status == kAlnOk) {
+            if (n == 0 || m == 0) {
+                best = static_cast<int32_t>(n + m);
+            } else {
+                build_peq(peq_f, q, n, false);
+                int32_t k = 64;
+                const int32_t kmax = static_cast<int32_t>(n > m ? n : m);
+                for (;;) {
+                    int32_t diff = static_cast<int32_t>(n) - static_cast<int32_t>(m);
+                    if (diff < 0) diff = -diff;
+                    if (k >= diff) {
+                        int32_t kk = k < kmax ? k : kmax;
+                        int32_t d = band_pass(peq_f, n, t, m, false, kk, m - 1, 0, nullptr);
+                        if (status != kAlnOk) break;
+                        if (d <= kk) {
+                            best = d;
+                            break;
+                        }
+                        if (kk == kmax) {
+                            fail(kAlnInternal);
+                            break;
+                        }
+                    }
+                    k *= 2;
+                }
+            }
+        }
+        uint32_t wpos = n + m;
+        if (status == kAlnOk) {
+            uint32_t sp = 0;
+            auto push = [&](uint32_t qo, uint32_t ql, uint32_t to, uint32_t tl, int32_t b) {
+                if (lane == 0) {
+                    stack[sp * 5 + 0] = qo;
+                    stack[sp * 5 + 1] = ql;
+                    stack[sp * 5 + 2] = to;
+                    stack[sp * 5 + 3] = tl;
+                    stack[sp * 5 + 4] = static_cast<uint32_t>(b);
+                }
+                ++sp;
+            };
+            push(0, n, 0, m, best);
+            syncwarp();
+            while (sp > 0 && status == kAlnOk) {
+                --sp;
+                const uint32_t qo = stack[sp * 5 + 0], ql = stack[sp * 5 + 1], to = stack[sp * 5 + 2],
+                               tl = stack[sp * 5 + 3];
+                const int32_t b = static_cast<int32_t>(stack[sp * 5 + 4]);
+                syncwarp();
+                if (ql == 0 || tl == 0) {  // edlib.cpp:1136-1143
+                    emit_run(ql == 0 ? 'D' : 'I', ql + tl, &wpos);
+                    continue;
+                }
+                const uint64_t blocks = (ql + 63) / 64;
+                const uint64_t data = 20ull * blocks * tl + 8ull * tl;  // edlib.cpp:1155-1157
+                if (data < 1024ull * 1024ull) {
+                    base_case(q + qo, ql, t + to, tl, b, &wpos);
+                    continue;
+                }
+                const uint32_t lw = tl / 2, rw = tl - lw;
+                build_peq(peq_f, q + qo, ql, false);
+                band_pass(peq_f, ql, t + to, tl, false, b, lw - 1, 1, col_l);      // col_l[r+1] = L[r]
+                if (status != kAlnOk) break;
+                build_peq(peq_r, q + qo, ql, true);
+                band_pass(peq_r, ql, t + to, tl, true, b, rw - 1, 1, col_r);        // col_r[x+1]: reversed rows
+                if (status != kAlnOk) break;
+                syncwarp();
+                /* R[r] = dist(q[r..], t[lw..]) = reversed-problem cell row (ql-1-r): col_r[ql - r]; R[ql] = rw */
+                uint32_t bestr = 0xffffffffu;
+                for (uint32_t r = lane; r + 2 <= ql; r += 32) {
+                    int32_t l = col_l[r + 1], rr = col_r[ql - (r + 1)];
+                    if (l + rr == b && r < bestr) bestr = r;
+                }
+                for (int d = 16; d > 0; d >>= 1) {
+                    uint32_t o = shfl_down(bestr, d);
+                    bestr = o < bestr ? o : bestr;
+                }
+                bestr = shfl(bestr, 0);
+                int32_t split, ls, rs;
+                if (bestr != 0xffffffffu) {
+                    split = static_cast<int32_t>(bestr);
+                    ls = col_l[bestr + 1];
+                    rs = col_r[ql - (bestr + 1)];
+                } else if (static_cast<int32_t>(lw) + col_r[ql] == b) {  // boundary row -1: R[0] = col_r[ql]
+                    split = -1;
+                    ls = static_cast<int32_t>(lw);
+                    rs = col_r[ql];
+                } else if (col_l[ql] + static_cast<int32_t>(rw) == b) {   // boundary row ql-1: L[ql-1] = col_l[ql]
+                    split = static_cast<int32_t>(ql) - 1;
+                    ls = col_l[ql];
+                    rs = static_cast<int32_t>(rw);
+                } else {
+                    fail(kAlnInternal);
+                    break;
+                }
+                const uint32_t ul = static_cast<uint32_t>(split + 1);
+                if (sp + 2 > 120) {
+                    fail(kAlnInternal);
+                    break;
+                }
+                push(qo, ul, to, lw, ls);
+                push(qo + ul, ql - ul, to + lw, rw, rs);  // popped first: operations are written backwards
+                syncwarp();
+            }
+        }
+        /* run-length encode ops[wpos .. n+m) */
+        if (status == kAlnOk) {
+            const uint32_t total = n + m - wpos;
+            const uint8_t* o = ops + wpos;
+            uint32_t* out = P->runs + P->run_off[p];
+            const uint32_t cap = P->run_cap[p];
+            uint32_t base = 0;
+            for (uint32_t x0 = 0; x0 < total; x0 += 32) {
+                uint32_t x = x0 + lane;
+                bool start = x < total && (x == 0 || o[x] != o[x - 1]);
+                uint32_t tot;
+                uint32_t pos = warp_rank(start, &tot);
+                if (start) {
+                    /* run length: scan forward (runs are short on real data; long runs cost one lane) */
+                    uint32_t e = x + 1;
+                    while (e < total && o[e] == o[x]) ++e;
+                    if (base + pos < cap) out[base + pos] = ((e - x) << 8) | o[x];
+                }
+                base += tot;
+            }
+            n_out = base;
+            if (n_out > cap) fail(kAlnRunLimit);
+        }
+        if (lane == 0) {
+            P->status[p] = status;
+            P->dist[p] = status == kAlnOk ? best : -1;
+            P->n_runs[p] = status == kAlnOk ? n_out : 0;
+        }
+        syncwarp();
+    }
+};
+
+RP_DEV void aln_pair(const AlnParams& P, uint32_t p, uint8_t* slot) {
+    AlnWarp W;
+    W.bind(&P, slot);
+    W.align_pair(p);
+}
+
+}  // namespace rp

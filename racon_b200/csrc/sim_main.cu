@@ -12,6 +12,7 @@
 #include <cstring>
 #include <vector>
 
+#include "myers_core.cuh"
 #include "poa_core.cuh"
 #include "poa_pack.hpp"
 
@@ -28,6 +29,17 @@ struct Job {
     uint8_t* smem;
 };
 
+struct AlnJob {
+    const rp::AlnParams* P;
+    uint32_t p;
+    uint8_t* slot;
+};
+
+void aln_entry(void* arg) {
+    AlnJob* j = static_cast<AlnJob*>(arg);
+    rp::aln_pair(*j->P, j->p, j->slot);
+}
+
 void warp_entry(void* arg) {
     Job* j = static_cast<Job*>(arg);
     rp::poa_window(*j->P, j->w, j->slot, j->smem);
@@ -36,6 +48,44 @@ void warp_entry(void* arg) {
 }  // namespace
 
 extern "C" {
+
+/* Pairwise alignment through the simulated device code.  runs: n_pairs x run_stride uint32 ((count << 8) | op). */
+int rp_sim_aln(uint32_t n_pairs, const uint8_t* bases, const uint32_t* q_off, const uint32_t* q_len,
+               const uint32_t* t_off, const uint32_t* t_len, uint32_t max_len, uint32_t store_words, uint32_t* runs,
+               uint32_t run_stride, uint32_t* n_runs, int32_t* dist, uint32_t* status) {
+    rp::AlnParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n_pairs = n_pairs;
+    P.bases = bases;
+    P.q_off = q_off;
+    P.q_len = q_len;
+    P.t_off = t_off;
+    P.t_len = t_len;
+    std::vector<uint32_t> roff(n_pairs), rcap(n_pairs, run_stride);
+    for (uint32_t p = 0; p < n_pairs; ++p) roff[p] = p * run_stride;
+    P.runs = runs;
+    P.run_off = roff.data();
+    P.run_cap = rcap.data();
+    P.n_runs = n_runs;
+    P.dist = dist;
+    P.status = status;
+    P.lim.max_len = max_len;
+    P.lim.store_words = store_words;
+    P.lay = rp::make_aln_layout(P.lim);
+    std::vector<uint8_t> slot(P.lay.bytes + 64);
+    uint8_t* slot_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slot.data()) + 15) & ~uintptr_t(15));
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        if (q_len[p] > max_len || t_len[p] > max_len) {
+            status[p] = rp::kAlnTooLong;
+            n_runs[p] = 0;
+            dist[p] = -1;
+            continue;
+        }
+        AlnJob job{&P, p, slot_al};
+        rp::sim::run_warp(aln_entry, &job);
+    }
+    return 0;
+}
 
 /* packing only (host-side cost of rp_poa_add_window): returns number of GPU windows packed */
 int rp_sim_pack_only(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,

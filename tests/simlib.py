@@ -17,6 +17,9 @@ def lib():
                                                                     C.c_void_p, C.c_void_p, C.c_uint32,
                                                                     C.c_void_p, C.c_void_p, C.c_void_p,
                                                                     C.c_void_p, C.c_void_p]
+        l.rp_sim_aln.restype = C.c_int
+        l.rp_sim_aln.argtypes = [C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
+                                                                    C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = l
     return _lib
 
@@ -45,3 +48,36 @@ def sim_consensus(ws, m=3, x=-5, g=-4, trim=True, nmax=4096, lmax=1535, ki=16, k
     cons = [out[w, :out_len[w]].tobytes() for w in range(n)]
     covs = [cov[w, :out_len[w]].copy() for w in range(n)]
     return cons, pol.astype(bool), st, covs, stats
+
+
+def runs_to_cigar(runs):
+    return "".join("%d%s" % (int(r) >> 8, chr(int(r) & 0xff)) for r in runs)
+
+
+def sim_align(pairs, max_len=None, store_words=53000):
+    """pairs: [(query bytes, target bytes), ...] -> ([(cigar, distance)], status array)"""
+    n = len(pairs)
+    blob = b"".join(q + t for q, t in pairs)
+    bases = np.frombuffer(blob, dtype=np.uint8).copy() if blob else np.zeros(1, np.uint8)
+    q_off = np.zeros(n, np.uint32)
+    q_len = np.zeros(n, np.uint32)
+    t_off = np.zeros(n, np.uint32)
+    t_len = np.zeros(n, np.uint32)
+    o = 0
+    for i, (q, t) in enumerate(pairs):
+        q_off[i], q_len[i] = o, len(q)
+        o += len(q)
+        t_off[i], t_len[i] = o, len(t)
+        o += len(t)
+    if max_len is None:
+        max_len = int(max([1] + [max(len(q), len(t)) for q, t in pairs]))
+    stride = 2 * max_len + 8
+    runs = np.zeros((n, stride), np.uint32)
+    n_runs = np.zeros(n, np.uint32)
+    dist = np.zeros(n, np.int32)
+    st = np.zeros(n, np.uint32)
+    r = lib().rp_sim_aln(n, bases.ctypes.data, q_off.ctypes.data, q_len.ctypes.data, t_off.ctypes.data,
+                         t_len.ctypes.data, max_len, store_words, runs.ctypes.data, stride, n_runs.ctypes.data,
+                         dist.ctypes.data, st.ctypes.data)
+    assert r == 0
+    return [(runs_to_cigar(runs[i, :n_runs[i]]), int(dist[i])) for i in range(n)], st

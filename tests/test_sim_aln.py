@@ -1,0 +1,45 @@
+"""Device code of the batched aligner (myers_core.cuh) through the test-only warp simulation, against the oracle
+(and, where built, the unmodified edlib): identical CIGAR strings and distances in both of edlib's regimes."""
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+from tests import simlib, util
+
+
+def _pair(rng, n, err, skew=0.0):
+    t = bytes(util.BASES[i] for i in rng.integers(4, size=n))
+    q = util.mutate(rng, t, err)
+    if skew:
+        k = int(len(q) * skew)
+        q = q[k // 2:len(q) - k // 2]
+    return q or b"A", t
+
+
+def _check(pairs, **kw):
+    got, st = simlib.sim_align(pairs, **kw)
+    assert (st == 0).all(), st
+    for (q, t), g in zip(pairs, got):
+        exp = ob.oracle_myers_cigar(q, t)
+        assert g == exp, (len(q), len(t), g[1], exp[1])
+        if ob.have_ref():
+            assert g == ob.ref_edlib_cigar(q, t)
+
+
+def test_sim_aln_small_and_degenerate():
+    pairs = [(b"A", b"A"), (b"A", b"C"), (b"ACGT", b"A"), (b"A", b"ACGT"), (b"AAAA", b"TTTT"), (b"ACGTACGT", b"ACGT"),
+             (b"ACGTTGCA" * 9, b"ACGTTGCA" * 9), (b"ACGT" * 40, b"ACGT" * 5)]
+    _check(pairs)
+
+
+@pytest.mark.parametrize("n,err,count", [(30, 0.2, 12), (64, 0.1, 8), (65, 0.3, 8), (200, 0.15, 8), (700, 0.12, 4),
+                                         (1500, 0.2, 2)])
+def test_sim_aln_traceback_regime(n, err, count):
+    rng = np.random.default_rng(n)
+    _check([_pair(rng, n, err, skew=rng.choice([0.0, 0.2])) for _ in range(count)])
+
+
+@pytest.mark.parametrize("n,err", [(2500, 0.12), (3500, 0.05), (3000, 0.3)])
+def test_sim_aln_hirschberg_regime(n, err):
+    rng = np.random.default_rng(n + 7)
+    _check([_pair(rng, n, err, skew=rng.choice([0.0, 0.15]))])
