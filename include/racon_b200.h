@@ -116,6 +116,50 @@ rp_status rp_poa_set_stream(rp_poa* p, void* cuda_stream);   /* use the caller's
 rp_status rp_poa_info(rp_poa* p, uint64_t info[8]);
 rp_status rp_poa_enable_counters(rp_poa* p, int on);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pre-alignment batch — replaces racon::CUDABatchAligner (src/cuda/cudaaligner.hpp:21-92) and the
+ * cudaaligner::Aligner it wraps (vendor/GenomeWorks/cudaaligner/include/.../aligner.hpp:56-82); per overlap it
+ * computes what Overlap::align_overlaps (src/overlap.cpp:205-224) computes with edlib:
+ * edlibAlign(query, target, NW, k = -1, TASK_PATH) -> edlibAlignmentToCigar(EDLIB_CIGAR_STANDARD).
+ * The CIGAR is byte-identical to edlib's (tests/test_gpu_aln.py).  An overlap the device cannot take
+ * (band wider than 8192 rows, sequence longer than the object's limit, > 8 distinct characters) gets a soft
+ * status and an empty CIGAR, exactly like a cudaaligner failure: the caller's CPU edlib call then handles it
+ * (src/cuda/cudapolisher.cpp:213, "overlaps whose cigar_ is still empty").
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rp_aln rp_aln;
+
+enum {
+    RP_ALN_OK = 0,
+    RP_ALN_BAND_LIMIT = 1,
+    RP_ALN_ALPHABET_LIMIT = 2,
+    RP_ALN_STORE_LIMIT = 3,
+    RP_ALN_INTERNAL = 4,
+    RP_ALN_RUN_LIMIT = 5,
+    RP_ALN_TOO_LONG = 6
+};
+
+/* createCUDABatchAligner(max_query, max_target, max_alignments, device), src/cuda/cudaaligner.cpp:18-49.
+ * max_len: longest query/target this object accepts (0 = 65536); mem_bytes: device budget (0 = 40 % of free). */
+rp_status rp_aln_create(rp_aln** out, int device, size_t mem_bytes, uint32_t max_len);
+void rp_aln_destroy(rp_aln* a);
+/* CUDABatchAligner::addOverlap (cudaaligner.cpp:51-78): query = read span, target = contig span, in racon's
+ * orientation (overlap.cpp:193-197).  RP_OK | RP_BATCH_FULL | RP_ERR_INVALID. */
+rp_status rp_aln_add(rp_aln* a, const char* q, uint32_t ql, const char* t, uint32_t tl);
+uint32_t rp_aln_size(const rp_aln* a);
+/* CUDABatchAligner::alignAll (async) / generate_cigar_strings (sync), cudaaligner.cpp:80-104 */
+rp_status rp_aln_run(rp_aln* a);
+rp_status rp_aln_sync(rp_aln* a);
+rp_status rp_aln_upload(rp_aln* a);
+rp_status rp_aln_launch(rp_aln* a);
+rp_status rp_aln_download(rp_aln* a);
+/* Overlap::cigar_ for overlap i (NUL-terminated; empty when status != RP_ALN_OK), its edit distance, soft status */
+rp_status rp_aln_fetch_cigar(rp_aln* a, uint32_t i, const char** cigar, uint32_t* len, int32_t* edit_distance,
+                             uint32_t* status);
+rp_status rp_aln_reset(rp_aln* a);
+rp_status rp_aln_set_stream(rp_aln* a, void* cuda_stream);
+/* info[0] kernel launches, [1] last H2D bytes, [2] last D2H bytes, [3] worker warps, [4] scratch bytes per warp */
+rp_status rp_aln_info(rp_aln* a, uint64_t info[8]);
+
 #ifdef __cplusplus
 }
 #endif

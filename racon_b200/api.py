@@ -70,12 +70,33 @@ def load(build_if_missing=True):
     lib.rp_poa_info.argtypes = [vp, vp]
     lib.rp_poa_enable_counters.restype = C.c_int32
     lib.rp_poa_enable_counters.argtypes = [vp, C.c_int]
+    _bind_aln(lib, C, vp, u32)
     if hasattr(lib, "rp_mirror_consensus"):
         lib.rp_mirror_consensus.restype = C.c_double
         lib.rp_mirror_consensus.argtypes = [u32] + [vp] * 8 + [C.c_int8, C.c_int8, C.c_int8, u32, C.c_int, u32, vp,
                                                                u32, vp, vp]
     _lib = lib
     return lib
+
+
+def _bind_aln(lib, C, vp, u32):
+    lib.rp_aln_create.restype = C.c_int32
+    lib.rp_aln_create.argtypes = [C.POINTER(vp), C.c_int, C.c_size_t, u32]
+    lib.rp_aln_destroy.restype = None
+    lib.rp_aln_destroy.argtypes = [vp]
+    lib.rp_aln_add.restype = C.c_int32
+    lib.rp_aln_add.argtypes = [vp, C.c_char_p, u32, C.c_char_p, u32]
+    lib.rp_aln_size.restype = u32
+    lib.rp_aln_size.argtypes = [vp]
+    for name in ("rp_aln_run", "rp_aln_sync", "rp_aln_upload", "rp_aln_launch", "rp_aln_download", "rp_aln_reset"):
+        getattr(lib, name).restype = C.c_int32
+        getattr(lib, name).argtypes = [vp]
+    lib.rp_aln_fetch_cigar.restype = C.c_int32
+    lib.rp_aln_fetch_cigar.argtypes = [vp, u32, vp, vp, vp, vp]
+    lib.rp_aln_set_stream.restype = C.c_int32
+    lib.rp_aln_set_stream.argtypes = [vp, vp]
+    lib.rp_aln_info.restype = C.c_int32
+    lib.rp_aln_info.argtypes = [vp, vp]
 
 
 def _check(lib, st, what):
@@ -193,6 +214,94 @@ class PoaBatch:
         cons = C.string_at(c, l.value) if l.value else b""
         coverage = np.ctypeslib.as_array(cov, shape=(l.value,)).copy() if (l.value and cov) else np.zeros(0, np.uint16)
         return cons, coverage, bool(pol.value)
+
+
+class AlnBatch:
+    """racon::CUDABatchAligner's shape (src/cuda/cudaaligner.hpp:21-92) over the rp_aln_* C ABI."""
+
+    def __init__(self, device=0, mem_bytes=0, max_len=0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.rp_aln_create(C.byref(self.h), device, mem_bytes, max_len), "rp_aln_create")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.rp_aln_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, query, target):
+        """addOverlap: True if taken, False if the batch is full (cudaaligner.cpp:51-78)."""
+        st = self.lib.rp_aln_add(self.h, query, len(query), target, len(target))
+        if st == 1:
+            return False
+        _check(self.lib, st, "rp_aln_add")
+        return True
+
+    def size(self):
+        return self.lib.rp_aln_size(self.h)
+
+    def set_stream(self, cuda_stream):
+        _check(self.lib, self.lib.rp_aln_set_stream(self.h, C.c_void_p(cuda_stream)), "rp_aln_set_stream")
+
+    def upload(self):
+        _check(self.lib, self.lib.rp_aln_upload(self.h), "rp_aln_upload")
+
+    def launch(self):
+        _check(self.lib, self.lib.rp_aln_launch(self.h), "rp_aln_launch")
+
+    def download(self):
+        _check(self.lib, self.lib.rp_aln_download(self.h), "rp_aln_download")
+
+    def run(self):
+        _check(self.lib, self.lib.rp_aln_run(self.h), "rp_aln_run")
+
+    def sync(self):
+        _check(self.lib, self.lib.rp_aln_sync(self.h), "rp_aln_sync")
+
+    def reset(self):
+        _check(self.lib, self.lib.rp_aln_reset(self.h), "rp_aln_reset")
+
+    def info(self):
+        a = (C.c_uint64 * 8)()
+        _check(self.lib, self.lib.rp_aln_info(self.h, a), "rp_aln_info")
+        return {"launches": a[0], "h2d_bytes": a[1], "d2h_bytes": a[2], "workers": a[3], "scratch_per_warp": a[4]}
+
+    def fetch(self, i):
+        """(cigar bytes, edit distance, status) of overlap i."""
+        p = C.c_char_p()
+        n = C.c_uint32()
+        d = C.c_int32()
+        st = C.c_uint32()
+        _check(self.lib, self.lib.rp_aln_fetch_cigar(self.h, i, C.byref(p), C.byref(n), C.byref(d), C.byref(st)),
+               "rp_aln_fetch_cigar")
+        return (p.value or b"")[: n.value], d.value, st.value
+
+
+def align(pairs, device=0, max_len=0):
+    """CIGARs for [(query, target), ...] as Overlap::align_overlaps would get them from edlib (overlap.cpp:205-224)."""
+    b = AlnBatch(device=device, max_len=max_len)
+    out = []
+    try:
+        i = 0
+        while i < len(pairs):
+            b.reset()
+            first = i
+            while i < len(pairs) and b.add(*pairs[i]):
+                i += 1
+            if i == first:
+                raise RaconB200Error("pair %d does not fit an empty batch" % i)
+            b.run()
+            b.sync()
+            out.extend(b.fetch(k) for k in range(i - first))
+    finally:
+        b.close()
+    return out
 
 
 def consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=500, device=0, want_coverage=False,

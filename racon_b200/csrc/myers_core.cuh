@@ -416,30 +416,36 @@ struct AlnWarp {
         syms = 0;
         nsyms = 0;
         {
-            uint32_t seen_lo = 0;  // bitmap via repeated ballot: collect distinct bytes cooperatively
-            (void)seen_lo;
-            /* small alphabets: scan with lane 0 only for the first distinct characters (cheap: stops at 8) */
-            if (lane == 0) {
-                uint64_t sy = 0;
-                uint32_t ns = 0;
-                bool over = false;
-                for (uint32_t x = 0; x < n + m && !over; ++x) {
-                    uint8_t c = x < n ? q[x] : t[x - n];
-                    uint32_t k = 0;
-                    for (; k < ns; ++k)
-                        if (static_cast<uint8_t>(sy >> (8 * k)) == c) break;
-                    if (k == ns) {
-                        if (ns == kAlnMaxSyms)
-                            over = true;
-                        else
-                            sy |= static_cast<uint64_t>(c) << (8 * ns++);
-                    }
-                }
-                syms = sy;
-                nsyms = over ? 0xffffffffu : ns;
+            /* 256-bit "seen" bitmap per lane over a strided share of the bytes, OR-reduced across the warp */
+            uint32_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (uint32_t x = lane; x < n + m; x += 32) {
+                const uint32_t c = x < n ? q[x] : t[x - n];
+                const uint32_t bit = 1u << (c & 31);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) seen[k] |= (c >> 5) == static_cast<uint32_t>(k) ? bit : 0u;
             }
-            syms = shfl(syms, 0);
-            nsyms = shfl(nsyms, 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) seen[k] |= shfl(seen[k], lane ^ d);
+            }
+            uint64_t sy = 0;
+            uint32_t ns = 0;
+            bool over = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t wbits = seen[k];
+                while (wbits && !over) {
+                    const uint32_t c = static_cast<uint32_t>(k) * 32 + static_cast<uint32_t>(ffs_(wbits) - 1);
+                    wbits &= wbits - 1;
+                    if (ns == kAlnMaxSyms)
+                        over = true;
+                    else
+                        sy |= static_cast<uint64_t>(c) << (8 * ns++);
+                }
+            }
+            syms = sy;
+            nsyms = over ? 0xffffffffu : ns;
             if (nsyms == 0xffffffffu) {
                 nsyms = 0;
                 fail(kAlnAlphabetLimit);

@@ -17,6 +17,7 @@
 #include <thread>
 #include <vector>
 
+#include "myers_core.cuh"
 #include "poa_core.cuh"
 #include "poa_pack.hpp"
 #include "racon_b200.h"
@@ -97,7 +98,49 @@ PoaKernel pick_kernel(int blocks_per_sm) {
     }
 }
 
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rp_aln_kernel(rp::AlnParams P) {
+    const int warp = threadIdx.x >> 5;
+    const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + warp;
+    uint8_t* slot = P.scratch + static_cast<uint64_t>(worker) * P.lay.bytes;
+    for (;;) {
+        uint32_t q = 0;
+        if ((threadIdx.x & 31) == 0) q = atomicAdd(P.queue_head, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= P.n_pairs) break;
+        rp::aln_pair(P, P.queue[q], slot);
+    }
+}
+
 }  // namespace
+
+struct rp_aln {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    rp::AlnParams P;
+    rp::GrowBuf<uint8_t> bases;
+    rp::GrowBuf<uint32_t> q_off, q_len, t_off, t_len, run_off, run_cap, queue;
+    std::vector<uint32_t> pre_status;      // per pair: soft status decided on the host (too long) or 0
+    uint64_t run_total = 0;
+    DevBuf d_bases, d_q_off, d_q_len, d_t_off, d_t_len, d_run_off, d_run_cap, d_queue, d_runs, d_n_runs, d_dist,
+        d_status, d_head, d_scratch;
+    rp::GrowBuf<uint32_t> h_runs, h_n_runs, h_status;
+    rp::GrowBuf<int32_t> h_dist;
+    std::vector<std::string> cigars;
+    std::vector<uint8_t> cigar_built;
+    uint32_t workers = 0;
+    int grid = 0;
+    uint32_t max_len = 0;
+    uint64_t max_bases = 0;
+    bool uploaded = false, launched = false, downloaded = false, synced = false;
+    uint64_t launches = 0, last_h2d = 0, last_d2h = 0;
+    rp_aln()
+        : bases(&kPinned), q_off(&kPinned), q_len(&kPinned), t_off(&kPinned), t_len(&kPinned), run_off(&kPinned),
+          run_cap(&kPinned), queue(&kPinned), h_runs(&kPinned), h_n_runs(&kPinned), h_status(&kPinned),
+          h_dist(&kPinned) {
+        std::memset(&P, 0, sizeof(P));
+    }
+};
 
 struct rp_poa {
     int device = 0;
@@ -608,6 +651,272 @@ rp_status rp_poa_info(rp_poa* p, uint64_t info[8]) {
 rp_status rp_poa_enable_counters(rp_poa* p, int on) {
     if (!p) return fail(RP_ERR_INVALID, "null object");
     p->counters = on != 0;
+    return RP_OK;
+}
+
+
+/* ---------------------------------------------------------------------------------------------------------
+ * pre-alignment batch (racon::CUDABatchAligner shape)
+ * --------------------------------------------------------------------------------------------------------- */
+rp_status rp_aln_create(rp_aln** out, int device, size_t mem_bytes, uint32_t max_len) {
+    if (!out) return fail(RP_ERR_INVALID, "null out");
+    *out = nullptr;
+    int ndev = rp_device_count();
+    if (ndev <= 0) return fail(RP_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RP_ERR_INVALID, "device index out of range");
+    RP_CUDA(cudaSetDevice(device));
+    rp_aln* a = new (std::nothrow) rp_aln();
+    if (!a) return fail(RP_ERR_NOMEM, "host allocation failed");
+    a->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete a;
+        return fail(RP_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (mem_bytes == 0 || mem_bytes > free_b) mem_bytes = static_cast<size_t>(free_b * 0.4);
+    a->max_len = max_len ? max_len : 65536;
+    a->P.lim.max_len = a->max_len;
+    a->P.lim.store_words = 53000;  // > 1 MiB / 20 B: the largest base case edlib's rule allows
+    a->P.lay = rp::make_aln_layout(a->P.lim);
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp_aln_kernel, kWarpsPerBlock * 32, 0);
+    if (e != cudaSuccess || occ < 1) {
+        rp_aln_destroy(a);
+        return fail(RP_ERR_CUDA, std::string("kernel configuration: ") + cudaGetErrorString(e));
+    }
+    uint64_t max_workers = static_cast<uint64_t>(prop.multiProcessorCount) * occ * kWarpsPerBlock;
+    uint64_t fit = (mem_bytes / 2) / a->P.lay.bytes;
+    uint64_t workers = std::min(max_workers, fit) / kWarpsPerBlock * kWarpsPerBlock;
+    if (workers < kWarpsPerBlock) {
+        rp_aln_destroy(a);
+        return fail(RP_ERR_NOMEM, "memory budget too small for one block of aligner workers");
+    }
+    a->workers = static_cast<uint32_t>(workers);
+    a->grid = static_cast<int>(workers / kWarpsPerBlock);
+    a->max_bases = std::min<uint64_t>(0xfff00000ull, mem_bytes / 8);
+    e = a->d_scratch.reserve(workers * a->P.lay.bytes);
+    if (e == cudaSuccess) e = a->d_head.reserve(256);
+    if (e != cudaSuccess) {
+        rp_aln_destroy(a);
+        return fail(RP_ERR_NOMEM, std::string("scratch allocation: ") + cudaGetErrorString(e));
+    }
+    *out = a;
+    return RP_OK;
+}
+
+void rp_aln_destroy(rp_aln* a) {
+    if (!a) return;
+    cudaSetDevice(a->device);
+    if (a->stream) cudaStreamSynchronize(a->stream);
+    DevBuf* bufs[] = {&a->d_bases, &a->d_q_off, &a->d_q_len, &a->d_t_off, &a->d_t_len, &a->d_run_off, &a->d_run_cap,
+                      &a->d_queue, &a->d_runs, &a->d_n_runs, &a->d_dist, &a->d_status, &a->d_head, &a->d_scratch};
+    for (DevBuf* b : bufs) b->release();
+    if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
+    delete a;
+}
+
+rp_status rp_aln_set_stream(rp_aln* a, void* cuda_stream) {
+    if (!a) return fail(RP_ERR_INVALID, "null object");
+    if (a->own_stream && a->stream) {
+        cudaStreamSynchronize(a->stream);
+        cudaStreamDestroy(a->stream);
+    }
+    a->stream = static_cast<cudaStream_t>(cuda_stream);
+    a->own_stream = false;
+    return RP_OK;
+}
+
+rp_status rp_aln_add(rp_aln* a, const char* q, uint32_t ql, const char* t, uint32_t tl) {
+    if (!a || (!q && ql) || (!t && tl)) return fail(RP_ERR_INVALID, "null argument");
+    if (a->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
+    const bool too_long = ql > a->max_len || tl > a->max_len;
+    const uint64_t add = too_long ? 0 : static_cast<uint64_t>(ql) + tl;
+    if (a->bases.size + add > a->max_bases) return RP_BATCH_FULL;
+    uint32_t off = static_cast<uint32_t>(a->bases.size);
+    if (!too_long) {
+        uint8_t* b = a->bases.extend(add);
+        if (!b) return fail(RP_ERR_NOMEM, "pinned staging allocation failed");
+        std::memcpy(b, q, ql);
+        std::memcpy(b + ql, t, tl);
+    }
+    const uint32_t cap = too_long ? 0 : (ql + tl) / 3 + 64;
+    if (!a->q_off.push(off) || !a->q_len.push(too_long ? 0 : ql) || !a->t_off.push(off + (too_long ? 0 : ql)) ||
+        !a->t_len.push(too_long ? 0 : tl) || !a->run_off.push(static_cast<uint32_t>(a->run_total)) ||
+        !a->run_cap.push(cap))
+        return fail(RP_ERR_NOMEM, "pinned staging allocation failed");
+    a->run_total += cap;
+    a->pre_status.push_back(too_long ? RP_ALN_TOO_LONG : RP_ALN_OK);
+    return RP_OK;
+}
+
+uint32_t rp_aln_size(const rp_aln* a) { return a ? static_cast<uint32_t>(a->pre_status.size()) : 0; }
+
+rp_status rp_aln_upload(rp_aln* a) {
+    if (!a) return fail(RP_ERR_INVALID, "null object");
+    RP_CUDA(cudaSetDevice(a->device));
+    const uint32_t n = rp_aln_size(a);
+    /* longest pairs first */
+    std::vector<uint32_t> idx(n);
+    for (uint32_t i = 0; i < n; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) {
+        return static_cast<uint64_t>(a->q_len.data[x]) * a->t_len.data[x] >
+               static_cast<uint64_t>(a->q_len.data[y]) * a->t_len.data[y];
+    });
+    a->queue.clear();
+    if (!a->queue.reserve(n ? n : 1)) return fail(RP_ERR_NOMEM, "queue allocation failed");
+    for (uint32_t i = 0; i < n; ++i) a->queue.push(idx[i]);
+    uint64_t h2d = 0;
+    auto up = [&](DevBuf& d, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = d.reserve(bytes ? bytes : 16);
+        if (e != cudaSuccess) return e;
+        h2d += bytes;
+        return bytes ? cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, a->stream) : cudaSuccess;
+    };
+    RP_CUDA(up(a->d_bases, a->bases.data, a->bases.bytes()));
+    RP_CUDA(up(a->d_q_off, a->q_off.data, a->q_off.bytes()));
+    RP_CUDA(up(a->d_q_len, a->q_len.data, a->q_len.bytes()));
+    RP_CUDA(up(a->d_t_off, a->t_off.data, a->t_off.bytes()));
+    RP_CUDA(up(a->d_t_len, a->t_len.data, a->t_len.bytes()));
+    RP_CUDA(up(a->d_run_off, a->run_off.data, a->run_off.bytes()));
+    RP_CUDA(up(a->d_run_cap, a->run_cap.data, a->run_cap.bytes()));
+    RP_CUDA(up(a->d_queue, a->queue.data, a->queue.bytes()));
+    RP_CUDA(a->d_runs.reserve((a->run_total + 16) * 4));
+    RP_CUDA(a->d_n_runs.reserve((n + 1) * 4));
+    RP_CUDA(a->d_dist.reserve((n + 1) * 4));
+    RP_CUDA(a->d_status.reserve((n + 1) * 4));
+    if (!a->h_runs.reserve(a->run_total + 16) || !a->h_n_runs.reserve(n + 1) || !a->h_status.reserve(n + 1) ||
+        !a->h_dist.reserve(n + 1))
+        return fail(RP_ERR_NOMEM, "pinned result allocation failed");
+    rp::AlnParams& P = a->P;
+    P.n_pairs = n;
+    P.bases = static_cast<const uint8_t*>(a->d_bases.p);
+    P.q_off = static_cast<const uint32_t*>(a->d_q_off.p);
+    P.q_len = static_cast<const uint32_t*>(a->d_q_len.p);
+    P.t_off = static_cast<const uint32_t*>(a->d_t_off.p);
+    P.t_len = static_cast<const uint32_t*>(a->d_t_len.p);
+    P.queue = static_cast<const uint32_t*>(a->d_queue.p);
+    P.queue_head = static_cast<uint32_t*>(a->d_head.p);
+    P.runs = static_cast<uint32_t*>(a->d_runs.p);
+    P.run_off = static_cast<const uint32_t*>(a->d_run_off.p);
+    P.run_cap = static_cast<const uint32_t*>(a->d_run_cap.p);
+    P.n_runs = static_cast<uint32_t*>(a->d_n_runs.p);
+    P.dist = static_cast<int32_t*>(a->d_dist.p);
+    P.status = static_cast<uint32_t*>(a->d_status.p);
+    P.scratch = static_cast<uint8_t*>(a->d_scratch.p);
+    a->last_h2d = h2d;
+    a->uploaded = true;
+    a->launched = a->downloaded = a->synced = false;
+    return RP_OK;
+}
+
+rp_status rp_aln_launch(rp_aln* a) {
+    if (!a) return fail(RP_ERR_INVALID, "null object");
+    if (!a->uploaded) return fail(RP_ERR_STATE, "launch before upload");
+    RP_CUDA(cudaSetDevice(a->device));
+    if (a->P.n_pairs > 0) {
+        RP_CUDA(cudaMemsetAsync(a->d_head.p, 0, 4, a->stream));
+        rp_aln_kernel<<<a->grid, kWarpsPerBlock * 32, 0, a->stream>>>(a->P);
+        RP_CUDA(cudaGetLastError());
+        a->launches += 1;
+    }
+    a->launched = true;
+    a->downloaded = a->synced = false;
+    return RP_OK;
+}
+
+rp_status rp_aln_download(rp_aln* a) {
+    if (!a) return fail(RP_ERR_INVALID, "null object");
+    if (!a->launched) return fail(RP_ERR_STATE, "download before launch");
+    RP_CUDA(cudaSetDevice(a->device));
+    const uint32_t n = a->P.n_pairs;
+    uint64_t d2h = 0;
+    if (n > 0) {
+        RP_CUDA(cudaMemcpyAsync(a->h_n_runs.data, a->d_n_runs.p, n * 4, cudaMemcpyDeviceToHost, a->stream));
+        RP_CUDA(cudaMemcpyAsync(a->h_dist.data, a->d_dist.p, n * 4, cudaMemcpyDeviceToHost, a->stream));
+        RP_CUDA(cudaMemcpyAsync(a->h_status.data, a->d_status.p, n * 4, cudaMemcpyDeviceToHost, a->stream));
+        RP_CUDA(cudaMemcpyAsync(a->h_runs.data, a->d_runs.p, a->run_total * 4, cudaMemcpyDeviceToHost, a->stream));
+        d2h = a->run_total * 4 + static_cast<uint64_t>(n) * 12;
+    }
+    a->last_d2h = d2h;
+    a->cigars.assign(n, std::string());
+    a->cigar_built.assign(n, 0);
+    a->downloaded = true;
+    a->synced = false;
+    return RP_OK;
+}
+
+rp_status rp_aln_run(rp_aln* a) {
+    rp_status s = rp_aln_upload(a);
+    if (s != RP_OK) return s;
+    s = rp_aln_launch(a);
+    if (s != RP_OK) return s;
+    return rp_aln_download(a);
+}
+
+rp_status rp_aln_sync(rp_aln* a) {
+    if (!a) return fail(RP_ERR_INVALID, "null object");
+    RP_CUDA(cudaSetDevice(a->device));
+    RP_CUDA(cudaStreamSynchronize(a->stream));
+    if (a->downloaded) a->synced = true;
+    return RP_OK;
+}
+
+rp_status rp_aln_fetch_cigar(rp_aln* a, uint32_t i, const char** cigar, uint32_t* len, int32_t* edit_distance,
+                             uint32_t* status) {
+    if (!a) return fail(RP_ERR_INVALID, "null object");
+    if (!a->downloaded) return fail(RP_ERR_STATE, "fetch before run/download");
+    if (!a->synced) {
+        rp_status s = rp_aln_sync(a);
+        if (s != RP_OK) return s;
+    }
+    if (i >= rp_aln_size(a)) return fail(RP_ERR_INVALID, "overlap index out of range");
+    uint32_t st = a->pre_status[i] ? a->pre_status[i] : a->h_status.data[i];
+    if (!a->cigar_built[i]) {
+        std::string& c = a->cigars[i];
+        if (st == RP_ALN_OK) {
+            const uint32_t* r = a->h_runs.data + a->run_off.data[i];
+            const uint32_t nr = a->h_n_runs.data[i];
+            char tmp[16];
+            for (uint32_t k = 0; k < nr; ++k) {
+                int w = snprintf(tmp, sizeof(tmp), "%u%c", r[k] >> 8, static_cast<char>(r[k] & 0xff));
+                c.append(tmp, static_cast<size_t>(w));
+            }
+        }
+        a->cigar_built[i] = 1;
+    }
+    if (cigar) *cigar = a->cigars[i].c_str();
+    if (len) *len = static_cast<uint32_t>(a->cigars[i].size());
+    if (edit_distance) *edit_distance = st == RP_ALN_OK ? a->h_dist.data[i] : -1;
+    if (status) *status = st;
+    return RP_OK;
+}
+
+rp_status rp_aln_reset(rp_aln* a) {
+    if (!a) return fail(RP_ERR_INVALID, "null object");
+    cudaSetDevice(a->device);
+    if (a->stream) RP_CUDA(cudaStreamSynchronize(a->stream));
+    a->bases.clear(); a->q_off.clear(); a->q_len.clear(); a->t_off.clear(); a->t_len.clear();
+    a->run_off.clear(); a->run_cap.clear(); a->queue.clear();
+    a->pre_status.clear();
+    a->run_total = 0;
+    a->cigars.clear();
+    a->cigar_built.clear();
+    a->uploaded = a->launched = a->downloaded = a->synced = false;
+    return RP_OK;
+}
+
+rp_status rp_aln_info(rp_aln* a, uint64_t info[8]) {
+    if (!a || !info) return fail(RP_ERR_INVALID, "null argument");
+    std::memset(info, 0, 8 * sizeof(uint64_t));
+    info[0] = a->launches;
+    info[1] = a->last_h2d;
+    info[2] = a->last_d2h;
+    info[3] = a->workers;
+    info[4] = a->P.lay.bytes;
     return RP_OK;
 }
 
