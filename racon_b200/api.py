@@ -71,6 +71,9 @@ def load(build_if_missing=True):
     lib.rp_poa_enable_counters.restype = C.c_int32
     lib.rp_poa_enable_counters.argtypes = [vp, C.c_int]
     _bind_aln(lib, C, vp, u32)
+    if hasattr(lib, "rp_mirror_align"):
+        lib.rp_mirror_align.restype = C.c_int
+        lib.rp_mirror_align.argtypes = [u32, vp, vp, vp, vp, vp, u32, u32, vp, u32]
     if hasattr(lib, "rp_mirror_consensus"):
         lib.rp_mirror_consensus.restype = C.c_double
         lib.rp_mirror_consensus.argtypes = [u32] + [vp] * 8 + [C.c_int8, C.c_int8, C.c_int8, u32, C.c_int, u32, vp,
@@ -302,6 +305,35 @@ def align(pairs, device=0, max_len=0):
     finally:
         b.close()
     return out
+
+
+def mirror_align(pairs, max_alignments=0, device=0):
+    """CIGARs through the C++ mirror of CUDABatchAligner (host_mirror.hpp), driven like
+    CUDAPolisher::find_overlap_breaking_points drives the reference's batches (cudapolisher.cpp:100-213)."""
+    lib = load()
+    n = len(pairs)
+    blob = b"".join(q + t for q, t in pairs)
+    q_off = np.zeros(n, np.uint64)
+    t_off = np.zeros(n, np.uint64)
+    q_len = np.array([len(q) for q, _ in pairs], np.uint32)
+    t_len = np.array([len(t) for _, t in pairs], np.uint32)
+    o = 0
+    for i, (q, t) in enumerate(pairs):
+        q_off[i] = o
+        t_off[i] = o + len(q)
+        o += len(q) + len(t)
+    stride = int(max((len(q) + len(t)) for q, t in pairs) * 4 + 16) if n else 16
+    out = np.zeros(max(n, 1) * stride, np.uint8)
+    buf = np.frombuffer(blob if blob else b"\0", np.uint8)
+    r = lib.rp_mirror_align(n, _ptr(buf), _ptr(q_off), _ptr(q_len), _ptr(t_off), _ptr(t_len), max_alignments, device,
+                            _ptr(out), stride)
+    if r != 0:
+        raise RaconB200Error("rp_mirror_align failed: %d" % r)
+    res = []
+    for i in range(n):
+        row = out[i * stride:(i + 1) * stride].tobytes()
+        res.append(row[: row.index(b"\0")])
+    return res
 
 
 def consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=500, device=0, want_coverage=False,

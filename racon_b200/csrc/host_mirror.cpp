@@ -132,7 +132,99 @@ void BatchProcessor::reset() {
     rp_poa_reset(poa_);
 }
 
+/* ---- BatchAligner ---- */
+std::atomic<uint32_t> BatchAligner::batches{0};
+
+std::unique_ptr<BatchAligner> createBatchAligner(uint32_t max_query_size, uint32_t max_target_size,
+                                                 uint32_t max_alignments, uint32_t device_id) {
+    return std::unique_ptr<BatchAligner>(new BatchAligner(max_query_size, max_target_size, max_alignments, device_id));
+}
+
+BatchAligner::BatchAligner(uint32_t max_query_size, uint32_t max_target_size, uint32_t max_alignments,
+                           uint32_t device_id)
+    : max_alignments_(max_alignments) {
+    bid_ = batches++;
+    rp_status s = rp_aln_create(&aln_, static_cast<int>(device_id), 0,
+                                max_query_size > max_target_size ? max_query_size : max_target_size);
+    if (s != RP_OK) {
+        fprintf(stderr, "[racon_b200::BatchAligner] error: %s (%s)\n", rp_strerror(s), rp_last_error());
+        exit(1);
+    }
+}
+
+BatchAligner::~BatchAligner() { rp_aln_destroy(aln_); }
+
+bool BatchAligner::addOverlap(const char* q, uint32_t q_len, const char* t, uint32_t t_len, std::string* cigar) {
+    if (max_alignments_ && cigars_.size() >= max_alignments_) return false;
+    rp_status s = rp_aln_add(aln_, q, q_len, t, t_len);
+    if (s == RP_BATCH_FULL) return false;
+    if (s != RP_OK) {
+        fprintf(stderr, "[racon_b200::BatchAligner::addOverlap] error: %s (%s)\n", rp_strerror(s), rp_last_error());
+        exit(1);
+    }
+    cigars_.push_back(cigar);
+    return true;
+}
+
+void BatchAligner::alignAll() {
+    rp_status s = rp_aln_run(aln_);
+    if (s != RP_OK) {
+        fprintf(stderr, "[racon_b200::BatchAligner::alignAll] error: %s (%s)\n", rp_strerror(s), rp_last_error());
+        exit(1);
+    }
+}
+
+void BatchAligner::generate_cigar_strings() {
+    rp_status s = rp_aln_sync(aln_);
+    if (s != RP_OK) {
+        fprintf(stderr, "[racon_b200::BatchAligner::generate_cigar_strings] error: %s (%s)\n", rp_strerror(s),
+                rp_last_error());
+        exit(1);
+    }
+    for (uint32_t i = 0; i < cigars_.size(); ++i) {
+        const char* c = nullptr;
+        uint32_t l = 0, st = 0;
+        rp_aln_fetch_cigar(aln_, i, &c, &l, nullptr, &st);
+        if (cigars_[i]) cigars_[i]->assign(st == RP_ALN_OK ? c : "", st == RP_ALN_OK ? l : 0);
+    }
+}
+
+void BatchAligner::reset() {
+    cigars_.clear();
+    rp_aln_reset(aln_);
+}
+
 }  // namespace racon_b200
+
+/* Test hook: CUDAPolisher::find_overlap_breaking_points' batch loop (cudapolisher.cpp:100-213) over flat pairs:
+ * fill a batch until addOverlap refuses, alignAll, generate_cigar_strings, reset, continue.  out: NUL-terminated
+ * CIGARs at out + i * stride (empty when the device could not take the overlap). */
+extern "C" int rp_mirror_align(uint32_t n_pairs, const char* bases, const uint64_t* q_off, const uint32_t* q_len,
+                               const uint64_t* t_off, const uint32_t* t_len, uint32_t max_alignments, uint32_t device,
+                               char* out, uint32_t stride) {
+    using namespace racon_b200;
+    uint32_t mq = 1, mt = 1;
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        if (q_len[i] > mq) mq = q_len[i];
+        if (t_len[i] > mt) mt = t_len[i];
+    }
+    auto batch = createBatchAligner(mq, mt, max_alignments, device);
+    std::vector<std::string> cigars(n_pairs);
+    uint32_t i = 0;
+    while (i < n_pairs) {
+        uint32_t first = i;
+        while (i < n_pairs && batch->addOverlap(bases + q_off[i], q_len[i], bases + t_off[i], t_len[i], &cigars[i])) ++i;
+        if (i == first) return -1;
+        batch->alignAll();
+        batch->generate_cigar_strings();
+        batch->reset();
+    }
+    for (uint32_t k = 0; k < n_pairs; ++k) {
+        if (cigars[k].size() + 1 > stride) return -2;
+        std::memcpy(out + static_cast<uint64_t>(k) * stride, cigars[k].c_str(), cigars[k].size() + 1);
+    }
+    return 0;
+}
 
 /* Test hook: drives the mirror classes exactly like CUDAPolisher::polish drives CUDABatchProcessor
  * (cudapolisher.cpp:254-276), over a flat window set. Same contract as oracle/ref_harness.cpp. */

@@ -15,6 +15,7 @@
 #include <vector>
 
 struct rp_poa;
+struct rp_aln;
 
 namespace racon_b200 {
 
@@ -88,6 +89,39 @@ private:
     bool trim_ = true;
     std::vector<std::shared_ptr<Window>> windows_;
     std::vector<bool> window_consensus_status_;
+};
+
+/* Mirror of racon::CUDABatchAligner (src/cuda/cudaaligner.hpp:21-92).  The reference's addOverlap takes an
+ * Overlap* plus the sequence table and derives the two spans (cudaaligner.cpp:53-58); the mirror takes the spans and a
+ * pointer to the std::string that plays Overlap::cigar_. */
+class BatchAligner;
+std::unique_ptr<BatchAligner> createBatchAligner(uint32_t max_query_size, uint32_t max_target_size,
+                                                 uint32_t max_alignments, uint32_t device_id);
+
+class BatchAligner {
+public:
+    ~BatchAligner();
+    /* false = batch full (exceeded_max_alignments / exceeded_max_length are soft: an over-long overlap is
+     * accepted and simply keeps an empty cigar, as in cudaaligner.cpp:61-77) */
+    bool addOverlap(const char* q, uint32_t q_len, const char* t, uint32_t t_len, std::string* cigar);
+    bool hasOverlaps() const { return !cigars_.empty(); }
+    void alignAll();                  // asynchronous launch (cudaaligner.cpp:80-84)
+    void generate_cigar_strings();    // sync + fill every *cigar (cudaaligner.cpp:86-104)
+    void reset();
+    uint32_t getBatchID() const { return bid_; }
+
+    friend std::unique_ptr<BatchAligner> createBatchAligner(uint32_t, uint32_t, uint32_t, uint32_t);
+
+private:
+    BatchAligner(uint32_t max_query_size, uint32_t max_target_size, uint32_t max_alignments, uint32_t device_id);
+    BatchAligner(const BatchAligner&) = delete;
+    const BatchAligner& operator=(const BatchAligner&) = delete;
+
+    static std::atomic<uint32_t> batches;
+    uint32_t bid_ = 0;
+    uint32_t max_alignments_ = 0;
+    rp_aln* aln_ = nullptr;
+    std::vector<std::string*> cigars_;
 };
 
 }  // namespace racon_b200

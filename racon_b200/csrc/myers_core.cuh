@@ -125,18 +125,24 @@ struct AlnWarp {
 
     /* match masks of the (possibly reversed) query sub-range: peq[s * nw + w] bit b = (q[64w+b] == symbol s) */
     RP_DEV void build_peq(uint64_t* peq, const uint8_t* q, uint32_t n, bool rev) {
+        /* 32 bases per step: one coalesced byte load, one ballot per symbol; lane s keeps symbol s's 32 bits */
         const uint32_t nw = (n + 63) / 64;
-        for (uint32_t idx = lane; idx < nsyms * nw; idx += 32) {
-            const uint32_t s = idx / nw, w = idx % nw;
-            const uint8_t c = static_cast<uint8_t>(syms >> (8 * s));
-            uint64_t m = 0;
-            for (uint32_t b = 0; b < 64; ++b) {
-                uint32_t i = w * 64 + b;
-                if (i >= n) break;
-                uint8_t qc = rev ? q[n - 1 - i] : q[i];
-                if (qc == c) m |= 1ull << b;
+        uint32_t* peq32 = reinterpret_cast<uint32_t*>(peq);
+        const uint32_t my_sym = lane < static_cast<int>(nsyms) ? static_cast<uint32_t>((syms >> (8 * lane)) & 0xff) : 0u;
+        (void)my_sym;
+        for (uint32_t g = 0; g < nw * 2; ++g) {
+            const uint32_t i = g * 32 + static_cast<uint32_t>(lane);
+            const bool valid = i < n;
+            const uint32_t c = valid ? (rev ? q[n - 1 - i] : q[i]) : 0u;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int sidx = 0; sidx < kAlnMaxSyms; ++sidx) {
+                if (sidx < static_cast<int>(nsyms)) {
+                    const uint32_t bits = ballot(valid && c == static_cast<uint32_t>((syms >> (8 * sidx)) & 0xff));
+                    if (lane == sidx) mine = bits;
+                }
             }
-            peq[s * nw + w] = m;
+            if (lane < static_cast<int>(nsyms)) peq32[(static_cast<uint64_t>(lane) * nw + (g >> 1)) * 2 + (g & 1)] = mine;
         }
         syncwarp();
     }
@@ -458,7 +464,9 @@ struct AlnWarp {
                 best = static_cast<int32_t>(n + m);
             } else {
                 build_peq(peq_f, q, n, false);
-                int32_t k = 64;
+                /* a column costs one round per 32 band words whatever the fill, so start with the widest band that
+                 * still fits one round (band = k + 1 rows); the distance found does not depend on the schedule */
+                int32_t k = 64 * 29;
                 const int32_t kmax = static_cast<int32_t>(n > m ? n : m);
                 for (;;) {
                     int32_t diff = static_cast<int32_t>(n) - static_cast<int32_t>(m);

@@ -98,7 +98,8 @@ PoaKernel pick_kernel(int blocks_per_sm) {
     }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) rp_aln_kernel(rp::AlnParams P) {
+template <int kBlocksPerSm>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_aln_kernel(rp::AlnParams P) {
     const int warp = threadIdx.x >> 5;
     const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + warp;
     uint8_t* slot = P.scratch + static_cast<uint64_t>(worker) * P.lay.bytes;
@@ -130,6 +131,7 @@ struct rp_aln {
     std::vector<uint8_t> cigar_built;
     uint32_t workers = 0;
     int grid = 0;
+    int blocks_per_sm = 4;
     uint32_t max_len = 0;
     uint64_t max_bases = 0;
     bool uploaded = false, launched = false, downloaded = false, synced = false;
@@ -683,7 +685,16 @@ rp_status rp_aln_create(rp_aln** out, int device, size_t mem_bytes, uint32_t max
     a->P.lim.store_words = 53000;  // > 1 MiB / 20 B: the largest base case edlib's rule allows
     a->P.lay = rp::make_aln_layout(a->P.lim);
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp_aln_kernel, kWarpsPerBlock * 32, 0);
+    if (const char* env = std::getenv("RP_ALN_BLOCKS_PER_SM")) {  // tuning knob (tools/bench_aln.py); default 4
+        int v = std::atoi(env);
+        if (v == 4 || v == 6 || v == 8) a->blocks_per_sm = v;
+    }
+    if (a->blocks_per_sm == 8)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp_aln_kernel<8>, kWarpsPerBlock * 32, 0);
+    else if (a->blocks_per_sm == 6)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp_aln_kernel<6>, kWarpsPerBlock * 32, 0);
+    else
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rp_aln_kernel<4>, kWarpsPerBlock * 32, 0);
     if (e != cudaSuccess || occ < 1) {
         rp_aln_destroy(a);
         return fail(RP_ERR_CUDA, std::string("kernel configuration: ") + cudaGetErrorString(e));
@@ -819,7 +830,12 @@ rp_status rp_aln_launch(rp_aln* a) {
     RP_CUDA(cudaSetDevice(a->device));
     if (a->P.n_pairs > 0) {
         RP_CUDA(cudaMemsetAsync(a->d_head.p, 0, 4, a->stream));
-        rp_aln_kernel<<<a->grid, kWarpsPerBlock * 32, 0, a->stream>>>(a->P);
+        if (a->blocks_per_sm == 8)
+            rp_aln_kernel<8><<<a->grid, kWarpsPerBlock * 32, 0, a->stream>>>(a->P);
+        else if (a->blocks_per_sm == 6)
+            rp_aln_kernel<6><<<a->grid, kWarpsPerBlock * 32, 0, a->stream>>>(a->P);
+        else
+            rp_aln_kernel<4><<<a->grid, kWarpsPerBlock * 32, 0, a->stream>>>(a->P);
         RP_CUDA(cudaGetLastError());
         a->launches += 1;
     }

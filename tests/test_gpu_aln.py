@@ -111,3 +111,13 @@ def test_aln_batch_reuse_and_state_errors():
     b.sync()
     assert b.size() == 0
     b.close()
+
+
+def test_aln_host_mirror_batch_aligner():
+    """racon_b200::BatchAligner (mirror of CUDABatchAligner) driven in small batches, as cudapolisher.cpp:100-213."""
+    from racon_b200 import api
+    rng = np.random.default_rng(16)
+    pairs = [_pair(rng, int(rng.integers(100, 3000)), float(rng.uniform(0.02, 0.2))) for _ in range(60)]
+    got = api.mirror_align(pairs, max_alignments=7)
+    for (q, t), c in zip(pairs, got):
+        assert c == _expected(q, t)[0]

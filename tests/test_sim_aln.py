@@ -43,3 +43,12 @@ def test_sim_aln_traceback_regime(n, err, count):
 def test_sim_aln_hirschberg_regime(n, err):
     rng = np.random.default_rng(n + 7)
     _check([_pair(rng, n, err, skew=rng.choice([0.0, 0.15]))])
+
+
+def test_sim_aln_band_growth_multi_round():
+    """Unrelated sequences: distance above the first threshold, so k doubles and the band spans several rounds of
+    32 words per column (carry hand-over between rounds)."""
+    rng = np.random.default_rng(99)
+    a = bytes(util.BASES[i] for i in rng.integers(4, size=3900))
+    b = bytes(util.BASES[i] for i in rng.integers(4, size=3600))
+    _check([(a, b)])
