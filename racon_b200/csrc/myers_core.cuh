@@ -154,103 +154,140 @@ struct AlnWarp {
      * mode 2: additionally stores the vertical-(+1) and horizontal-(+1) words of every column (base case). */
     RP_DEV int32_t band_pass(const uint64_t* peq, uint32_t n, const uint8_t* t, uint32_t m, bool rev_t, int32_t k,
                              uint32_t stop_col, int mode, int32_t* col) {
+        /* widest the band can get, in words: its k+1 rows straddle at most ceil(rows / 64) + 1 words */
+        const int32_t delta = static_cast<int32_t>(n) - static_cast<int32_t>(m);
+        const int32_t rows = (k + delta) / 2 + (k - delta) / 2 + 1;
+        int32_t span = (rows + 63) / 64 + 1;
+        const int32_t nw = static_cast<int32_t>((n + 63) / 64);
+        if (span > nw) span = nw;
+        if (span <= 32) return band_pass_t<1>(peq, n, t, m, rev_t, k, stop_col, mode, col);
+        if (span <= 32 * kAlnSlots) return band_pass_t<kAlnSlots>(peq, n, t, m, rev_t, k, stop_col, mode, col);
+        fail(kAlnBandLimit);
+        return kAlnInf;
+    }
+
+    RP_DEV static uint32_t rotr32(uint32_t x, int r) {
+        r &= 31;
+        return r ? (x >> r) | (x << (32 - r)) : x;
+    }
+
+    /* SLOTS = band words a lane may hold at once.  With a band of <= 32 words (SLOTS = 1) the word that enters at
+     * the bottom always lands in the lane whose previous word has just left at the top. */
+    template <int SLOTS>
+    RP_DEV int32_t band_pass_t(const uint64_t* peq, uint32_t n, const uint8_t* t, uint32_t m, bool rev_t, int32_t k,
+                               uint32_t stop_col, int mode, int32_t* col) {
         const int32_t delta = static_cast<int32_t>(n) - static_cast<int32_t>(m);
         const int32_t dlo = -((k - delta) / 2), dhi = (k + delta) / 2;  // diagonals i - j a cost-<=k path can touch
         const uint32_t nw = (n + 63) / 64;
-        uint64_t pv[kAlnSlots], mv[kAlnSlots];
+        if (dhi < 0 || dlo > 0) {  // k < |delta|: the band misses the corner cell (callers never ask for this)
+            fail(kAlnInternal);
+            return kAlnInf;
+        }
+        uint64_t pv[SLOTS], mv[SLOTS];
 #pragma unroll
-        for (int s = 0; s < kAlnSlots; ++s) {
+        for (int s = 0; s < SLOTS; ++s) {
             pv[s] = ~0ull;
             mv[s] = 0;
         }
         int32_t whi_prev = -1;   // last active word of the previous column
         int32_t sb = 0;          // H at the bottom row of word whi_prev (after the previous column)
         uint64_t store_pos = 0;
+        const int32_t n1 = static_cast<int32_t>(n) - 1;
+        const uint64_t rep = 0x0101010101010101ull;
+        uint32_t tc_next = rev_t ? t[m - 1] : t[0];
         for (uint32_t j = 0; j <= stop_col; ++j) {
             int32_t rlo = static_cast<int32_t>(j) + dlo, rhi = static_cast<int32_t>(j) + dhi;
             if (rlo < 0) rlo = 0;
-            if (rhi > static_cast<int32_t>(n) - 1) rhi = static_cast<int32_t>(n) - 1;
-            if (rhi < rlo) {  // band left the matrix (cannot happen for k >= |delta|)
-                fail(kAlnInternal);
-                return kAlnInf;
-            }
+            if (rhi > n1) rhi = n1;
             const int32_t wlo = rlo >> 6, whi = rhi >> 6;
-            if (whi - wlo + 1 > 32 * kAlnSlots) {
-                fail(kAlnBandLimit);
-                return kAlnInf;
-            }
-            /* words entering the band at the bottom start with vertical +1 everywhere */
-            if (whi_prev < 0) {
-                sb = static_cast<int32_t>(j) + 64 * (whi + 1);  // column j-1 boundary: H[r][j-1] = j + r + 1 for j = 0
-                if (j != 0) sb = kAlnInf;                       // never: the first column is j = 0
-            } else {
-                sb += 64 * (whi - whi_prev);
-            }
-            for (int32_t w = whi_prev + 1; w <= whi; ++w) {
-                if ((w & 31) == lane) {
-                    const int s = (w >> 5) % kAlnSlots;
+            /* the band slides one row per column, so at most one word enters at the bottom (vertical +1 everywhere);
+             * the words of column 0 are still in their initial state */
+            if (j == 0) {
+                sb = 64 * (whi + 1);  // boundary column: H[r][-1] = r + 1
+            } else if (whi != whi_prev) {
+                sb += 64;
+                if ((whi & 31) == lane) {
 #pragma unroll
-                    for (int q = 0; q < kAlnSlots; ++q)
-                        if (q == s) {
+                    for (int q = 0; q < SLOTS; ++q)
+                        if (SLOTS == 1 || q == ((whi >> 5) % SLOTS)) {
                             pv[q] = ~0ull;
                             mv[q] = 0;
                         }
                 }
             }
-            const uint8_t tc = rev_t ? t[m - 1 - j] : t[j];
-            const uint32_t sidx = sym_index(tc);
+            const uint32_t tc = tc_next;
+            if (j < stop_col) tc_next = rev_t ? t[m - 2 - j] : t[j + 1];
+            /* index of tc among the pair's symbols: first zero byte of syms ^ (tc repeated) */
+            const uint64_t x = syms ^ (rep * tc);
+            const uint64_t z = (x - rep) & ~x & (rep << 7);
+            const uint32_t zlo = static_cast<uint32_t>(z), zhi = static_cast<uint32_t>(z >> 32);
+            const uint32_t sidx = zlo ? static_cast<uint32_t>(ffs_(zlo) - 1) >> 3
+                                      : (zhi ? 4u + (static_cast<uint32_t>(ffs_(zhi) - 1) >> 3) : kAlnMaxSyms);
+            const uint64_t* peq_row = peq + static_cast<uint64_t>(sidx < nsyms ? sidx : 0) * nw;
+            const bool known = sidx < nsyms;
             int32_t carry = 1;  // horizontal delta entering the top word of the band (edlib.cpp:766: hout = 1)
             int32_t last_hout = 0;
             if (mode == 2 && lane == 0) store_first[j] = (static_cast<uint32_t>(wlo) << 16) | static_cast<uint32_t>(whi - wlo + 1);
             /* rounds of 32 consecutive words */
             for (int32_t w0 = wlo; w0 <= whi; w0 += 32) {
-                const int32_t w = w0 + ((lane - (w0 & 31)) & 31);  // the word of this round that lives in my lane
+                const int rot = w0 & 31;
+                const int pos = (lane - rot) & 31;       // my word's position inside the round
+                const int32_t w = w0 + pos;              // the word of this round that lives in my lane
                 const bool act = w <= whi;
-                const int s = (w >> 5) % kAlnSlots;
-                uint64_t Pv = 0, Mv = 0, Eq = 0;
+                uint64_t Pv = pv[0], Mv = mv[0];
+                if (SLOTS > 1) {
+                    const int s = (w >> 5) % SLOTS;
 #pragma unroll
-                for (int q = 0; q < kAlnSlots; ++q)
-                    if (q == s) {
-                        Pv = pv[q];
-                        Mv = mv[q];
-                    }
-                if (act) Eq = sidx < nsyms ? peq[sidx * nw + w] : 0ull;
-                const int first_lane = w0 & 31;
-                int32_t hin = (lane == first_lane) ? carry : 0;
-                uint64_t Ph = 0, Mh = 0, Xv = 0;
-                int32_t hout = 0;
-                for (int it = 0; it < 34; ++it) {
-                    const uint64_t hneg = hin < 0 ? 1ull : 0ull;
-                    Xv = Eq | Mv;
-                    const uint64_t Eq2 = Eq | hneg;
-                    const uint64_t Xh = (((Eq2 & Pv) + Pv) ^ Pv) | Eq2;
-                    Ph = Mv | ~(Xh | Pv);
-                    Mh = Pv & Xh;
-                    hout = static_cast<int32_t>(Ph >> 63) - static_cast<int32_t>(Mh >> 63);
-                    /* my carry-in is the hout of the previous word: the lane before me (cyclically) */
-                    int32_t nh = shfl(hout, (lane + 31) & 31);
-                    if (lane == first_lane) nh = carry;
-                    const bool changed = act && nh != hin;
-                    hin = nh;
-                    if (!ballot(changed)) break;
+                    for (int q = 1; q < SLOTS; ++q)
+                        if (q == s) {
+                            Pv = pv[q];
+                            Mv = mv[q];
+                        }
                 }
-                /* commit */
-                uint64_t Phs = (Ph << 1) | (hin > 0 ? 1ull : 0ull);
-                uint64_t Mhs = (Mh << 1) | (hin < 0 ? 1ull : 0ull);
+                const uint64_t Eq = (act && known) ? peq_row[w] : 0ull;
+                /* The carry into a word matters to its carry-out only through "hin < 0" (it ORs bit 0 into Eq), and
+                 * a negative carry-in can only lower the carry-out.  So every word evaluates both cases, and the
+                 * chain "negative out = generate | (propagate & negative in)" is resolved for all 32 words at once
+                 * with two ballots and one integer add. */
+                const uint64_t Eq1 = Eq | 1ull;
+                const uint64_t Xh0 = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                const uint64_t Xh1 = (((Eq1 & Pv) + Pv) ^ Pv) | Eq1;
+                const bool neg0 = act && ((Pv & Xh0) >> 63) != 0;
+                const bool neg1 = act && ((Pv & Xh1) >> 63) != 0;
+                const uint32_t gen = rotr32(ballot(neg0), rot);
+                const uint32_t prop = rotr32(ballot(neg1 && !neg0), rot);
+                const uint32_t cin = carry < 0 ? 1u : 0u;
+                const uint32_t negin = ((gen | prop) + gen + cin) ^ prop;  // bit p: negative carry into position p
+                const bool hneg = ((negin >> pos) & 1u) != 0;
+                const uint64_t Xh = hneg ? Xh1 : Xh0;
+                const uint64_t Xv = Eq | Mv;
+                const uint64_t Ph = Mv | ~(Xh | Pv);
+                const uint64_t Mh = Pv & Xh;
+                const int32_t hout = act ? static_cast<int32_t>(Ph >> 63) - static_cast<int32_t>(Mh >> 63) : 0;
+                int32_t hin = shfl(hout, (lane + 31) & 31);
+                if (pos == 0) hin = carry;
+                const uint64_t Phs = (Ph << 1) | (hin > 0 ? 1ull : 0ull);
+                const uint64_t Mhs = (Mh << 1) | (hneg ? 1ull : 0ull);
                 const uint64_t Pvn = Mhs | ~(Xv | Phs);
                 const uint64_t Mvn = Phs & Xv;
                 if (act) {
+                    if (SLOTS == 1) {
+                        pv[0] = Pvn;
+                        mv[0] = Mvn;
+                    } else {
+                        const int s = (w >> 5) % SLOTS;
 #pragma unroll
-                    for (int q = 0; q < kAlnSlots; ++q)
-                        if (q == s) {
-                            pv[q] = Pvn;
-                            mv[q] = Mvn;
-                        }
+                        for (int q = 0; q < SLOTS; ++q)
+                            if (q == s) {
+                                pv[q] = Pvn;
+                                mv[q] = Mvn;
+                            }
+                    }
                     if (mode == 2) {
-                        const uint64_t pos = store_pos + static_cast<uint64_t>(w - wlo);
-                        if (pos < P->lim.store_words) {
-                            store_pv[pos] = Pvn;
-                            store_ph[pos] = Ph;
+                        const uint64_t spos = store_pos + static_cast<uint64_t>(w - wlo);
+                        if (spos < P->lim.store_words) {
+                            store_pv[spos] = Pvn;
+                            store_ph[spos] = Ph;
                         } else {
                             status = kAlnStoreLimit;
                         }
@@ -288,10 +325,10 @@ struct AlnWarp {
             const int32_t wbot = w1;
             const int32_t w = wbot - ((wbot - lane) & 31);  // the word <= wbot congruent to my lane
             const bool act = w >= wlo && w >= wbot - 31;
-            const int s = (w >> 5) % kAlnSlots;
+            const int s = (w >> 5) % SLOTS;
             uint64_t Pv = 0, Mv = 0;
 #pragma unroll
-            for (int q = 0; q < kAlnSlots; ++q)
+            for (int q = 0; q < SLOTS; ++q)
                 if (q == s && act) {
                     Pv = pv[q];
                     Mv = mv[q];
