@@ -145,6 +145,14 @@ void rp_aln_destroy(rp_aln* a);
 /* CUDABatchAligner::addOverlap (cudaaligner.cpp:51-78): query = read span, target = contig span, in racon's
  * orientation (overlap.cpp:193-197).  RP_OK | RP_BATCH_FULL | RP_ERR_INVALID. */
 rp_status rp_aln_add(rp_aln* a, const char* q, uint32_t ql, const char* t, uint32_t tl);
+/* Breaking points on the device (Overlap::find_breaking_points_from_cigar, src/overlap.cpp:226-292): set the window
+ * length (Polisher::window_length_) on an empty batch, add overlaps with their coordinates — t_begin = Overlap::t_begin_,
+ * q_start = strand ? q_length - q_end : q_begin (overlap.cpp:241) — and fetch, after the run, the (t, q) points the
+ * reference would have stored in Overlap::breaking_points_ (uint32 pairs, two points per window with a match). */
+rp_status rp_aln_set_window_length(rp_aln* a, uint32_t window_length);
+rp_status rp_aln_add_overlap(rp_aln* a, const char* q, uint32_t ql, const char* t, uint32_t tl, uint32_t t_begin,
+                             uint32_t q_start);
+rp_status rp_aln_fetch_breaking_points(rp_aln* a, uint32_t i, const uint32_t** points, uint32_t* n_points);
 uint32_t rp_aln_size(const rp_aln* a);
 /* CUDABatchAligner::alignAll (async) / generate_cigar_strings (sync), cudaaligner.cpp:80-104 */
 rp_status rp_aln_run(rp_aln* a);

@@ -41,7 +41,10 @@ def ref_lib():
 def oracle_lib():
     global _oracle
     if _oracle is None:
-        if not os.path.exists(ORACLE_SO):
+        srcs = [os.path.join(HERE, f) for f in ("poa_oracle.cpp", "myers_oracle.cpp", "bp_oracle.cpp")]
+        stale = not os.path.exists(ORACLE_SO) or any(
+            os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(ORACLE_SO) for f in srcs)
+        if stale:
             import subprocess
             subprocess.check_call(["make", "-C", HERE, "oracle"], stdout=subprocess.DEVNULL)
         lib = C.CDLL(ORACLE_SO)
@@ -53,6 +56,10 @@ def oracle_lib():
             lib.oracle_myers_cigar.restype = C.c_int64
             lib.oracle_myers_cigar.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p,
                                                C.c_uint64, C.c_void_p]
+        if hasattr(lib, "oracle_breaking_points"):
+            lib.oracle_breaking_points.restype = C.c_int64
+            lib.oracle_breaking_points.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                   C.c_uint32, C.c_void_p, C.c_uint64]
         _oracle = lib
     return _oracle
 
@@ -120,3 +127,17 @@ def oracle_myers_cigar(q, t):
     if n < 0:
         raise RuntimeError("oracle myers failed (%d)" % n)
     return buf.raw[:n].decode(), ed.value
+
+
+def oracle_breaking_points(cigar, t_begin, t_end, q_start, window_length):
+    """(n, 2) uint32 array of (t, q) breaking points, two rows per window with a match (overlap.cpp:226-292)."""
+    if isinstance(cigar, str):
+        cigar = cigar.encode()
+    cap = 2 * ((t_end - t_begin) // max(1, window_length) + 3)
+    out = np.zeros((cap, 2), np.uint32)
+    n = oracle_lib().oracle_breaking_points(cigar, len(cigar), t_begin, t_end, q_start, window_length,
+                                            out.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError("oracle breaking points failed (%d)" % n)
+    return out[:n].copy()
+

@@ -17,17 +17,80 @@
 
 #define private public
 #define protected public
+#include "overlap.hpp"
 #include "polisher.hpp"
 #include "window.hpp"
 #undef private
 #undef protected
+#include <cstdio>
+#include <cstdlib>
+
+#include "bioparser/parser.hpp"
+#include "logger.hpp"
 #include "sequence.hpp"
+#include "spoa/spoa.hpp"
+#include "thread_pool/thread_pool.hpp"
 
 namespace {
 struct Handle {
     std::unique_ptr<racon::Polisher> polisher;
     std::vector<std::shared_ptr<racon::Window>> windows;  // copies keep the windows alive across polish()
     std::vector<std::unique_ptr<racon::Sequence>> polished;
+};
+
+/* Same Polisher, one hook: after the reference has aligned every overlap and found its breaking points
+ * (Polisher::find_overlap_breaking_points -> Overlap::find_breaking_points, src/overlap.cpp:172-292), write the
+ * sequences and the overlaps (coordinates + breaking points) to the file named by $REFPOL_OVERLAP_DUMP.  This is
+ * the fixture the CIGAR->breaking-points->windows row is pinned against. */
+struct DumpPolisher : public racon::Polisher {
+    using racon::Polisher::Polisher;
+    void find_overlap_breaking_points(std::vector<std::unique_ptr<racon::Overlap>>& overlaps) override {
+        racon::Polisher::find_overlap_breaking_points(overlaps);
+        const char* path = std::getenv("REFPOL_OVERLAP_DUMP");
+        if (!path) return;
+        FILE* f = std::fopen(path, "wb");
+        if (!f) return;
+        auto u32 = [&](uint32_t v) { std::fwrite(&v, 4, 1, f); };
+        auto u64 = [&](uint64_t v) { std::fwrite(&v, 8, 1, f); };
+        auto rc = [](const std::string& r) {
+            std::string d(r.rbegin(), r.rend());
+            for (auto& c : d) {
+                switch (c) {
+                    case 'A': c = 'T'; break;
+                    case 'C': c = 'G'; break;
+                    case 'G': c = 'C'; break;
+                    case 'T': c = 'A'; break;
+                    default: break;
+                }
+            }
+            return d;
+        };
+        u64(sequences_.size());
+        for (const auto& sq : sequences_) {
+            std::string data = !sq->data().empty() ? sq->data() : rc(sq->reverse_complement());
+            std::string qual = !sq->quality().empty()
+                                   ? sq->quality()
+                                   : std::string(sq->reverse_quality().rbegin(), sq->reverse_quality().rend());
+            u32(static_cast<uint32_t>(sq->name().size()));
+            std::fwrite(sq->name().data(), 1, sq->name().size(), f);
+            u64(data.size());
+            std::fwrite(data.data(), 1, data.size(), f);
+            u64(qual.size());
+            std::fwrite(qual.data(), 1, qual.size(), f);
+        }
+        u64(overlaps.size());
+        for (const auto& o : overlaps) {
+            u32(o->q_id_); u32(o->t_id_); u32(o->strand_);
+            u32(o->q_begin_); u32(o->q_end_); u32(o->q_length_);
+            u32(o->t_begin_); u32(o->t_end_); u32(o->t_length_);
+            u32(static_cast<uint32_t>(o->breaking_points_.size()));
+            for (const auto& bp : o->breaking_points_) {
+                u32(bp.first);
+                u32(bp.second);
+            }
+        }
+        std::fclose(f);
+    }
 };
 }  // namespace
 
@@ -41,6 +104,14 @@ void* ref_polisher_open(const char* reads, const char* overlaps, const char* tar
                                         fragment_correction ? racon::PolisherType::kF : racon::PolisherType::kC,
                                         window_length, quality_threshold, error_threshold, trim != 0, match, mismatch,
                                         gap, threads);
+    if (std::getenv("REFPOL_OVERLAP_DUMP")) {
+        /* re-seat the parsers the factory chose into the hooked subclass (same constructor arguments) */
+        racon::Polisher* p = h->polisher.get();
+        std::unique_ptr<racon::Polisher> hooked(new DumpPolisher(
+            std::move(p->sparser_), std::move(p->oparser_), std::move(p->tparser_), p->type_, window_length,
+            quality_threshold, error_threshold, trim != 0, match, mismatch, gap, threads));
+        h->polisher = std::move(hooked);
+    }
     h->polisher->initialize();
     h->windows = h->polisher->windows_;
     return h;

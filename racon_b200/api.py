@@ -89,6 +89,12 @@ def _bind_aln(lib, C, vp, u32):
     lib.rp_aln_destroy.argtypes = [vp]
     lib.rp_aln_add.restype = C.c_int32
     lib.rp_aln_add.argtypes = [vp, C.c_char_p, u32, C.c_char_p, u32]
+    lib.rp_aln_set_window_length.restype = C.c_int32
+    lib.rp_aln_set_window_length.argtypes = [vp, u32]
+    lib.rp_aln_add_overlap.restype = C.c_int32
+    lib.rp_aln_add_overlap.argtypes = [vp, C.c_char_p, u32, C.c_char_p, u32, u32, u32]
+    lib.rp_aln_fetch_breaking_points.restype = C.c_int32
+    lib.rp_aln_fetch_breaking_points.argtypes = [vp, u32, vp, vp]
     lib.rp_aln_size.restype = u32
     lib.rp_aln_size.argtypes = [vp]
     for name in ("rp_aln_run", "rp_aln_sync", "rp_aln_upload", "rp_aln_launch", "rp_aln_download", "rp_aln_reset"):
@@ -238,9 +244,23 @@ class AlnBatch:
         except Exception:
             pass
 
-    def add(self, query, target):
+    def set_window_length(self, window_length):
+        _check(self.lib, self.lib.rp_aln_set_window_length(self.h, window_length), "rp_aln_set_window_length")
+
+    def fetch_breaking_points(self, i):
+        """(n, 2) uint32 (t, q) points of overlap i, as Overlap::breaking_points_ (overlap.cpp:226-292)."""
+        p = C.c_void_p()
+        n = C.c_uint32()
+        _check(self.lib, self.lib.rp_aln_fetch_breaking_points(self.h, i, C.byref(p), C.byref(n)),
+               "rp_aln_fetch_breaking_points")
+        if n.value == 0:
+            return np.zeros((0, 2), np.uint32)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n.value * 2,))
+        return a.reshape(n.value, 2).copy()
+
+    def add(self, query, target, t_begin=0, q_start=0):
         """addOverlap: True if taken, False if the batch is full (cudaaligner.cpp:51-78)."""
-        st = self.lib.rp_aln_add(self.h, query, len(query), target, len(target))
+        st = self.lib.rp_aln_add_overlap(self.h, query, len(query), target, len(target), t_begin, q_start)
         if st == 1:
             return False
         _check(self.lib, st, "rp_aln_add")
@@ -334,6 +354,79 @@ def mirror_align(pairs, max_alignments=0, device=0):
         row = out[i * stride:(i + 1) * stride].tobytes()
         res.append(row[: row.index(b"\0")])
     return res
+
+
+class MirrorPolisher:
+    """Drives racon_b200::Polisher (host_mirror.hpp) through its test hooks: overlaps -> device alignment + breaking
+    points -> windows -> device consensus -> stitched sequences.  Same call shape as oracle/ref_polisher_harness.cpp."""
+
+    def __init__(self, bases, quals, seq_off, seq_has_qual, n_targets, overlaps, window_length=500,
+                 quality_threshold=10.0, trim=True, match=3, mismatch=-5, gap=-4, window_type_tgs=True,
+                 fragment_correction=False, device=0):
+        self.lib = load()
+        L = self.lib
+        vp = C.c_void_p
+        L.rp_mirror_polisher_open.restype = vp
+        L.rp_mirror_polisher_open.argtypes = [C.c_uint32, vp, vp, vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_uint32, vp,
+                                              C.c_uint32, C.c_double, C.c_int, C.c_int8, C.c_int8, C.c_int8, C.c_uint32]
+        L.rp_mirror_polisher_counts.restype = None
+        L.rp_mirror_polisher_counts.argtypes = [vp, vp]
+        L.rp_mirror_polisher_export.restype = None
+        L.rp_mirror_polisher_export.argtypes = [vp] * 11
+        L.rp_mirror_polisher_polish.restype = C.c_uint32
+        L.rp_mirror_polisher_polish.argtypes = [vp, C.c_int]
+        L.rp_mirror_polisher_window_consensus.restype = C.c_uint32
+        L.rp_mirror_polisher_window_consensus.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
+        L.rp_mirror_polisher_polished.restype = C.c_uint64
+        L.rp_mirror_polisher_polished.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint64]
+        L.rp_mirror_polisher_close.restype = None
+        L.rp_mirror_polisher_close.argtypes = [vp]
+        # keep the sequence bytes alive: the windows point into them
+        self._bases = np.ascontiguousarray(np.frombuffer(bases, np.uint8))
+        self._quals = np.ascontiguousarray(np.frombuffer(quals, np.uint8))
+        self._off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        self._hq = np.ascontiguousarray(seq_has_qual, dtype=np.uint8)
+        ov = np.ascontiguousarray(overlaps, dtype=np.uint32)
+        self.h = L.rp_mirror_polisher_open(len(self._off) - 1, _ptr(self._bases), _ptr(self._quals), _ptr(self._off),
+                                           _ptr(self._hq), n_targets, 1 if window_type_tgs else 0,
+                                           1 if fragment_correction else 0, len(ov), _ptr(ov), window_length,
+                                           quality_threshold, 1 if trim else 0, match, mismatch, gap, device)
+
+    def export(self):
+        c = (C.c_uint64 * 3)()
+        self.lib.rp_mirror_polisher_counts(self.h, c)
+        nw, ns, nb = int(c[0]), int(c[1]), int(c[2])
+        r = dict(bases=np.zeros(nb, np.uint8), quals=np.zeros(nb, np.uint8), seq_off=np.zeros(ns + 1, np.uint64),
+                 seq_has_qual=np.zeros(ns, np.uint8), seq_begin=np.zeros(ns, np.uint32), seq_end=np.zeros(ns, np.uint32),
+                 win_first=np.zeros(nw + 1, np.uint32), win_type=np.zeros(nw, np.uint8),
+                 win_target=np.zeros(nw, np.uint64), win_rank=np.zeros(nw, np.uint32))
+        self.lib.rp_mirror_polisher_export(self.h, *[_ptr(r[k]) for k in (
+            "bases", "quals", "seq_off", "seq_has_qual", "seq_begin", "seq_end", "win_first", "win_type", "win_target",
+            "win_rank")])
+        return r
+
+    def polish(self, drop_unpolished=False):
+        n = self.lib.rp_mirror_polisher_polish(self.h, 1 if drop_unpolished else 0)
+        c = (C.c_uint64 * 3)()
+        self.lib.rp_mirror_polisher_counts(self.h, c)
+        buf = C.create_string_buffer(1 << 20)
+        cons = []
+        for w in range(int(c[0])):
+            k = self.lib.rp_mirror_polisher_window_consensus(self.h, w, buf, len(buf))
+            cons.append(buf.raw[:k])
+        out = []
+        data = C.create_string_buffer(1 << 27)
+        tags = C.create_string_buffer(4096)
+        for i in range(n):
+            tid = C.c_uint64()
+            k = self.lib.rp_mirror_polisher_polished(self.h, i, C.byref(tid), tags, len(tags), data, len(data))
+            out.append((tid.value, tags.value.decode(), data.raw[:k]))
+        return cons, out
+
+    def close(self):
+        if self.h:
+            self.lib.rp_mirror_polisher_close(self.h)
+            self.h = None
 
 
 def consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=500, device=0, want_coverage=False,

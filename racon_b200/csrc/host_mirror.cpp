@@ -3,9 +3,11 @@
  */
 #include "host_mirror.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 
 #include "racon_b200.h"
 
@@ -194,7 +196,305 @@ void BatchAligner::reset() {
     rp_aln_reset(aln_);
 }
 
+/* ---- Polisher ---- */
+Polisher::Polisher(std::vector<SequenceView> sequences, uint64_t targets_size, WindowType window_type,
+                   bool fragment_correction, uint32_t window_length, double quality_threshold, bool trim, int8_t match,
+                   int8_t mismatch, int8_t gap, uint32_t device)
+    : sequences_(std::move(sequences)), targets_size_(targets_size), window_type_(window_type),
+      fragment_correction_(fragment_correction), window_length_(window_length), quality_threshold_(quality_threshold),
+      trim_(trim), match_(match), mismatch_(mismatch), gap_(gap), device_(device),
+      dummy_quality_(window_length, '!'),  // polisher.cpp:174
+      reverse_complement_(sequences_.size()), reverse_quality_(sequences_.size()) {
+    if (window_length == 0) {  // polisher.cpp:71-75
+        fprintf(stderr, "[racon_b200::Polisher] error: invalid window length!\n");
+        exit(1);
+    }
+}
+
+Polisher::~Polisher() {}
+
+const char* Polisher::reverse_complement(uint32_t id) {  // Sequence::create_reverse_complement, sequence.cpp:58-93
+    std::string& r = reverse_complement_[id];
+    if (r.empty() && sequences_[id].length) {
+        const SequenceView& s = sequences_[id];
+        r.resize(s.length);
+        for (uint32_t i = 0; i < s.length; ++i) {
+            char c = s.data[s.length - 1 - i];
+            switch (c) {
+                case 'A': c = 'T'; break;
+                case 'C': c = 'G'; break;
+                case 'G': c = 'C'; break;
+                case 'T': c = 'A'; break;
+                default: break;
+            }
+            r[i] = c;
+        }
+    }
+    return r.data();
+}
+
+const char* Polisher::reverse_quality(uint32_t id) {
+    std::string& r = reverse_quality_[id];
+    const SequenceView& s = sequences_[id];
+    if (r.empty() && s.quality && s.length) r.assign(std::reverse_iterator<const char*>(s.quality + s.length),
+                                                     std::reverse_iterator<const char*>(s.quality));
+    return s.quality ? r.data() : nullptr;
+}
+
+void Polisher::find_overlap_breaking_points(std::vector<Overlap>& overlaps) {
+    rp_aln* aln = nullptr;
+    uint32_t longest = 1;
+    for (const Overlap& o : overlaps) {
+        longest = std::max(longest, std::max(o.q_end - o.q_begin, o.t_end - o.t_begin));
+    }
+    rp_status s = rp_aln_create(&aln, static_cast<int>(device_), 0, longest);
+    if (s == RP_OK) s = rp_aln_set_window_length(aln, window_length_);
+    if (s != RP_OK) {
+        fprintf(stderr, "[racon_b200::Polisher::find_overlap_breaking_points] error: %s (%s)\n", rp_strerror(s),
+                rp_last_error());
+        exit(1);
+    }
+    size_t i = 0;
+    while (i < overlaps.size()) {
+        const size_t first = i;
+        for (; i < overlaps.size(); ++i) {
+            const Overlap& o = overlaps[i];
+            /* the spans racon hands to the aligner (overlap.cpp:193-197) */
+            const uint32_t q_start = o.strand ? o.q_length - o.q_end : o.q_begin;
+            const char* q = (o.strand ? reverse_complement(o.q_id) : sequences_[o.q_id].data) + q_start;
+            const char* t = sequences_[o.t_id].data + o.t_begin;
+            s = rp_aln_add_overlap(aln, q, o.q_end - o.q_begin, t, o.t_end - o.t_begin, o.t_begin, q_start);
+            if (s == RP_BATCH_FULL) break;
+            if (s != RP_OK) {
+                fprintf(stderr, "[racon_b200::Polisher::find_overlap_breaking_points] error: %s (%s)\n",
+                        rp_strerror(s), rp_last_error());
+                exit(1);
+            }
+        }
+        if (i == first) {
+            fprintf(stderr, "[racon_b200::Polisher::find_overlap_breaking_points] error: overlap does not fit an empty batch\n");
+            exit(1);
+        }
+        s = rp_aln_run(aln);
+        if (s == RP_OK) s = rp_aln_sync(aln);
+        if (s != RP_OK) {
+            fprintf(stderr, "[racon_b200::Polisher::find_overlap_breaking_points] error: %s (%s)\n", rp_strerror(s),
+                    rp_last_error());
+            exit(1);
+        }
+        for (size_t k = first; k < i; ++k) {
+            const uint32_t* pts = nullptr;
+            uint32_t n = 0, st = 0;
+            rp_aln_fetch_cigar(aln, static_cast<uint32_t>(k - first), nullptr, nullptr, nullptr, &st);
+            if (st != RP_ALN_OK) {
+                /* the reference re-aligns such overlaps with its CPU edlib (cudapolisher.cpp:213); this path has no CPU
+                 * aligner, so the overlap contributes no layers and the caller is told */
+                fprintf(stderr, "[racon_b200::Polisher] warning: overlap %zu exceeded device limit %u\n", k, st);
+                continue;
+            }
+            rp_aln_fetch_breaking_points(aln, static_cast<uint32_t>(k - first), &pts, &n);
+            overlaps[k].breaking_points_.clear();
+            for (uint32_t b = 0; b < n; ++b) overlaps[k].breaking_points_.emplace_back(pts[2 * b], pts[2 * b + 1]);
+        }
+        rp_aln_reset(aln);
+    }
+    rp_aln_destroy(aln);
+}
+
+void Polisher::initialize(std::vector<Overlap>& overlaps) {
+    find_overlap_breaking_points(overlaps);
+
+    /* one window per window_length_ bases of every target (polisher.cpp:383-401) */
+    std::vector<uint64_t> id_to_first_window_id(targets_size_ + 1, 0);
+    for (uint64_t i = 0; i < targets_size_; ++i) {
+        uint32_t k = 0;
+        const SequenceView& tgt = sequences_[i];
+        for (uint32_t j = 0; j < tgt.length; j += window_length_, ++k) {
+            const uint32_t length = std::min(j + window_length_, tgt.length) - j;
+            windows_.emplace_back(createWindow(i, k, window_type_, tgt.data + j, length,
+                                               tgt.quality ? tgt.quality + j : dummy_quality_.data(), length));
+        }
+        id_to_first_window_id[i + 1] = id_to_first_window_id[i] + k;
+    }
+
+    targets_coverages_.assign(targets_size_, 0);
+
+    /* one layer per pair of breaking points (polisher.cpp:405-458) */
+    for (uint64_t i = 0; i < overlaps.size(); ++i) {
+        const Overlap& o = overlaps[i];
+        ++targets_coverages_[o.t_id];
+        const SequenceView& sequence = sequences_[o.q_id];
+        const auto& breaking_points = o.breaking_points();
+        for (uint32_t j = 0; j + 1 < breaking_points.size(); j += 2) {
+            if (breaking_points[j + 1].second - breaking_points[j].second < 0.02 * window_length_) continue;
+
+            const char* quality = o.strand ? reverse_quality(o.q_id) : sequence.quality;
+            if (quality != nullptr) {
+                double average_quality = 0;
+                for (uint32_t k = breaking_points[j].second; k < breaking_points[j + 1].second; ++k) {
+                    average_quality += static_cast<uint32_t>(quality[k]) - 33;
+                }
+                average_quality /= breaking_points[j + 1].second - breaking_points[j].second;
+                if (average_quality < quality_threshold_) continue;
+            }
+
+            const uint64_t window_id = id_to_first_window_id[o.t_id] + breaking_points[j].first / window_length_;
+            const uint32_t window_start = (breaking_points[j].first / window_length_) * window_length_;
+            const char* data = (o.strand ? reverse_complement(o.q_id) : sequence.data) + breaking_points[j].second;
+            const uint32_t data_length = breaking_points[j + 1].second - breaking_points[j].second;
+            const char* layer_quality = quality == nullptr ? nullptr : quality + breaking_points[j].second;
+            const uint32_t quality_length = quality == nullptr ? 0 : data_length;
+
+            windows_[window_id]->add_layer(data, data_length, layer_quality, quality_length,
+                                           breaking_points[j].first - window_start,
+                                           breaking_points[j + 1].first - window_start - 1);
+        }
+    }
+}
+
+void Polisher::polish(std::vector<PolishedSequence>& dst, bool drop_unpolished_sequences) {
+    auto batch = createBatch(0, device_, 0, gap_, mismatch_, match_, false, window_length_, trim_);
+    std::vector<bool> polished(windows_.size(), false);
+    size_t i = 0;
+    while (i < windows_.size()) {  // cudapolisher.cpp:254-276: fill, run, collect, reset
+        const size_t first = i;
+        while (i < windows_.size() && batch->addWindow(windows_[i])) ++i;
+        if (i == first) {
+            fprintf(stderr, "[racon_b200::Polisher::polish] error: window does not fit an empty batch\n");
+            exit(1);
+        }
+        const std::vector<bool>& flags = batch->generateConsensus();
+        for (size_t k = 0; k < flags.size(); ++k) polished[first + k] = flags[k];
+        batch->reset();
+    }
+
+    /* stitch (polisher.cpp:504-537) */
+    std::string polished_data;
+    uint32_t num_polished_windows = 0;
+    for (uint64_t w = 0; w < windows_.size(); ++w) {
+        num_polished_windows += polished[w] ? 1 : 0;
+        polished_data += windows_[w]->consensus();
+        if (w == windows_.size() - 1 || windows_[w + 1]->rank() == 0) {
+            const double polished_ratio = num_polished_windows / static_cast<double>(windows_[w]->rank() + 1);
+            if (!drop_unpolished_sequences || polished_ratio > 0) {
+                std::string tags = fragment_correction_ ? "r" : "";
+                tags += " LN:i:" + std::to_string(polished_data.size());
+                tags += " RC:i:" + std::to_string(targets_coverages_[windows_[w]->id()]);
+                tags += " XC:f:" + std::to_string(polished_ratio);
+                dst.push_back(PolishedSequence{windows_[w]->id(), tags, polished_data});
+            }
+            num_polished_windows = 0;
+            polished_data.clear();
+        }
+    }
+}
+
 }  // namespace racon_b200
+
+/* Test hooks with the shape of oracle/ref_polisher_harness.cpp (open -> counts -> export -> polish -> polished), so
+ * that tests/test_pipeline.py compares this pipeline and the unmodified reference Polisher field by field. */
+namespace {
+struct PolHandle {
+    std::unique_ptr<racon_b200::Polisher> polisher;
+    std::vector<racon_b200::PolishedSequence> polished;
+};
+}  // namespace
+
+extern "C" void* rp_mirror_polisher_open(uint32_t n_seq, const char* bases, const char* quals, const uint64_t* seq_off,
+                                         const uint8_t* seq_has_qual, uint32_t n_targets, int window_type_tgs,
+                                         int fragment_correction, uint32_t n_overlaps, const uint32_t* overlaps,
+                                         uint32_t window_length, double quality_threshold, int trim, int8_t match,
+                                         int8_t mismatch, int8_t gap, uint32_t device) {
+    using namespace racon_b200;
+    std::vector<SequenceView> seqs(n_seq);
+    for (uint32_t i = 0; i < n_seq; ++i) {
+        seqs[i].data = bases + seq_off[i];
+        seqs[i].quality = seq_has_qual[i] ? quals + seq_off[i] : nullptr;
+        seqs[i].length = static_cast<uint32_t>(seq_off[i + 1] - seq_off[i]);
+    }
+    std::vector<Overlap> ovl(n_overlaps);
+    for (uint32_t i = 0; i < n_overlaps; ++i) {
+        const uint32_t* o = overlaps + 9ull * i;
+        ovl[i] = Overlap{o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], {}};
+    }
+    PolHandle* h = new PolHandle();
+    h->polisher.reset(new Polisher(std::move(seqs), n_targets, window_type_tgs ? WindowType::kTGS : WindowType::kNGS,
+                                   fragment_correction != 0, window_length, quality_threshold, trim != 0, match,
+                                   mismatch, gap, device));
+    h->polisher->initialize(ovl);
+    return h;
+}
+
+extern "C" void rp_mirror_polisher_counts(void* hv, uint64_t* counts) {
+    PolHandle* h = static_cast<PolHandle*>(hv);
+    counts[0] = h->polisher->windows().size();
+    counts[1] = counts[2] = 0;
+    for (const auto& w : h->polisher->windows()) {
+        counts[1] += w->sequences().size();
+        for (const auto& s : w->sequences()) counts[2] += s.second;
+    }
+}
+
+extern "C" void rp_mirror_polisher_export(void* hv, char* bases, char* quals, uint64_t* seq_off, uint8_t* seq_has_qual,
+                                          uint32_t* seq_begin, uint32_t* seq_end, uint32_t* win_first, uint8_t* win_type,
+                                          uint64_t* win_target, uint32_t* win_rank) {
+    PolHandle* h = static_cast<PolHandle*>(hv);
+    uint64_t nb = 0, ns = 0;
+    seq_off[0] = 0;
+    const auto& windows = h->polisher->windows();
+    for (size_t w = 0; w < windows.size(); ++w) {
+        const auto& win = windows[w];
+        win_first[w] = static_cast<uint32_t>(ns);
+        win_type[w] = win->type() == racon_b200::WindowType::kTGS ? 1 : 0;
+        win_target[w] = win->id();
+        win_rank[w] = win->rank();
+        for (size_t s = 0; s < win->sequences().size(); ++s) {
+            const uint32_t len = win->sequences()[s].second;
+            std::memcpy(bases + nb, win->sequences()[s].first, len);
+            const char* q = win->qualities()[s].first;
+            if (q) {
+                std::memcpy(quals + nb, q, len);
+                seq_has_qual[ns] = 1;
+            } else {
+                std::memset(quals + nb, '!', len);
+                seq_has_qual[ns] = 0;
+            }
+            seq_begin[ns] = win->positions()[s].first;
+            seq_end[ns] = win->positions()[s].second;
+            nb += len;
+            seq_off[++ns] = nb;
+        }
+    }
+    win_first[windows.size()] = static_cast<uint32_t>(ns);
+}
+
+extern "C" uint32_t rp_mirror_polisher_polish(void* hv, int drop_unpolished) {
+    PolHandle* h = static_cast<PolHandle*>(hv);
+    h->polisher->polish(h->polished, drop_unpolished != 0);
+    return static_cast<uint32_t>(h->polished.size());
+}
+
+extern "C" uint32_t rp_mirror_polisher_window_consensus(void* hv, uint32_t w, char* out, uint32_t cap) {
+    PolHandle* h = static_cast<PolHandle*>(hv);
+    const std::string& c = h->polisher->windows()[w]->consensus();
+    if (c.size() > cap) return 0xffffffffu;
+    std::memcpy(out, c.data(), c.size());
+    return static_cast<uint32_t>(c.size());
+}
+
+extern "C" uint64_t rp_mirror_polisher_polished(void* hv, uint32_t i, uint64_t* target_id, char* tags, uint32_t tags_cap,
+                                                char* data, uint64_t data_cap) {
+    PolHandle* h = static_cast<PolHandle*>(hv);
+    const auto& s = h->polished[i];
+    *target_id = s.id;
+    std::strncpy(tags, s.tags.c_str(), tags_cap - 1);
+    tags[tags_cap - 1] = 0;
+    if (s.data.size() > data_cap) return ~0ull;
+    std::memcpy(data, s.data.data(), s.data.size());
+    return s.data.size();
+}
+
+extern "C" void rp_mirror_polisher_close(void* hv) { delete static_cast<PolHandle*>(hv); }
 
 /* Test hook: CUDAPolisher::find_overlap_breaking_points' batch loop (cudapolisher.cpp:100-213) over flat pairs:
  * fill a batch until addOverlap refuses, alignAll, generate_cigar_strings, reset, continue.  out: NUL-terminated

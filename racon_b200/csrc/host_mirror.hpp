@@ -31,6 +31,10 @@ public:
     uint64_t id() const { return id_; }
     uint32_t rank() const { return rank_; }
     const std::string& consensus() const { return consensus_; }
+    WindowType type() const { return type_; }
+    const std::vector<std::pair<const char*, uint32_t>>& sequences() const { return sequences_; }
+    const std::vector<std::pair<const char*, uint32_t>>& qualities() const { return qualities_; }
+    const std::vector<std::pair<uint32_t, uint32_t>>& positions() const { return positions_; }
 
     /* same checks, same silent skips and the same fatal errors as the reference (window.cpp:42-63) */
     void add_layer(const char* sequence, uint32_t sequence_length, const char* quality, uint32_t quality_length,
@@ -122,6 +126,66 @@ private:
     uint32_t max_alignments_ = 0;
     rp_aln* aln_ = nullptr;
     std::vector<std::string*> cigars_;
+};
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Mirror of the device-facing half of racon::CUDAPolisher: overlaps -> (device) alignment + breaking points ->
+ * windows -> (device) consensus -> stitched sequences.  Parsing, overlap filtering and FASTA output stay with the
+ * caller (SURVEY §8 out of scope); everything that touches sequence bytes in bulk runs on the GPU.
+ *   find_overlap_breaking_points : src/cuda/cudapolisher.cpp:72-213  (batched aligner loop)
+ *                                  + src/overlap.cpp:226-292          (breaking points, on the device here)
+ *   initialize (window building) : src/polisher.cpp:383-461
+ *   polish                       : src/cuda/cudapolisher.cpp:215-395 (batch loop), src/polisher.cpp:504-537 (stitch)
+ * ------------------------------------------------------------------------------------------------------------------ */
+struct SequenceView {        // racon::Sequence as the polisher needs it; the bytes stay owned by the caller
+    const char* data;
+    const char* quality;     // nullptr when the sequence has no quality string
+    uint32_t length;
+};
+
+struct Overlap {             // racon::Overlap after transmute() (src/overlap.hpp:82-98)
+    uint32_t q_id, t_id, strand, q_begin, q_end, q_length, t_begin, t_end, t_length;
+    std::vector<std::pair<uint32_t, uint32_t>> breaking_points_;
+    const std::vector<std::pair<uint32_t, uint32_t>>& breaking_points() const { return breaking_points_; }
+};
+
+struct PolishedSequence {
+    uint64_t id;             // target index
+    std::string tags;        // " LN:i:.. RC:i:.. XC:f:.." exactly as polisher.cpp:521-524 appends them to the name
+    std::string data;
+};
+
+class Polisher {
+public:
+    /* sequences: the targets first (targets_size of them), then the reads — the order racon::Polisher::sequences_ has */
+    Polisher(std::vector<SequenceView> sequences, uint64_t targets_size, WindowType window_type, bool fragment_correction,
+             uint32_t window_length, double quality_threshold, bool trim, int8_t match, int8_t mismatch, int8_t gap,
+             uint32_t device);
+    ~Polisher();
+    void find_overlap_breaking_points(std::vector<Overlap>& overlaps);
+    void initialize(std::vector<Overlap>& overlaps);
+    void polish(std::vector<PolishedSequence>& dst, bool drop_unpolished_sequences);
+    const std::vector<std::shared_ptr<Window>>& windows() const { return windows_; }
+
+private:
+    Polisher(const Polisher&) = delete;
+    const Polisher& operator=(const Polisher&) = delete;
+    const char* reverse_complement(uint32_t id);
+    const char* reverse_quality(uint32_t id);
+
+    std::vector<SequenceView> sequences_;
+    uint64_t targets_size_;
+    WindowType window_type_;
+    bool fragment_correction_;
+    uint32_t window_length_;
+    double quality_threshold_;
+    bool trim_;
+    int8_t match_, mismatch_, gap_;
+    uint32_t device_;
+    std::string dummy_quality_;
+    std::vector<std::string> reverse_complement_, reverse_quality_;
+    std::vector<uint32_t> targets_coverages_;
+    std::vector<std::shared_ptr<Window>> windows_;
 };
 
 }  // namespace racon_b200

@@ -83,6 +83,15 @@ struct AlnParams {
     uint32_t* n_runs;
     int32_t* dist;
     uint32_t* status;
+    /* breaking points (Overlap::find_breaking_points_from_cigar, src/overlap.cpp:226-292), when window_length != 0:
+     * pair p writes n_bp[p] (t, q) points (two per window that saw a match) at bp + 2 * bp_off[p] */
+    uint32_t window_length;
+    const uint32_t* t_begin;    // target coordinate of the first target base of the pair
+    const uint32_t* q_start;    // query coordinate (in alignment orientation) of the first query base
+    uint32_t* bp;
+    const uint32_t* bp_off;     // in points
+    const uint32_t* bp_cap;     // in points
+    uint32_t* n_bp;
     uint8_t* scratch;
     AlnLimits lim;
     AlnLayout lay;
@@ -449,6 +458,76 @@ struct AlnWarp {
         syncwarp();
     }
 
+    /* Walks the pair's run-length encoded operations once (one lane: a few thousand runs) and emits, per target
+     * window that saw at least one match, the first matching (t, q) and the position one past the last match
+     * (src/overlap.cpp:226-292).  Window ends are i-1 for every multiple i of window_length with
+     * t_begin < i < t_end, then t_end-1 (:229-235).  Returns the number of points, 0xffffffff on overflow. */
+    RP_DEV uint32_t breaking_points(uint32_t p, uint32_t m, uint32_t n_runs) {
+        const uint32_t w = P->window_length;
+        const int64_t t_begin = P->t_begin[p], t_end = t_begin + m;
+        const uint32_t* runs = P->runs + P->run_off[p];
+        uint32_t* out = P->bp + 2ull * P->bp_off[p];
+        const uint32_t cap = P->bp_cap[p];
+        int64_t t = t_begin - 1, q = static_cast<int64_t>(P->q_start[p]) - 1;
+        const int64_t i0 = (t_begin / w + 1) * static_cast<int64_t>(w);
+        const int64_t none = static_cast<int64_t>(1) << 40;
+        int64_t wend = i0 < t_end ? i0 - 1 : t_end - 1;
+        bool found = false;
+        uint32_t ft = 0, fq = 0, lt = 0, lq = 0, nb = 0;
+        bool overflow = false;
+        auto boundary = [&]() {
+            if (found) {
+                if (nb + 2 <= cap) {
+                    out[2 * nb] = ft;
+                    out[2 * nb + 1] = fq;
+                    out[2 * nb + 2] = lt;
+                    out[2 * nb + 3] = lq;
+                } else {
+                    overflow = true;
+                }
+                nb += 2;
+            }
+            found = false;
+            if (wend == t_end - 1)
+                wend = none;
+            else
+                wend = (wend + 1 + w < t_end) ? wend + w : t_end - 1;
+        };
+        for (uint32_t r = 0; r < n_runs; ++r) {
+            const uint32_t run = runs[r];
+            int64_t c = run >> 8;
+            const uint32_t op = run & 0xffu;
+            if (op == 'M') {
+                while (c > 0) {
+                    if (!found) {
+                        found = true;
+                        ft = static_cast<uint32_t>(t + 1);
+                        fq = static_cast<uint32_t>(q + 1);
+                    }
+                    const int64_t room = wend - t;
+                    const int64_t step = c < room ? c : room;
+                    t += step;
+                    q += step;
+                    c -= step;
+                    lt = static_cast<uint32_t>(t + 1);
+                    lq = static_cast<uint32_t>(q + 1);
+                    if (t == wend) boundary();
+                }
+            } else if (op == 'I') {
+                q += c;
+            } else {
+                while (c > 0) {
+                    const int64_t room = wend - t;
+                    const int64_t step = c < room ? c : room;
+                    t += step;
+                    c -= step;
+                    if (t == wend) boundary();
+                }
+            }
+        }
+        return overflow ? 0xffffffffu : nb;
+    }
+
     /* whole pair: distance, Hirschberg recursion (explicit stack), run-length encoding */
     RP_DEV void align_pair(uint32_t p) {
         const uint8_t* q = P->bases + P->q_off[p];
@@ -624,6 +703,17 @@ struct AlnWarp {
             }
             n_out = base;
             if (n_out > cap) fail(kAlnRunLimit);
+        }
+        syncwarp();
+        if (P->window_length != 0) {
+            uint32_t nb = 0;
+            if (status == kAlnOk && lane == 0) nb = breaking_points(p, m, n_out);
+            nb = shfl(nb, 0);
+            if (nb == 0xffffffffu) {
+                fail(kAlnInternal);
+                nb = 0;
+            }
+            if (lane == 0) P->n_bp[p] = nb;
         }
         if (lane == 0) {
             P->status[p] = status;

@@ -120,12 +120,14 @@ struct rp_aln {
     bool own_stream = true;
     rp::AlnParams P;
     rp::GrowBuf<uint8_t> bases;
-    rp::GrowBuf<uint32_t> q_off, q_len, t_off, t_len, run_off, run_cap, queue;
+    rp::GrowBuf<uint32_t> q_off, q_len, t_off, t_len, run_off, run_cap, queue, t_begin, q_start, bp_off, bp_cap;
+    uint32_t window_length = 0;
+    uint64_t bp_total = 0;
     std::vector<uint32_t> pre_status;      // per pair: soft status decided on the host (too long) or 0
     uint64_t run_total = 0;
     DevBuf d_bases, d_q_off, d_q_len, d_t_off, d_t_len, d_run_off, d_run_cap, d_queue, d_runs, d_n_runs, d_dist,
-        d_status, d_head, d_scratch;
-    rp::GrowBuf<uint32_t> h_runs, h_n_runs, h_status;
+        d_status, d_head, d_scratch, d_t_begin, d_q_start, d_bp_off, d_bp_cap, d_bp, d_n_bp;
+    rp::GrowBuf<uint32_t> h_runs, h_n_runs, h_status, h_bp, h_n_bp;
     rp::GrowBuf<int32_t> h_dist;
     std::vector<std::string> cigars;
     std::vector<uint8_t> cigar_built;
@@ -138,8 +140,9 @@ struct rp_aln {
     uint64_t launches = 0, last_h2d = 0, last_d2h = 0;
     rp_aln()
         : bases(&kPinned), q_off(&kPinned), q_len(&kPinned), t_off(&kPinned), t_len(&kPinned), run_off(&kPinned),
-          run_cap(&kPinned), queue(&kPinned), h_runs(&kPinned), h_n_runs(&kPinned), h_status(&kPinned),
-          h_dist(&kPinned) {
+          run_cap(&kPinned), queue(&kPinned), t_begin(&kPinned), q_start(&kPinned), bp_off(&kPinned),
+          bp_cap(&kPinned), h_runs(&kPinned), h_n_runs(&kPinned), h_status(&kPinned), h_bp(&kPinned),
+          h_n_bp(&kPinned), h_dist(&kPinned) {
         std::memset(&P, 0, sizeof(P));
     }
 };
@@ -724,7 +727,8 @@ void rp_aln_destroy(rp_aln* a) {
     cudaSetDevice(a->device);
     if (a->stream) cudaStreamSynchronize(a->stream);
     DevBuf* bufs[] = {&a->d_bases, &a->d_q_off, &a->d_q_len, &a->d_t_off, &a->d_t_len, &a->d_run_off, &a->d_run_cap,
-                      &a->d_queue, &a->d_runs, &a->d_n_runs, &a->d_dist, &a->d_status, &a->d_head, &a->d_scratch};
+                      &a->d_queue, &a->d_runs, &a->d_n_runs, &a->d_dist, &a->d_status, &a->d_head, &a->d_scratch,
+                      &a->d_t_begin, &a->d_q_start, &a->d_bp_off, &a->d_bp_cap, &a->d_bp, &a->d_n_bp};
     for (DevBuf* b : bufs) b->release();
     if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
     delete a;
@@ -741,8 +745,22 @@ rp_status rp_aln_set_stream(rp_aln* a, void* cuda_stream) {
     return RP_OK;
 }
 
+rp_status rp_aln_set_window_length(rp_aln* a, uint32_t window_length) {
+    if (!a) return fail(RP_ERR_INVALID, "null object");
+    if (!a->pre_status.empty()) return fail(RP_ERR_STATE, "window length must be set on an empty batch");
+    a->window_length = window_length;
+    return RP_OK;
+}
+
 rp_status rp_aln_add(rp_aln* a, const char* q, uint32_t ql, const char* t, uint32_t tl) {
+    return rp_aln_add_overlap(a, q, ql, t, tl, 0, 0);
+}
+
+rp_status rp_aln_add_overlap(rp_aln* a, const char* q, uint32_t ql, const char* t, uint32_t tl, uint32_t t_begin,
+                             uint32_t q_start) {
     if (!a || (!q && ql) || (!t && tl)) return fail(RP_ERR_INVALID, "null argument");
+    if (static_cast<uint64_t>(t_begin) + tl > 0xffffffffull || static_cast<uint64_t>(q_start) + ql > 0xffffffffull)
+        return fail(RP_ERR_INVALID, "coordinates exceed 32 bits");
     if (a->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
     const bool too_long = ql > a->max_len || tl > a->max_len;
     const uint64_t add = too_long ? 0 : static_cast<uint64_t>(ql) + tl;
@@ -760,6 +778,15 @@ rp_status rp_aln_add(rp_aln* a, const char* q, uint32_t ql, const char* t, uint3
         !a->run_cap.push(cap))
         return fail(RP_ERR_NOMEM, "pinned staging allocation failed");
     a->run_total += cap;
+    uint32_t bcap = 0;
+    if (a->window_length && !too_long && tl > 0) {
+        const uint64_t w = a->window_length;
+        bcap = static_cast<uint32_t>(2 * ((static_cast<uint64_t>(t_begin) + tl - 1) / w - t_begin / w + 1));
+    }
+    if (!a->t_begin.push(t_begin) || !a->q_start.push(q_start) ||
+        !a->bp_off.push(static_cast<uint32_t>(a->bp_total)) || !a->bp_cap.push(bcap))
+        return fail(RP_ERR_NOMEM, "pinned staging allocation failed");
+    a->bp_total += bcap;
     a->pre_status.push_back(too_long ? RP_ALN_TOO_LONG : RP_ALN_OK);
     return RP_OK;
 }
@@ -795,6 +822,16 @@ rp_status rp_aln_upload(rp_aln* a) {
     RP_CUDA(up(a->d_run_off, a->run_off.data, a->run_off.bytes()));
     RP_CUDA(up(a->d_run_cap, a->run_cap.data, a->run_cap.bytes()));
     RP_CUDA(up(a->d_queue, a->queue.data, a->queue.bytes()));
+    if (a->window_length) {
+        RP_CUDA(up(a->d_t_begin, a->t_begin.data, a->t_begin.bytes()));
+        RP_CUDA(up(a->d_q_start, a->q_start.data, a->q_start.bytes()));
+        RP_CUDA(up(a->d_bp_off, a->bp_off.data, a->bp_off.bytes()));
+        RP_CUDA(up(a->d_bp_cap, a->bp_cap.data, a->bp_cap.bytes()));
+        RP_CUDA(a->d_bp.reserve((a->bp_total + 4) * 8));
+        RP_CUDA(a->d_n_bp.reserve((n + 1) * 4));
+        if (!a->h_bp.reserve(2 * a->bp_total + 8) || !a->h_n_bp.reserve(n + 1))
+            return fail(RP_ERR_NOMEM, "pinned result allocation failed");
+    }
     RP_CUDA(a->d_runs.reserve((a->run_total + 16) * 4));
     RP_CUDA(a->d_n_runs.reserve((n + 1) * 4));
     RP_CUDA(a->d_dist.reserve((n + 1) * 4));
@@ -818,6 +855,13 @@ rp_status rp_aln_upload(rp_aln* a) {
     P.dist = static_cast<int32_t*>(a->d_dist.p);
     P.status = static_cast<uint32_t*>(a->d_status.p);
     P.scratch = static_cast<uint8_t*>(a->d_scratch.p);
+    P.window_length = a->window_length;
+    P.t_begin = static_cast<const uint32_t*>(a->d_t_begin.p);
+    P.q_start = static_cast<const uint32_t*>(a->d_q_start.p);
+    P.bp = static_cast<uint32_t*>(a->d_bp.p);
+    P.bp_off = static_cast<const uint32_t*>(a->d_bp_off.p);
+    P.bp_cap = static_cast<const uint32_t*>(a->d_bp_cap.p);
+    P.n_bp = static_cast<uint32_t*>(a->d_n_bp.p);
     a->last_h2d = h2d;
     a->uploaded = true;
     a->launched = a->downloaded = a->synced = false;
@@ -856,6 +900,12 @@ rp_status rp_aln_download(rp_aln* a) {
         RP_CUDA(cudaMemcpyAsync(a->h_status.data, a->d_status.p, n * 4, cudaMemcpyDeviceToHost, a->stream));
         RP_CUDA(cudaMemcpyAsync(a->h_runs.data, a->d_runs.p, a->run_total * 4, cudaMemcpyDeviceToHost, a->stream));
         d2h = a->run_total * 4 + static_cast<uint64_t>(n) * 12;
+        if (a->window_length) {
+            RP_CUDA(cudaMemcpyAsync(a->h_n_bp.data, a->d_n_bp.p, n * 4, cudaMemcpyDeviceToHost, a->stream));
+            if (a->bp_total)
+                RP_CUDA(cudaMemcpyAsync(a->h_bp.data, a->d_bp.p, a->bp_total * 8, cudaMemcpyDeviceToHost, a->stream));
+            d2h += a->bp_total * 8 + static_cast<uint64_t>(n) * 4;
+        }
     }
     a->last_d2h = d2h;
     a->cigars.assign(n, std::string());
@@ -911,14 +961,31 @@ rp_status rp_aln_fetch_cigar(rp_aln* a, uint32_t i, const char** cigar, uint32_t
     return RP_OK;
 }
 
+rp_status rp_aln_fetch_breaking_points(rp_aln* a, uint32_t i, const uint32_t** points, uint32_t* n_points) {
+    if (!a || !points || !n_points) return fail(RP_ERR_INVALID, "null argument");
+    if (!a->downloaded) return fail(RP_ERR_STATE, "fetch before run/download");
+    if (!a->window_length) return fail(RP_ERR_STATE, "no window length set: breaking points were not computed");
+    if (!a->synced) {
+        rp_status s = rp_aln_sync(a);
+        if (s != RP_OK) return s;
+    }
+    if (i >= rp_aln_size(a)) return fail(RP_ERR_INVALID, "overlap index out of range");
+    const uint32_t st = a->pre_status[i] ? a->pre_status[i] : a->h_status.data[i];
+    *points = a->h_bp.data + 2ull * a->bp_off.data[i];
+    *n_points = st == RP_ALN_OK ? a->h_n_bp.data[i] : 0;
+    return RP_OK;
+}
+
 rp_status rp_aln_reset(rp_aln* a) {
     if (!a) return fail(RP_ERR_INVALID, "null object");
     cudaSetDevice(a->device);
     if (a->stream) RP_CUDA(cudaStreamSynchronize(a->stream));
     a->bases.clear(); a->q_off.clear(); a->q_len.clear(); a->t_off.clear(); a->t_len.clear();
     a->run_off.clear(); a->run_cap.clear(); a->queue.clear();
+    a->t_begin.clear(); a->q_start.clear(); a->bp_off.clear(); a->bp_cap.clear();
     a->pre_status.clear();
     a->run_total = 0;
+    a->bp_total = 0;
     a->cigars.clear();
     a->cigar_built.clear();
     a->uploaded = a->launched = a->downloaded = a->synced = false;

@@ -87,6 +87,49 @@ int rp_sim_aln(uint32_t n_pairs, const uint8_t* bases, const uint32_t* q_off, co
     return 0;
 }
 
+/* Same, plus breaking points: bp = n_pairs x bp_stride (t, q) points, n_bp = points per pair. */
+int rp_sim_aln_bp(uint32_t n_pairs, const uint8_t* bases, const uint32_t* q_off, const uint32_t* q_len,
+                  const uint32_t* t_off, const uint32_t* t_len, uint32_t max_len, uint32_t store_words, uint32_t* runs,
+                  uint32_t run_stride, uint32_t* n_runs, int32_t* dist, uint32_t* status, uint32_t window_length,
+                  const uint32_t* t_begin, const uint32_t* q_start, uint32_t* bp, uint32_t bp_stride, uint32_t* n_bp) {
+    rp::AlnParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.n_pairs = n_pairs;
+    P.bases = bases;
+    P.q_off = q_off;
+    P.q_len = q_len;
+    P.t_off = t_off;
+    P.t_len = t_len;
+    std::vector<uint32_t> roff(n_pairs), rcap(n_pairs, run_stride), boff(n_pairs), bcap(n_pairs, bp_stride);
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        roff[p] = p * run_stride;
+        boff[p] = p * bp_stride;
+    }
+    P.runs = runs;
+    P.run_off = roff.data();
+    P.run_cap = rcap.data();
+    P.n_runs = n_runs;
+    P.dist = dist;
+    P.status = status;
+    P.window_length = window_length;
+    P.t_begin = t_begin;
+    P.q_start = q_start;
+    P.bp = bp;
+    P.bp_off = boff.data();
+    P.bp_cap = bcap.data();
+    P.n_bp = n_bp;
+    P.lim.max_len = max_len;
+    P.lim.store_words = store_words;
+    P.lay = rp::make_aln_layout(P.lim);
+    std::vector<uint8_t> slot(P.lay.bytes + 64);
+    uint8_t* slot_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slot.data()) + 15) & ~uintptr_t(15));
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        AlnJob job{&P, p, slot_al};
+        rp::sim::run_warp(aln_entry, &job);
+    }
+    return 0;
+}
+
 /* packing only (host-side cost of rp_poa_add_window): returns number of GPU windows packed */
 int rp_sim_pack_only(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
                      const uint8_t* seq_has_qual, const uint32_t* seq_begin, const uint32_t* seq_end,

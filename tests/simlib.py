@@ -20,6 +20,11 @@ def lib():
         l.rp_sim_aln.restype = C.c_int
         l.rp_sim_aln.argtypes = [C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
                                                                     C.c_void_p, C.c_void_p, C.c_void_p]
+        l.rp_sim_aln_bp.restype = C.c_int
+        l.rp_sim_aln_bp.argtypes = [C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
+                                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                                       C.c_void_p]
         _lib = l
     return _lib
 
@@ -81,3 +86,38 @@ def sim_align(pairs, max_len=None, store_words=53000):
                          dist.ctypes.data, st.ctypes.data)
     assert r == 0
     return [(runs_to_cigar(runs[i, :n_runs[i]]), int(dist[i])) for i in range(n)], st
+
+
+def sim_align_bp(cases, window_length, store_words=53000):
+    """cases: [(query, target, t_begin, q_start)] -> [(cigar, distance, (n,2) breaking points)], status"""
+    n = len(cases)
+    blob = b"".join(q + t for q, t, _, _ in cases)
+    bases = np.frombuffer(blob, dtype=np.uint8).copy()
+    q_off = np.zeros(n, np.uint32)
+    q_len = np.zeros(n, np.uint32)
+    t_off = np.zeros(n, np.uint32)
+    t_len = np.zeros(n, np.uint32)
+    t_begin = np.asarray([c[2] for c in cases], np.uint32)
+    q_start = np.asarray([c[3] for c in cases], np.uint32)
+    o = 0
+    for i, (q, t, _, _) in enumerate(cases):
+        q_off[i], q_len[i] = o, len(q)
+        o += len(q)
+        t_off[i], t_len[i] = o, len(t)
+        o += len(t)
+    max_len = int(max(max(len(q), len(t)) for q, t, _, _ in cases))
+    stride = 2 * max_len + 8
+    bstride = 2 * (max_len // window_length + 3)
+    runs = np.zeros((n, stride), np.uint32)
+    n_runs = np.zeros(n, np.uint32)
+    dist = np.zeros(n, np.int32)
+    st = np.zeros(n, np.uint32)
+    bp = np.zeros((n, bstride, 2), np.uint32)
+    n_bp = np.zeros(n, np.uint32)
+    r = lib().rp_sim_aln_bp(n, bases.ctypes.data, q_off.ctypes.data, q_len.ctypes.data, t_off.ctypes.data,
+                            t_len.ctypes.data, max_len, store_words, runs.ctypes.data, stride, n_runs.ctypes.data,
+                            dist.ctypes.data, st.ctypes.data, window_length, t_begin.ctypes.data, q_start.ctypes.data,
+                            bp.ctypes.data, bstride, n_bp.ctypes.data)
+    assert r == 0
+    return [(runs_to_cigar(runs[i, :n_runs[i]]), int(dist[i]), bp[i, :n_bp[i]].copy()) for i in range(n)], st
+
