@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--windows", type=int, default=10000, help="windows per GPU per step (BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-batches", type=int, default=2,
+                    help="batch objects the end-to-end arm cycles through (racon's -c/--cudapoa-batches)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -243,14 +245,23 @@ def main():
     gpu_launches = batch.info()["launches"] - launches0
 
     # ---- end-to-end arm: C-ABI call with host buffers (H2D + kernel + D2H + fetch) ------------------
+    # what racon's CUDAPolisher does with `-c K` batch objects (cudapolisher.cpp:254-276): each object, on its own
+    # stream, is reset, filled from host buffers (copied into pinned staging), run (H2D + kernel + D2H, asynchronous)
+    # and read back; while one object's kernel runs, the host fills the next one.
+    nb = max(1, args.e2e_batches)
+    objs = [batch] + [api.PoaBatch(device=local, window_length=500) for _ in range(nb - 1)]
+    bounds = [n * k // nb for k in range(nb + 1)]
+
     def plugin_step():
-        # exactly what racon's CUDABatchProcessor does per batch: reset, addWindow x n (host buffers are copied
-        # into pinned staging), generateConsensus (H2D + kernel + D2H), read the consensus strings back
-        batch.reset()
-        assert batch.add_window_set(ws) == n
-        batch.run()
-        batch.sync()
-        return batch.fetch_all(stride)
+        for k, b in enumerate(objs):
+            b.reset()
+            assert b.add_window_set(ws, first=bounds[k], count=bounds[k + 1] - bounds[k]) == bounds[k + 1] - bounds[k]
+            b.run()
+        parts = []
+        for b in objs:
+            b.sync()
+            parts.append(b.fetch_all(stride))
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(4))
 
     for _ in range(2):
         plugin_step()
@@ -263,7 +274,11 @@ def main():
             gathered = shard.gather_packed(out[mask], lens, device="cuda")
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    if windows.fnv1a64([out[i, :lens[i]].tobytes() for i in range(min(n, 200))]) != int(checksum, 16):
+        raise SystemExit("bench.py: end-to-end arm produced a different consensus than the kernel-only arm")
     io = batch.info()
+    io["h2d_bytes"] = sum(b.info()["h2d_bytes"] for b in objs)
+    io["d2h_bytes"] = sum(b.info()["d2h_bytes"] for b in objs)
 
     # ---- max over ranks ---------------------------------------------------------------------------
     tt = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
@@ -290,8 +305,9 @@ def main():
                        "consensus_fnv_first200": checksum},
             "e2e": {"value": world * n * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": io["h2d_bytes"], "d2h_bytes_per_step": io["d2h_bytes"],
-                    "includes": "rp_poa_reset + rp_poa_add_window_set (host buffers -> pinned staging) + rp_poa_run (H2D, kernel, "
-                                "D2H) + rp_poa_sync + rp_poa_fetch_all"
+                    "batch_objects": nb,
+                    "includes": "per batch object: rp_poa_reset + rp_poa_add_window_set (host buffers -> pinned staging) + "
+                                "rp_poa_run (H2D, kernel, D2H) + rp_poa_sync + rp_poa_fetch_all"
                                 + ("; + NCCL all_gather of consensus bytes" if distributed else "")},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
@@ -304,7 +320,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
-    batch.close()
+    for b in objs:
+        b.close()
     if distributed:
         dist.destroy_process_group()
 
