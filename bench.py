@@ -349,9 +349,26 @@ def cpu_baseline(args):
         threads = cores if fn(probe, threads=cores)[2] <= fn(probe, threads=cores // 2)[2] else cores // 2
     out = fn(ws, threads=threads)
     secs = out[2]
-    return {"value": n_sample / secs, "unit": "windows/s", "cores": threads, "kind": kind,
-            "sample": "first %d windows of the workload, %d host threads (of %d hardware threads), consensus loop "
-                      "only (%.1f s)" % (n_sample, threads, cores, secs)}
+    res = {"value": n_sample / secs, "unit": "windows/s", "cores": threads, "kind": kind,
+           "sample": "first %d windows of the workload, %d host threads (of %d hardware threads), consensus loop "
+                     "only (%.1f s)" % (n_sample, threads, cores, secs)}
+    res["gpu_reference"] = gpu_reference(args)
+    return res
+
+
+def gpu_reference(args):
+    """The reference's OWN GPU path (GenomeWorks cudapoa, unmodified, oracle/_ref/libref_cudapoa.so) on the same
+    workload and the same GPU — SURVEY §8(d)'s GPU baseline.  Separate process with a time limit: a failure inside the
+    reference library must not take the bench line down.  Timing only (cudapoa's consensus is not spoa's)."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    try:
+        p = subprocess.run([sys.executable, "-m", "oracle.cudapoa_time", "--windows", str(min(args.windows, 10000))],
+                           cwd=here, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=240, text=True)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"unavailable": "no output (exit %d)" % p.returncode}
+    except Exception as e:  # noqa: BLE001 - reported, never fatal
+        return {"unavailable": "%s" % e}
 
 
 if __name__ == "__main__":

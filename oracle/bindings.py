@@ -141,3 +141,33 @@ def oracle_breaking_points(cigar, t_begin, t_end, q_start, window_length):
         raise RuntimeError("oracle breaking points failed (%d)" % n)
     return out[:n].copy()
 
+
+CUDAPOA_SO = os.path.join(HERE, "_ref", "libref_cudapoa.so")
+
+
+def have_ref_cudapoa():
+    return os.path.exists(CUDAPOA_SO)
+
+
+def ref_cudapoa_consensus(ws, match=3, mismatch=-5, gap=-4, banded=False, max_depth=200, device=0, mem_fraction=0.5):
+    """The reference's own GPU path (GenomeWorks cudapoa, unmodified; oracle/ref_cudapoa_harness.cu) on a window set.
+    Returns (list of consensus bytes — b"" where cudapoa rejected the window —, n_ok, wall seconds, GPU-call seconds).
+    Timing only: cudapoa's consensus is not spoa's."""
+    lib = C.CDLL(CUDAPOA_SO)
+    lib.ref_cudapoa_consensus.restype = C.c_int64
+    lib.ref_cudapoa_consensus.argtypes = [C.c_uint32] + [C.c_void_p] * 6 + [C.c_int8, C.c_int8, C.c_int8, C.c_int,
+                                                                            C.c_uint32, C.c_int, C.c_double, C.c_void_p,
+                                                                            C.c_uint32, C.c_void_p, C.c_void_p]
+    n = ws.n_windows
+    stride = 2048
+    out = np.zeros((n, stride), np.uint8)
+    out_len = np.zeros(n, np.uint32)
+    times = np.zeros(2, np.float64)
+    seq_off = np.ascontiguousarray(ws.seq_off, dtype=np.uint64)
+    ok = lib.ref_cudapoa_consensus(n, _ptr(ws.bases), _ptr(ws.quals), _ptr(seq_off), _ptr(ws.seq_has_qual),
+                                   _ptr(ws.seq_begin), _ptr(ws.win_first), match, mismatch, gap, 1 if banded else 0,
+                                   max_depth, device, mem_fraction, _ptr(out), stride, _ptr(out_len), _ptr(times))
+    if ok < 0:
+        raise RuntimeError("reference cudapoa failed (%d)" % ok)
+    return [out[i, :out_len[i]].tobytes() for i in range(n)], int(ok), float(times[0]), float(times[1])
+

@@ -22,3 +22,21 @@ def build_ref():
     if os.path.isdir("/root/reference/src"):
         _make("ref")
     return out if os.path.exists(out) else None
+
+
+def build_ref_cudapoa():
+    """The reference's own GPU path (GenomeWorks cudapoa) compiled unmodified for sm_100 — timing baseline only."""
+    out = os.path.join(HERE, "_ref", "libref_cudapoa.so")
+    if os.path.isdir("/root/reference/vendor/GenomeWorks/cudapoa/src"):
+        try:
+            _make("refcuda")
+        except RuntimeError as e:  # a baseline, not a checker: its absence is reported by bench.py, not fatal
+            print("[oracle] reference cudapoa not built: %s" % str(e)[:500])
+    return out if os.path.exists(out) else None
+
+
+def build_refpol():
+    out = os.path.join(HERE, "_ref", "refpol_dump")
+    if os.path.isdir("/root/reference/src"):
+        _make("refpol")
+    return out if os.path.exists(out) else None
