@@ -163,28 +163,61 @@ struct AlnWarp {
      * mode 2: additionally stores the vertical-(+1) and horizontal-(+1) words of every column (base case). */
     RP_DEV int32_t band_pass(const uint64_t* peq, uint32_t n, const uint8_t* t, uint32_t m, bool rev_t, int32_t k,
                              uint32_t stop_col, int mode, int32_t* col) {
-        /* widest the band can get, in words: its k+1 rows straddle at most ceil(rows / 64) + 1 words */
-        const int32_t delta = static_cast<int32_t>(n) - static_cast<int32_t>(m);
-        const int32_t rows = (k + delta) / 2 + (k - delta) / 2 + 1;
-        int32_t span = (rows + 63) / 64 + 1;
-        const int32_t nw = static_cast<int32_t>((n + 63) / 64);
-        if (span > nw) span = nw;
-        if (span <= 32) return band_pass_t<1>(peq, n, t, m, rev_t, k, stop_col, mode, col);
-        if (span <= 32 * kAlnSlots) return band_pass_t<kAlnSlots>(peq, n, t, m, rev_t, k, stop_col, mode, col);
+        const int32_t span = band_span(n, m, k);
+        if (span <= 32) return band_pass_t<1, 32>(peq, peq, n, t, m, rev_t, rev_t, k, stop_col, stop_col, mode, col, col);
+        if (span <= 32 * kAlnSlots)
+            return band_pass_t<kAlnSlots, 32>(peq, peq, n, t, m, rev_t, rev_t, k, stop_col, stop_col, mode, col, col);
         fail(kAlnBandLimit);
         return kAlnInf;
     }
 
-    RP_DEV static uint32_t rotr32(uint32_t x, int r) {
-        r &= 31;
-        return r ? (x >> r) | (x << (32 - r)) : x;
+    /* widest the band can get, in words: its k+1 rows straddle at most ceil(rows / 64) + 1 words */
+    RP_DEV static int32_t band_span(uint32_t n, uint32_t m, int32_t k) {
+        const int32_t delta = static_cast<int32_t>(n) - static_cast<int32_t>(m);
+        const int32_t rows = (k + delta) / 2 + (k - delta) / 2 + 1;
+        int32_t span = (rows + 63) / 64 + 1;
+        const int32_t nw = static_cast<int32_t>((n + 63) / 64);
+        return span > nw ? nw : span;
     }
 
-    /* SLOTS = band words a lane may hold at once.  With a band of <= 32 words (SLOTS = 1) the word that enters at
-     * the bottom always lands in the lane whose previous word has just left at the top. */
-    template <int SLOTS>
-    RP_DEV int32_t band_pass_t(const uint64_t* peq, uint32_t n, const uint8_t* t, uint32_t m, bool rev_t, int32_t k,
-                               uint32_t stop_col, int mode, int32_t* col) {
+    /* The two passes of one Hirschberg node — forward over the left half of the target into col_a, reverse over the
+     * right half into col_b (edlib.cpp:1237-1262) — have the same n, m, k and therefore the same band geometry.
+     * When that band fits 16 words they run side by side, one per half-warp; otherwise one after the other. */
+    RP_DEV void band_pass_pair(const uint64_t* peq_a, const uint64_t* peq_b, uint32_t n, const uint8_t* t, uint32_t m,
+                               int32_t k, uint32_t stop_a, uint32_t stop_b, int32_t* col_a, int32_t* col_b) {
+        if (band_span(n, m, k) <= 16) {
+            band_pass_t<1, 16>(peq_a, peq_b, n, t, m, false, true, k, stop_a, stop_b, 1, col_a, col_b);
+        } else {
+            band_pass(peq_a, n, t, m, false, k, stop_a, 1, col_a);
+            if (status != kAlnOk) return;
+            band_pass(peq_b, n, t, m, true, k, stop_b, 1, col_b);
+        }
+    }
+
+    RP_DEV static uint32_t rotr_w(uint32_t x, int r, int width) {  // rotate right inside the low `width` bits
+        const uint32_t mask = width == 32 ? 0xffffffffu : ((1u << width) - 1u);
+        x &= mask;
+        return r ? ((x >> r) | (x << (width - r))) & mask : x;
+    }
+
+    /* SLOTS = band words a lane may hold at once.  With a band of <= W words (SLOTS = 1) the word that enters at
+     * the bottom always lands in the lane whose previous word has just left at the top.
+     * W = lanes per problem: 32 (one problem, the *_a arguments) or 16 (problem a in lanes 0-15, b in lanes 16-31;
+     * same n, m, k; SLOTS = 1, mode 1 only). */
+    template <int SLOTS, int W>
+    RP_DEV int32_t band_pass_t(const uint64_t* peq_a, const uint64_t* peq_b, uint32_t n, const uint8_t* t, uint32_t m,
+                               bool rev_a, bool rev_b, int32_t k, uint32_t stop_a, uint32_t stop_b, int mode,
+                               int32_t* col_a, int32_t* col_b) {
+        static_assert(W == 32 || (W == 16 && SLOTS == 1), "two problems per warp need single-slot bands");
+        const bool second = W == 16 && lane >= 16;
+        const uint64_t* peq = second ? peq_b : peq_a;
+        const bool rev_t = second ? rev_b : rev_a;
+        const uint32_t stop_col = second ? stop_b : stop_a;
+        int32_t* col = second ? col_b : col_a;
+        const int sl = lane & (W - 1);        // my lane inside the problem's lane group
+        const int gbase = lane & ~(W - 1);    // first lane of the group
+        const uint32_t last_col = stop_a > stop_b ? stop_a : stop_b;
+
         const int32_t delta = static_cast<int32_t>(n) - static_cast<int32_t>(m);
         const int32_t dlo = -((k - delta) / 2), dhi = (k + delta) / 2;  // diagonals i - j a cost-<=k path can touch
         const uint32_t nw = (n + 63) / 64;
@@ -204,24 +237,27 @@ struct AlnWarp {
         const int32_t n1 = static_cast<int32_t>(n) - 1;
         const uint64_t rep = 0x0101010101010101ull;
         uint32_t tc_next = rev_t ? t[m - 1] : t[0];
-        for (uint32_t j = 0; j <= stop_col; ++j) {
+        for (uint32_t j = 0; j <= last_col; ++j) {
+            const bool live = j <= stop_col;   // the other half-warp's problem may run one column longer
             int32_t rlo = static_cast<int32_t>(j) + dlo, rhi = static_cast<int32_t>(j) + dhi;
             if (rlo < 0) rlo = 0;
             if (rhi > n1) rhi = n1;
             const int32_t wlo = rlo >> 6, whi = rhi >> 6;
             /* the band slides one row per column, so at most one word enters at the bottom (vertical +1 everywhere);
              * the words of column 0 are still in their initial state */
-            if (j == 0) {
-                sb = 64 * (whi + 1);  // boundary column: H[r][-1] = r + 1
-            } else if (whi != whi_prev) {
-                sb += 64;
-                if ((whi & 31) == lane) {
+            if (live) {
+                if (j == 0) {
+                    sb = 64 * (whi + 1);  // boundary column: H[r][-1] = r + 1
+                } else if (whi != whi_prev) {
+                    sb += 64;
+                    if ((whi & (W - 1)) == sl) {
 #pragma unroll
-                    for (int q = 0; q < SLOTS; ++q)
-                        if (SLOTS == 1 || q == ((whi >> 5) % SLOTS)) {
-                            pv[q] = ~0ull;
-                            mv[q] = 0;
-                        }
+                        for (int q = 0; q < SLOTS; ++q)
+                            if (SLOTS == 1 || q == ((whi >> 5) % SLOTS)) {
+                                pv[q] = ~0ull;
+                                mv[q] = 0;
+                            }
+                    }
                 }
             }
             const uint32_t tc = tc_next;
@@ -237,12 +273,12 @@ struct AlnWarp {
             int32_t carry = 1;  // horizontal delta entering the top word of the band (edlib.cpp:766: hout = 1)
             int32_t last_hout = 0;
             if (mode == 2 && lane == 0) store_first[j] = (static_cast<uint32_t>(wlo) << 16) | static_cast<uint32_t>(whi - wlo + 1);
-            /* rounds of 32 consecutive words */
-            for (int32_t w0 = wlo; w0 <= whi; w0 += 32) {
-                const int rot = w0 & 31;
-                const int pos = (lane - rot) & 31;       // my word's position inside the round
+            /* rounds of W consecutive words */
+            for (int32_t w0 = wlo; w0 <= whi; w0 += W) {
+                const int rot = w0 & (W - 1);
+                const int pos = (sl - rot) & (W - 1);    // my word's position inside the round
                 const int32_t w = w0 + pos;              // the word of this round that lives in my lane
-                const bool act = w <= whi;
+                const bool act = live && w <= whi;
                 uint64_t Pv = pv[0], Mv = mv[0];
                 if (SLOTS > 1) {
                     const int s = (w >> 5) % SLOTS;
@@ -256,15 +292,15 @@ struct AlnWarp {
                 const uint64_t Eq = (act && known) ? peq_row[w] : 0ull;
                 /* The carry into a word matters to its carry-out only through "hin < 0" (it ORs bit 0 into Eq), and
                  * a negative carry-in can only lower the carry-out.  So every word evaluates both cases, and the
-                 * chain "negative out = generate | (propagate & negative in)" is resolved for all 32 words at once
+                 * chain "negative out = generate | (propagate & negative in)" is resolved for all words at once
                  * with two ballots and one integer add. */
                 const uint64_t Eq1 = Eq | 1ull;
                 const uint64_t Xh0 = (((Eq & Pv) + Pv) ^ Pv) | Eq;
                 const uint64_t Xh1 = (((Eq1 & Pv) + Pv) ^ Pv) | Eq1;
                 const bool neg0 = act && ((Pv & Xh0) >> 63) != 0;
                 const bool neg1 = act && ((Pv & Xh1) >> 63) != 0;
-                const uint32_t gen = rotr32(ballot(neg0), rot);
-                const uint32_t prop = rotr32(ballot(neg1 && !neg0), rot);
+                const uint32_t gen = rotr_w(ballot(neg0) >> gbase, rot, W);
+                const uint32_t prop = rotr_w(ballot(neg1 && !neg0) >> gbase, rot, W);
                 const uint32_t cin = carry < 0 ? 1u : 0u;
                 const uint32_t negin = ((gen | prop) + gen + cin) ^ prop;  // bit p: negative carry into position p
                 const bool hneg = ((negin >> pos) & 1u) != 0;
@@ -273,7 +309,7 @@ struct AlnWarp {
                 const uint64_t Ph = Mv | ~(Xh | Pv);
                 const uint64_t Mh = Pv & Xh;
                 const int32_t hout = act ? static_cast<int32_t>(Ph >> 63) - static_cast<int32_t>(Mh >> 63) : 0;
-                int32_t hin = shfl(hout, (lane + 31) & 31);
+                int32_t hin = shfl(hout, gbase | ((sl + W - 1) & (W - 1)));
                 if (pos == 0) hin = carry;
                 const uint64_t Phs = (Ph << 1) | (hin > 0 ? 1ull : 0ull);
                 const uint64_t Mhs = (Mh << 1) | (hneg ? 1ull : 0ull);
@@ -303,8 +339,8 @@ struct AlnWarp {
                     }
                 }
                 /* carry into the next round = hout of the last word of this round */
-                const int32_t last_w = (w0 + 31 <= whi) ? w0 + 31 : whi;
-                last_hout = shfl(hout, last_w & 31);
+                const int32_t last_w = (w0 + W - 1 <= whi) ? w0 + W - 1 : whi;
+                last_hout = shfl(hout, gbase | (last_w & (W - 1)));
                 carry = last_hout;
             }
             if (mode == 2) {
@@ -314,8 +350,10 @@ struct AlnWarp {
                     return kAlnInf;
                 }
             }
-            sb += last_hout;
-            whi_prev = whi;
+            if (live) {
+                sb += last_hout;
+                whi_prev = whi;
+            }
         }
         /* H at row r of the stop column: bottom score minus the vertical deltas below r */
         const int32_t j = static_cast<int32_t>(stop_col);
@@ -325,29 +363,40 @@ struct AlnWarp {
         const int32_t wlo = rlo >> 6, whi = rhi >> 6;
         int32_t result = kAlnInf;
         if (mode == 1)
-            for (uint32_t r = lane; r <= n; r += 32) col[r] = (r == 0) ? j + 1 : kAlnInf;
+            for (uint32_t r = sl; r <= n; r += W) col[r] = (r == 0) ? j + 1 : kAlnInf;
         syncwarp();
-        /* walk the words from the bottom of the band up; words of one round are handled together */
+        /* walk the words from the bottom of the band up; words of one round are handled together.  With two problems
+         * per warp the band is a single round, so the loop bounds below are the same for every lane that matters. */
         int32_t below = 0;  // sum of vertical deltas of all words below the current round
-        for (int32_t w1 = whi; w1 >= wlo; w1 -= 32) {
-            /* this round covers words (w1-31 .. w1) clipped to wlo */
-            const int32_t wbot = w1;
-            const int32_t w = wbot - ((wbot - lane) & 31);  // the word <= wbot congruent to my lane
-            const bool act = w >= wlo && w >= wbot - 31;
-            const int s = (w >> 5) % SLOTS;
+        const int32_t rounds = W == 16 ? 1 : (whi - wlo) / W + 1;
+        for (int32_t rd = 0; rd < rounds; ++rd) {
+            /* this round covers words (wbot-W+1 .. wbot) clipped to wlo */
+            const int32_t wbot = whi - rd * W;
+            const int32_t w = wbot - ((wbot - sl) & (W - 1));  // the word <= wbot congruent to my lane
+            const bool act = w >= wlo && w > wbot - W;
             uint64_t Pv = 0, Mv = 0;
-#pragma unroll
-            for (int q = 0; q < SLOTS; ++q)
-                if (q == s && act) {
-                    Pv = pv[q];
-                    Mv = mv[q];
+            if (SLOTS == 1) {
+                if (act) {
+                    Pv = pv[0];
+                    Mv = mv[0];
                 }
+            } else {
+                const int s = (w >> 5) % SLOTS;
+#pragma unroll
+                for (int q = 0; q < SLOTS; ++q)
+                    if (q == s && act) {
+                        Pv = pv[q];
+                        Mv = mv[q];
+                    }
+            }
             const int32_t mine = act ? popc64(Pv) - popc64(Mv) : 0;
-            /* suffix sum over the words of this round that lie below mine (larger w) */
-            int32_t suffix = 0;
-            for (int32_t ww = wbot; ww > wbot - 32 && ww >= wlo; --ww) {
-                const int32_t v = shfl(mine, ww & 31);
+            /* suffix sum over the words of this round that lie below mine (larger w); round_sum over all of them */
+            int32_t suffix = 0, round_sum = 0;
+            for (int d = 0; d < W; ++d) {
+                const int32_t ww = wbot - d;
+                const int32_t v = shfl(mine, gbase | (ww & (W - 1)));
                 if (ww > w) suffix += v;
+                round_sum += v;
             }
             if (act) {
                 const int32_t hbot = sb - below - suffix;  // H at row 64w + 63
@@ -368,12 +417,10 @@ struct AlnWarp {
                     result = hbot - (popc64(Pv & above) - popc64(Mv & above));
                 }
             }
-            int32_t round_sum = 0;
-            for (int32_t ww = wbot; ww > wbot - 32 && ww >= wlo; --ww) round_sum += shfl(mine, ww & 31);
             below += round_sum;
         }
-        /* the lane that owns row n-1 holds the result */
-        for (int d = 16; d > 0; d >>= 1) {
+        /* the lane that owns row n-1 holds the result (W == 16: the first problem's) */
+        for (int d = W / 2; d > 0; d >>= 1) {
             int32_t o = shfl_down(result, d);
             result = o < result ? o : result;
         }
@@ -410,41 +457,72 @@ struct AlnWarp {
             run += shfl(inc, 31);
         }
         syncwarp();
+        /* The walk is serial, its loads need not be: the lanes hold the stored words of 32 consecutive columns
+         * (lane l: column jhi - l, band words wa and wa - 1), refilled with one round of parallel loads whenever the
+         * walk leaves that block; every step then takes its column's words from the owning lane by shuffle.  All
+         * lanes execute the (uniform) walk; lane 0 writes the operations. */
         int32_t i = static_cast<int32_t>(n) - 1, j = static_cast<int32_t>(m) - 1;
         uint32_t pos = *wpos;
-        if (lane == 0) {
-            while (i >= 0 && j >= 0) {
-                const uint32_t sf = store_first[j];
-                const int32_t wl = static_cast<int32_t>(sf >> 16), cnt = static_cast<int32_t>(sf & 0xffffu);
-                const int32_t w = i >> 6;
-                uint8_t op;
-                if (w < wl || w >= wl + cnt) {  // cannot happen: optimal paths stay inside the band
-                    status = kAlnInternal;
-                    break;
+        int32_t jhi = -1, jlo = 0, wa = 0;
+        uint64_t pva = 0, pha = 0, pvb = 0, phb = 0;
+        uint32_t have = 0;  // bit 0: word wa stored for my column, bit 1: word wa - 1
+        while (i >= 0 && j >= 0) {
+            const int32_t w = i >> 6;
+            if (j > jhi || j < jlo || w > wa || w < wa - 1) {
+                jhi = j;
+                jlo = j >= 31 ? j - 31 : 0;
+                wa = w;
+                const int32_t c = j - lane;
+                pva = pha = pvb = phb = 0;
+                have = 0;
+                if (c >= 0) {
+                    const uint32_t sf = store_first[c];
+                    const int32_t wl = static_cast<int32_t>(sf >> 16), cnt = static_cast<int32_t>(sf & 0xffffu);
+                    const uint64_t base = static_cast<uint64_t>(col_l[c]);
+                    if (wa >= wl && wa < wl + cnt) {
+                        pva = store_pv[base + static_cast<uint64_t>(wa - wl)];
+                        pha = store_ph[base + static_cast<uint64_t>(wa - wl)];
+                        have |= 1u;
+                    }
+                    if (wa - 1 >= wl && wa - 1 < wl + cnt) {
+                        pvb = store_pv[base + static_cast<uint64_t>(wa - 1 - wl)];
+                        phb = store_ph[base + static_cast<uint64_t>(wa - 1 - wl)];
+                        have |= 2u;
+                    }
                 }
-                const uint64_t at = static_cast<uint64_t>(col_l[j]) + static_cast<uint64_t>(w - wl);
-                const uint64_t bit = 1ull << (i & 63);
-                if (store_pv[at] & bit) {
-                    op = 'I';
-                    --i;
-                } else if (store_ph[at] & bit) {
-                    op = 'D';
-                    --j;
-                } else {
-                    op = 'M';
-                    --i;
-                    --j;
-                }
-                ops[--pos] = op;
             }
-            while (i >= 0) {
-                ops[--pos] = 'I';
+            const int src = jhi - j;
+            const bool first_word = w == wa;
+            const uint64_t pv = shfl(first_word ? pva : pvb, src);
+            const uint64_t ph = shfl(first_word ? pha : phb, src);
+            const uint32_t hv = shfl(have, src);
+            if (!(hv & (first_word ? 1u : 2u))) {  // cannot happen: optimal paths stay inside the band
+                status = kAlnInternal;
+                break;
+            }
+            const uint64_t bit = 1ull << (i & 63);
+            uint8_t op;
+            if (pv & bit) {
+                op = 'I';
                 --i;
-            }
-            while (j >= 0) {
-                ops[--pos] = 'D';
+            } else if (ph & bit) {
+                op = 'D';
+                --j;
+            } else {
+                op = 'M';
+                --i;
                 --j;
             }
+            --pos;
+            if (lane == 0) ops[pos] = op;
+        }
+        if (status == kAlnOk) {
+            /* the rest of the query / target is all insertions / deletions */
+            const uint32_t ri = static_cast<uint32_t>(i + 1), rj = static_cast<uint32_t>(j + 1);
+            for (uint32_t x = lane; x < ri; x += 32) ops[pos - 1 - x] = 'I';
+            pos -= ri;
+            for (uint32_t x = lane; x < rj; x += 32) ops[pos - 1 - x] = 'D';
+            pos -= rj;
         }
         *wpos = shfl(pos, 0);
         status = shfl(status, 0);
@@ -637,10 +715,9 @@ struct AlnWarp {
                 }
                 const uint32_t lw = tl / 2, rw = tl - lw;
                 build_peq(peq_f, q + qo, ql, false);
-                band_pass(peq_f, ql, t + to, tl, false, b, lw - 1, 1, col_l);      // col_l[r+1] = L[r]
-                if (status != kAlnOk) break;
                 build_peq(peq_r, q + qo, ql, true);
-                band_pass(peq_r, ql, t + to, tl, true, b, rw - 1, 1, col_r);        // col_r[x+1]: reversed rows
+                /* col_l[r+1] = L[r] (forward, left half); col_r[x+1]: reversed rows (reverse, right half) */
+                band_pass_pair(peq_f, peq_r, ql, t + to, tl, b, lw - 1, rw - 1, col_l, col_r);
                 if (status != kAlnOk) break;
                 syncwarp();
                 /* R[r] = dist(q[r..], t[lw..]) = reversed-problem cell row (ql-1-r): col_r[ql - r]; R[ql] = rw */
