@@ -42,7 +42,7 @@ struct AlnLimits {
 };
 
 struct AlnLayout {
-    uint64_t peq_f, peq_r, col_l, col_r, store_pv, store_ph, store_first, ops, stack, bytes;
+    uint64_t peq_f, peq_r, col_l, col_r, store_pv, store_ph, store_first, ops, stack, lut, bytes;
 };
 
 RP_HD AlnLayout make_aln_layout(const AlnLimits& L) {
@@ -63,6 +63,7 @@ RP_HD AlnLayout make_aln_layout(const AlnLimits& L) {
     a.store_first = take((static_cast<uint64_t>(L.max_len) + 2) * 4);
     a.ops = take(2ull * L.max_len + 64);
     a.stack = take(128 * 5 * 4);
+    a.lut = take(256);
     a.bytes = (o + 4095) / 4096 * 4096;
     return a;
 }
@@ -105,6 +106,7 @@ struct AlnWarp {
     uint32_t* store_first;
     uint8_t* ops;
     uint32_t* stack;
+    uint8_t* lut;       // byte -> index among the pair's symbols (kAlnMaxSyms = not present)
     uint32_t status;
     uint64_t syms;      // up to 8 distinct characters of the pair
     uint32_t nsyms;
@@ -122,6 +124,7 @@ struct AlnWarp {
         store_first = reinterpret_cast<uint32_t*>(slot + y.store_first);
         ops = slot + y.ops;
         stack = reinterpret_cast<uint32_t*>(slot + y.stack);
+        lut = slot + y.lut;
         status = kAlnOk;
     }
 
@@ -235,8 +238,8 @@ struct AlnWarp {
         int32_t sb = 0;          // H at the bottom row of word whi_prev (after the previous column)
         uint64_t store_pos = 0;
         const int32_t n1 = static_cast<int32_t>(n) - 1;
-        const uint64_t rep = 0x0101010101010101ull;
-        uint32_t tc_next = rev_t ? t[m - 1] : t[0];
+        uint32_t sidx_next = lut[rev_t ? t[m - 1] : t[0]];
+        uint32_t tc_next = stop_col >= 1 ? (rev_t ? t[m - 2] : t[1]) : 0;
         for (uint32_t j = 0; j <= last_col; ++j) {
             const bool live = j <= stop_col;   // the other half-warp's problem may run one column longer
             int32_t rlo = static_cast<int32_t>(j) + dlo, rhi = static_cast<int32_t>(j) + dhi;
@@ -260,14 +263,11 @@ struct AlnWarp {
                     }
                 }
             }
-            const uint32_t tc = tc_next;
-            if (j < stop_col) tc_next = rev_t ? t[m - 2 - j] : t[j + 1];
-            /* index of tc among the pair's symbols: first zero byte of syms ^ (tc repeated) */
-            const uint64_t x = syms ^ (rep * tc);
-            const uint64_t z = (x - rep) & ~x & (rep << 7);
-            const uint32_t zlo = static_cast<uint32_t>(z), zhi = static_cast<uint32_t>(z >> 32);
-            const uint32_t sidx = zlo ? static_cast<uint32_t>(ffs_(zlo) - 1) >> 3
-                                      : (zhi ? 4u + (static_cast<uint32_t>(ffs_(zhi) - 1) >> 3) : kAlnMaxSyms);
+            /* symbol index of this column's target character; the character two columns ahead and the index one
+             * column ahead are already in flight */
+            const uint32_t sidx = sidx_next;
+            sidx_next = lut[tc_next];
+            if (j + 1 < stop_col) tc_next = rev_t ? t[m - 3 - j] : t[j + 2];
             const uint64_t* peq_row = peq + static_cast<uint64_t>(sidx < nsyms ? sidx : 0) * nw;
             const bool known = sidx < nsyms;
             int32_t carry = 1;  // horizontal delta entering the top word of the band (edlib.cpp:766: hout = 1)
@@ -646,6 +646,24 @@ struct AlnWarp {
             }
             syms = sy;
             nsyms = over ? 0xffffffffu : ns;
+            /* byte -> symbol index table (256 B, stays in L1) for the per-column lookup of the target character:
+             * lane l fills bytes 8l .. 8l+7, which all live in bitmap word l / 4 */
+            {
+                uint32_t myword = 0, before = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k == (lane >> 2)) myword = seen[k];
+                    if (k < (lane >> 2)) before += static_cast<uint32_t>(popc(seen[k]));
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const uint32_t c = static_cast<uint32_t>(lane) * 8 + e;
+                    const uint32_t hit = (myword >> (c & 31)) & 1u;
+                    const uint32_t idx = before + static_cast<uint32_t>(popc(myword & ((1u << (c & 31)) - 1u)));
+                    lut[c] = static_cast<uint8_t>((hit && idx < kAlnMaxSyms) ? idx : kAlnMaxSyms);
+                }
+            }
+            syncwarp();
             if (nsyms == 0xffffffffu) {
                 nsyms = 0;
                 fail(kAlnAlphabetLimit);
