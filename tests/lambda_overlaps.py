@@ -12,8 +12,9 @@ def revcomp(b):
 
 
 class LambdaOverlaps:
-    def __init__(self):
-        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lambda_overlaps.npz"))
+    def __init__(self, name="lambda_overlaps.npz"):
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+        self.z = z
         self.bases = z["bases"].tobytes()
         self.quals = z["quals"].tobytes()
         self.seq_off = z["seq_off"].astype(np.int64)

@@ -85,6 +85,24 @@ def test_gpu_bp_lambda(lam):
 
 
 @pytest.mark.gpu
+def test_gpu_bp_lambda_fragment_correction():
+    """The 7780 all-vs-all overlaps (both strands) of the -f configuration: device breaking points == the reference's."""
+    from racon_b200 import api
+    lam = LambdaOverlaps("lambda_frag_overlaps.npz")
+    b = api.AlnBatch()
+    b.set_window_length(lam.window_length)
+    for k in range(lam.n_overlaps()):
+        q, t, t_begin, t_end, q_start = lam.spans(k)
+        assert b.add(q, t, t_begin=t_begin, q_start=q_start)
+    b.run()
+    b.sync()
+    for k in range(lam.n_overlaps()):
+        assert b.fetch(k)[2] == 0, k
+        assert np.array_equal(b.fetch_breaking_points(k), lam.expected_bp(k)), k
+    b.close()
+
+
+@pytest.mark.gpu
 def test_gpu_bp_random_pairs_vs_oracle():
     from racon_b200 import api
     rng = np.random.default_rng(21)
