@@ -270,7 +270,8 @@ def main():
     # stream, is reset, filled from host buffers (copied into pinned staging), run (H2D + kernel + D2H, asynchronous)
     # and read back; while one object's kernel runs, the host fills the next one.
     nb = max(1, args.e2e_batches)
-    objs = [batch] + [api.PoaBatch(device=local, window_length=500) for _ in range(nb - 1)]
+    # (each on its own stream; torch's current stream stays free for the NCCL gather)
+    objs = [api.PoaBatch(device=local, window_length=500) for _ in range(nb)]
     bounds = [n * k // nb for k in range(nb + 1)]
 
     last = {}
@@ -278,8 +279,8 @@ def main():
     def finalize(parts):
         out, lens, pol, st = (np.concatenate([p[i] for p in parts]) for i in range(4))
         if distributed:  # the one exchange step of the path: final consensus gather over NCCL
-            mask = np.arange(out.shape[1], dtype=np.uint32)[None, :] < lens[:, None]
-            last["gathered"] = shard.gather_packed(out[mask], lens, device="cuda")
+            flat = np.concatenate([out[i, :lens[i]] for i in range(len(lens))])
+            last["gathered"] = shard.gather_packed(flat, lens, device="cuda")
         last["out"], last["lens"] = out, lens
 
     def plugin_steps(n_steps):
@@ -319,7 +320,7 @@ def main():
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     if windows.fnv1a64([out[i, :lens[i]].tobytes() for i in range(min(n, 200))]) != int(checksum, 16):
         raise SystemExit("bench.py: end-to-end arm produced a different consensus than the kernel-only arm")
-    io = batch.info()
+    io = objs[0].info()
     io["h2d_bytes"] = sum(b.info()["h2d_bytes"] for b in objs)
     io["d2h_bytes"] = sum(b.info()["d2h_bytes"] for b in objs)
 
@@ -369,7 +370,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
-    for b in objs:
+    for b in objs + [batch]:
         b.close()
     if distributed:
         dist.destroy_process_group()
