@@ -121,3 +121,43 @@ def test_aln_host_mirror_batch_aligner():
     got = api.mirror_align(pairs, max_alignments=7)
     for (q, t), c in zip(pairs, got):
         assert c == _expected(q, t)[0]
+
+
+def _cigar_cost(cigar, q, t):
+    """(query bases, target bases, edit operations) implied by a CIGAR on the two sequences"""
+    import re
+    qa = np.frombuffer(q, np.uint8)
+    ta = np.frombuffer(t, np.uint8)
+    i = j = cost = 0
+    for cnt, op in re.findall(rb"(\d+)([MID])", cigar):
+        c = int(cnt)
+        if op == b"M":
+            cost += int((qa[i:i + c] != ta[j:j + c]).sum())
+            i += c
+            j += c
+        elif op == b"I":
+            cost += c
+            i += c
+        else:
+            cost += c
+            j += c
+    return i, j, cost
+
+
+def test_aln_full_size_properties():
+    """BASELINE config 5's shape (10-kb reads, 12 % error), checked through properties that need no oracle: every
+    CIGAR consumes exactly both sequences, its own cost equals the reported edit distance, and the distance is
+    symmetric (query and target swapped in a second batch)."""
+    from racon_b200 import api
+    rng = np.random.default_rng(17)
+    pairs = []
+    for _ in range(1500):
+        n = int(rng.integers(8000, 12000))
+        t = bytes(util.BASES[i] for i in rng.integers(4, size=n))
+        pairs.append((util.mutate(rng, t, 0.12), t))
+    fwd = api.align(pairs)
+    rev = api.align([(t, q) for q, t in pairs])
+    for (q, t), (cig, dist, st), (_, rdist, rst) in zip(pairs, fwd, rev):
+        assert st == 0 and rst == 0
+        assert _cigar_cost(cig, q, t) == (len(q), len(t), dist)
+        assert dist == rdist
