@@ -122,7 +122,7 @@ rp_status rp_poa_enable_counters(rp_poa* p, int on);
  * computes what Overlap::align_overlaps (src/overlap.cpp:205-224) computes with edlib:
  * edlibAlign(query, target, NW, k = -1, TASK_PATH) -> edlibAlignmentToCigar(EDLIB_CIGAR_STANDARD).
  * The CIGAR is byte-identical to edlib's (tests/test_gpu_aln.py).  An overlap the device cannot take
- * (band wider than 8192 rows, sequence longer than the object's limit, > 8 distinct characters) gets a soft
+ * (band wider than 16384 rows, sequence longer than the object's limit, > 16 distinct characters) gets a soft
  * status and an empty CIGAR, exactly like a cudaaligner failure: the caller's CPU edlib call then handles it
  * (src/cuda/cudapolisher.cpp:213, "overlaps whose cigar_ is still empty").
  * ------------------------------------------------------------------------------------------------ */

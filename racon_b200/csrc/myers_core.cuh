@@ -22,8 +22,8 @@
 
 namespace rp {
 
-constexpr int kAlnSlots = 4;                  // band words per lane -> band of up to 128 words = 8192 rows
-constexpr uint32_t kAlnMaxSyms = 8;
+constexpr int kAlnSlots = 8;                  // band words per lane -> band of up to 256 words = 16384 rows
+constexpr uint32_t kAlnMaxSyms = 16;             // distinct characters per pair (match-mask rows)
 constexpr int32_t kAlnInf = 1 << 28;
 
 enum : uint32_t {
@@ -108,8 +108,7 @@ struct AlnWarp {
     uint32_t* stack;
     uint8_t* lut;       // byte -> index among the pair's symbols (kAlnMaxSyms = not present)
     uint32_t status;
-    uint64_t syms;      // up to 8 distinct characters of the pair
-    uint32_t nsyms;
+    uint32_t nsyms;     // distinct characters of the pair (<= kAlnMaxSyms); lut maps a byte to its index
 
     RP_DEV void bind(const AlnParams* p, uint8_t* slot) {
         P = p;
@@ -128,31 +127,19 @@ struct AlnWarp {
         status = kAlnOk;
     }
 
-    RP_DEV uint32_t sym_index(uint8_t c) const {
-        uint32_t k = 0;
-        for (; k < nsyms; ++k)
-            if (static_cast<uint8_t>(syms >> (8 * k)) == c) break;
-        return k;
-    }
-
     /* match masks of the (possibly reversed) query sub-range: peq[s * nw + w] bit b = (q[64w+b] == symbol s) */
     RP_DEV void build_peq(uint64_t* peq, const uint8_t* q, uint32_t n, bool rev) {
         /* 32 bases per step: one coalesced byte load, one ballot per symbol; lane s keeps symbol s's 32 bits */
         const uint32_t nw = (n + 63) / 64;
         uint32_t* peq32 = reinterpret_cast<uint32_t*>(peq);
-        const uint32_t my_sym = lane < static_cast<int>(nsyms) ? static_cast<uint32_t>((syms >> (8 * lane)) & 0xff) : 0u;
-        (void)my_sym;
         for (uint32_t g = 0; g < nw * 2; ++g) {
             const uint32_t i = g * 32 + static_cast<uint32_t>(lane);
             const bool valid = i < n;
-            const uint32_t c = valid ? (rev ? q[n - 1 - i] : q[i]) : 0u;
+            const uint32_t code = valid ? lut[rev ? q[n - 1 - i] : q[i]] : 0xffu;
             uint32_t mine = 0;
-#pragma unroll
-            for (int sidx = 0; sidx < kAlnMaxSyms; ++sidx) {
-                if (sidx < static_cast<int>(nsyms)) {
-                    const uint32_t bits = ballot(valid && c == static_cast<uint32_t>((syms >> (8 * sidx)) & 0xff));
-                    if (lane == sidx) mine = bits;
-                }
+            for (uint32_t sidx = 0; sidx < nsyms; ++sidx) {
+                const uint32_t bits = ballot(code == sidx);
+                if (static_cast<uint32_t>(lane) == sidx) mine = bits;
             }
             if (lane < static_cast<int>(nsyms)) peq32[(static_cast<uint64_t>(lane) * nw + (g >> 1)) * 2 + (g & 1)] = mine;
         }
@@ -613,7 +600,6 @@ struct AlnWarp {
         const uint32_t n = P->q_len[p], m = P->t_len[p];
         status = kAlnOk;
         /* alphabet of the pair */
-        syms = 0;
         nsyms = 0;
         {
             /* 256-bit "seen" bitmap per lane over a strided share of the bytes, OR-reduced across the warp */
@@ -629,23 +615,10 @@ struct AlnWarp {
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) seen[k] |= shfl(seen[k], lane ^ d);
             }
-            uint64_t sy = 0;
             uint32_t ns = 0;
-            bool over = false;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint32_t wbits = seen[k];
-                while (wbits && !over) {
-                    const uint32_t c = static_cast<uint32_t>(k) * 32 + static_cast<uint32_t>(ffs_(wbits) - 1);
-                    wbits &= wbits - 1;
-                    if (ns == kAlnMaxSyms)
-                        over = true;
-                    else
-                        sy |= static_cast<uint64_t>(c) << (8 * ns++);
-                }
-            }
-            syms = sy;
-            nsyms = over ? 0xffffffffu : ns;
+            for (int k = 0; k < 8; ++k) ns += static_cast<uint32_t>(popc(seen[k]));
+            nsyms = ns > kAlnMaxSyms ? 0xffffffffu : ns;
             /* byte -> symbol index table (256 B, stays in L1) for the per-column lookup of the target character:
              * lane l fills bytes 8l .. 8l+7, which all live in bitmap word l / 4 */
             {

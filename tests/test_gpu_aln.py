@@ -74,12 +74,14 @@ def test_aln_soft_failures():
     from racon_b200 import api
     rng = np.random.default_rng(14)
     ok = _pair(rng, 300, 0.1)
-    many_syms = (bytes(range(65, 65 + 12)) * 10, bytes(range(65, 65 + 12)) * 10)
+    many_syms = (bytes(range(65, 65 + 20)) * 10, bytes(range(65, 65 + 20)) * 10)
     too_long = (b"A" * 3000, b"A" * 3000)
-    got = api.align([ok, many_syms, too_long, ok], max_len=2048)
+    iupac = (b"ACGTNRYKMSWB" * 30 + b"ACGT" * 50, b"ACGTNRYKMSW" * 30 + b"ACGA" * 55)   # 12 symbols: fine
+    got = api.align([ok, many_syms, too_long, ok, iupac], max_len=2048)
     assert got[0][2] == 0 and got[3][2] == 0 and got[0] == got[3]
     assert got[0][0] == _expected(*ok)[0]
-    assert got[1][2] == 2 and got[1][0] == b""      # RP_ALN_ALPHABET_LIMIT
+    assert got[4][2] == 0 and (got[4][0], got[4][1]) == _expected(*iupac)
+    assert got[1][2] == 2 and got[1][0] == b""      # RP_ALN_ALPHABET_LIMIT (> 16 distinct characters)
     assert got[2][2] == 6 and got[2][0] == b""      # RP_ALN_TOO_LONG
     # unrelated sequences: band grows to the limit or finishes; either way never a wrong CIGAR
     a = bytes(util.BASES[i] for i in rng.integers(4, size=20000))

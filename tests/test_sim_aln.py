@@ -52,3 +52,12 @@ def test_sim_aln_band_growth_multi_round():
     a = bytes(util.BASES[i] for i in rng.integers(4, size=3900))
     b = bytes(util.BASES[i] for i in rng.integers(4, size=3600))
     _check([(a, b)])
+
+
+def test_sim_aln_wide_alphabet():
+    """Up to 16 distinct characters per pair (IUPAC codes, mixed case); beyond that a soft status."""
+    q = b"ACGTNRYKMSWB" * 12 + b"acgt" * 9
+    t = b"ACGTNRYKMSW" * 13 + b"acga" * 8
+    _check([(q, t)])
+    got, st = simlib.sim_align([(bytes(range(65, 85)) * 4, bytes(range(65, 85)) * 4)])
+    assert st[0] == 2 and got[0][0] == ""
