@@ -9,13 +9,18 @@
  * 1198-1363).  Any exact banded method therefore reproduces it; this one is built for a warp:
  *
  *   * one warp per overlap, lanes = 64-bit words of the Myers/Hyyro bit-vector column (word w of the band lives
- *     in lane w % 32, slot (w / 32) % kSlots), Ukkonen band of the diagonals that a path of cost <= k can touch;
- *   * the horizontal carry between the words of a column is resolved iteratively with one SHFL per round
- *     (it converges in 2-3 rounds in practice) instead of a 32-step serial chain;
- *   * distance by k doubling from 64 (any k that succeeds gives the exact distance); Hirschberg columns with
- *     k = the known score of the sub-problem; base cases store the vertical-(+1) and horizontal-(+1) bit-vectors
- *     of every band word and are walked back with edlib's move priority;
- *   * operations are written backwards into one buffer (right sub-problem first), then run-length encoded.
+ *     in lane w % 32, slot (w / 32) % kAlnSlots), Ukkonen band of the diagonals that a path of cost <= k can touch
+ *     (k + 1 rows, sliding one row per column); a column is processed in rounds of 32 words;
+ *   * the horizontal carry between the words of a round: a word's carry-out depends on its carry-in only through
+ *     "carry-in < 0", monotonically, so every word evaluates both cases and the chain is a generate/propagate
+ *     carry chain, resolved for all words at once with two ballots and one integer add;
+ *   * distance by k doubling, starting at the widest band that still fits one round (any k that succeeds gives
+ *     the exact distance); Hirschberg columns with k = the known score of the sub-problem, the forward and the
+ *     reverse pass of a node side by side in the two half-warps when the band fits 16 words; base cases store the
+ *     vertical-(+1) and horizontal-(+1) bit-vectors of every band word and are walked back with edlib's move
+ *     priority, the stored words of 32 columns at a time held in the lanes;
+ *   * operations are written backwards into one buffer (right sub-problem first), run-length encoded, and — when
+ *     a window length is set — turned into racon's breaking points (src/overlap.cpp:226-292) by the same warp.
  */
 #pragma once
 #include "rp_warp.cuh"
