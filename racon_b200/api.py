@@ -362,7 +362,9 @@ class MirrorPolisher:
 
     def __init__(self, bases, quals, seq_off, seq_has_qual, n_targets, overlaps, window_length=500,
                  quality_threshold=10.0, trim=True, match=3, mismatch=-5, gap=-4, window_type_tgs=True,
-                 fragment_correction=False, device=0):
+                 fragment_correction=False, device=0, breaking_points=None):
+        """breaking_points=(bp_off, bp): skip the device alignment and build the windows from given breaking points
+        (host logic only; no GPU needed, polish() is then not available)."""
         self.lib = load()
         L = self.lib
         vp = C.c_void_p
@@ -387,6 +389,18 @@ class MirrorPolisher:
         self._off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         self._hq = np.ascontiguousarray(seq_has_qual, dtype=np.uint8)
         ov = np.ascontiguousarray(overlaps, dtype=np.uint32)
+        if breaking_points is not None:
+            L.rp_mirror_polisher_open_with_bp.restype = vp
+            L.rp_mirror_polisher_open_with_bp.argtypes = [C.c_uint32, vp, vp, vp, vp, C.c_uint32, C.c_int, C.c_int,
+                                                          C.c_uint32, vp, vp, vp, C.c_uint32, C.c_double]
+            bp_off = np.ascontiguousarray(breaking_points[0], dtype=np.uint64)
+            bp = np.ascontiguousarray(breaking_points[1], dtype=np.uint32)
+            self.h = L.rp_mirror_polisher_open_with_bp(len(self._off) - 1, _ptr(self._bases), _ptr(self._quals),
+                                                       _ptr(self._off), _ptr(self._hq), n_targets,
+                                                       1 if window_type_tgs else 0, 1 if fragment_correction else 0,
+                                                       len(ov), _ptr(ov), _ptr(bp_off), _ptr(bp), window_length,
+                                                       quality_threshold)
+            return
         self.h = L.rp_mirror_polisher_open(len(self._off) - 1, _ptr(self._bases), _ptr(self._quals), _ptr(self._off),
                                            _ptr(self._hq), n_targets, 1 if window_type_tgs else 0,
                                            1 if fragment_correction else 0, len(ov), _ptr(ov), window_length,

@@ -303,6 +303,10 @@ void Polisher::find_overlap_breaking_points(std::vector<Overlap>& overlaps) {
 
 void Polisher::initialize(std::vector<Overlap>& overlaps) {
     find_overlap_breaking_points(overlaps);
+    build_windows(overlaps);
+}
+
+void Polisher::build_windows(const std::vector<Overlap>& overlaps) {
 
     /* one window per window_length_ bases of every target (polisher.cpp:383-401) */
     std::vector<uint64_t> id_to_first_window_id(targets_size_ + 1, 0);
@@ -422,6 +426,32 @@ extern "C" void* rp_mirror_polisher_open(uint32_t n_seq, const char* bases, cons
                                    fragment_correction != 0, window_length, quality_threshold, trim != 0, match,
                                    mismatch, gap, device));
     h->polisher->initialize(ovl);
+    return h;
+}
+
+/* Host logic only (no device call): the same, with the breaking points given (bp_off in points, bp = (t, q) pairs). */
+extern "C" void* rp_mirror_polisher_open_with_bp(uint32_t n_seq, const char* bases, const char* quals,
+                                                 const uint64_t* seq_off, const uint8_t* seq_has_qual,
+                                                 uint32_t n_targets, int window_type_tgs, int fragment_correction,
+                                                 uint32_t n_overlaps, const uint32_t* overlaps, const uint64_t* bp_off,
+                                                 const uint32_t* bp, uint32_t window_length, double quality_threshold) {
+    using namespace racon_b200;
+    std::vector<SequenceView> seqs(n_seq);
+    for (uint32_t i = 0; i < n_seq; ++i) {
+        seqs[i].data = bases + seq_off[i];
+        seqs[i].quality = seq_has_qual[i] ? quals + seq_off[i] : nullptr;
+        seqs[i].length = static_cast<uint32_t>(seq_off[i + 1] - seq_off[i]);
+    }
+    std::vector<Overlap> ovl(n_overlaps);
+    for (uint32_t i = 0; i < n_overlaps; ++i) {
+        const uint32_t* o = overlaps + 9ull * i;
+        ovl[i] = Overlap{o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], {}};
+        for (uint64_t b = bp_off[i]; b < bp_off[i + 1]; ++b) ovl[i].breaking_points_.emplace_back(bp[2 * b], bp[2 * b + 1]);
+    }
+    PolHandle* h = new PolHandle();
+    h->polisher.reset(new Polisher(std::move(seqs), n_targets, window_type_tgs ? WindowType::kTGS : WindowType::kNGS,
+                                   fragment_correction != 0, window_length, quality_threshold, true, 3, -5, -4, 0));
+    h->polisher->build_windows(ovl);
     return h;
 }
 

@@ -164,6 +164,8 @@ public:
     ~Polisher();
     void find_overlap_breaking_points(std::vector<Overlap>& overlaps);
     void initialize(std::vector<Overlap>& overlaps);
+    /* the window-building half of initialize() alone, for overlaps whose breaking points are already known */
+    void build_windows(const std::vector<Overlap>& overlaps);
     void polish(std::vector<PolishedSequence>& dst, bool drop_unpolished_sequences);
     const std::vector<std::shared_ptr<Window>>& windows() const { return windows_; }
 
