@@ -27,6 +27,10 @@
 
 namespace rp {
 
+#if defined(RP_HOST_SIM)
+static unsigned long g_sim_leaf_pairs = 0;   // test-only: how often two leaves shared a warp
+#endif
+
 constexpr int kAlnSlots = 8;                  // band words per lane -> band of up to 256 words = 16384 rows
 constexpr uint32_t kAlnMaxSyms = 16;             // distinct characters per pair (match-mask rows)
 constexpr int32_t kAlnInf = 1 << 28;
@@ -47,7 +51,8 @@ struct AlnLimits {
 };
 
 struct AlnLayout {
-    uint64_t peq_f, peq_r, col_l, col_r, store_pv, store_ph, store_first, ops, stack, lut, bytes;
+    uint64_t peq_f, peq_r, col_l, col_r, store_pv, store_ph, store_first, store2_pv, store2_ph, store2_first, ops, stack,
+        lut, bytes;
 };
 
 RP_HD AlnLayout make_aln_layout(const AlnLimits& L) {
@@ -66,6 +71,9 @@ RP_HD AlnLayout make_aln_layout(const AlnLimits& L) {
     a.store_pv = take(static_cast<uint64_t>(L.store_words) * 8);
     a.store_ph = take(static_cast<uint64_t>(L.store_words) * 8);
     a.store_first = take((static_cast<uint64_t>(L.max_len) + 2) * 4);
+    a.store2_pv = take(static_cast<uint64_t>(L.store_words) * 8);   // second store set: two leaves per warp
+    a.store2_ph = take(static_cast<uint64_t>(L.store_words) * 8);
+    a.store2_first = take((static_cast<uint64_t>(L.max_len) + 2) * 4);
     a.ops = take(2ull * L.max_len + 64);
     a.stack = take(128 * 5 * 4);
     a.lut = take(256);
@@ -106,7 +114,8 @@ struct AlnParams {
 struct AlnWarp {
     const AlnParams* P;
     int lane;
-    uint64_t *peq_f, *peq_r, *store_pv, *store_ph;
+    uint64_t *peq_f, *peq_r, *store_pv, *store_ph, *store2_pv, *store2_ph;
+    uint32_t* store2_first;
     int32_t *col_l, *col_r;
     uint32_t* store_first;
     uint8_t* ops;
@@ -126,6 +135,9 @@ struct AlnWarp {
         store_pv = reinterpret_cast<uint64_t*>(slot + y.store_pv);
         store_ph = reinterpret_cast<uint64_t*>(slot + y.store_ph);
         store_first = reinterpret_cast<uint32_t*>(slot + y.store_first);
+        store2_pv = reinterpret_cast<uint64_t*>(slot + y.store2_pv);
+        store2_ph = reinterpret_cast<uint64_t*>(slot + y.store2_ph);
+        store2_first = reinterpret_cast<uint32_t*>(slot + y.store2_first);
         ops = slot + y.ops;
         stack = reinterpret_cast<uint32_t*>(slot + y.stack);
         lut = slot + y.lut;
@@ -431,21 +443,32 @@ struct AlnWarp {
 
     /* base case: store the band, then walk back with edlib's priority up > left > diagonal (edlib.cpp:987-1097).
      * Operations are written backwards: ops[--wpos]. */
-    RP_DEV void base_case(const uint8_t* q, uint32_t n, const uint8_t* t, uint32_t m, int32_t best, uint32_t* wpos) {
-        build_peq(peq_f, q, n, false);
-        int32_t d = band_pass(peq_f, n, t, m, false, best, m - 1, 2, nullptr);
-        if (status != kAlnOk) return;
-        if (d != best) {
-            fail(kAlnInternal);
-            return;
+    RP_DEV void base_case(const uint8_t* q, uint32_t n, const uint8_t* t, uint32_t m, int32_t best, uint32_t* wpos,
+                          bool stored) {
+        if (!stored) {  // (a whole pair below the 1 MiB rule arrives with the band of its distance pass stored)
+            build_peq(peq_f, q, n, false);
+            int32_t d = band_pass(peq_f, n, t, m, false, best, m - 1, 2, nullptr);
+            if (status != kAlnOk) return;
+            if (d != best) {
+                fail(kAlnInternal);
+                return;
+            }
         }
+        walk_stored(n, m, store_pv, store_ph, store_first, col_l, wpos);
+    }
+
+    /* Walks a stored band back from its bottom-right cell with edlib's priority up > left > diagonal
+     * (edlib.cpp:987-1097).  spv/sph/sfirst: the store set filled by a mode-2 pass; coloff: an idle int32 array that
+     * receives the start of every column in the store. */
+    RP_DEV void walk_stored(uint32_t n, uint32_t m, const uint64_t* spv, const uint64_t* sph, const uint32_t* sfirst,
+                            int32_t* coloff, uint32_t* wpos) {
         /* column offsets of the store: exclusive prefix of the per-column word counts */
         uint32_t run = 0;
         for (uint32_t j0 = 0; j0 < m; j0 += 32) {
             uint32_t j = j0 + lane;
-            uint32_t cnt = j < m ? (store_first[j] & 0xffffu) : 0;
+            uint32_t cnt = j < m ? (sfirst[j] & 0xffffu) : 0;
             uint32_t inc = warp_incl_sum(cnt);
-            if (j < m) col_l[j] = static_cast<int32_t>(run + inc - cnt);  // col_l is idle here: start of column j
+            if (j < m) coloff[j] = static_cast<int32_t>(run + inc - cnt);  // start of column j in the store
             run += shfl(inc, 31);
         }
         syncwarp();
@@ -468,17 +491,17 @@ struct AlnWarp {
                 pva = pha = pvb = phb = 0;
                 have = 0;
                 if (c >= 0) {
-                    const uint32_t sf = store_first[c];
+                    const uint32_t sf = sfirst[c];
                     const int32_t wl = static_cast<int32_t>(sf >> 16), cnt = static_cast<int32_t>(sf & 0xffffu);
-                    const uint64_t base = static_cast<uint64_t>(col_l[c]);
+                    const uint64_t base = static_cast<uint64_t>(coloff[c]);
                     if (wa >= wl && wa < wl + cnt) {
-                        pva = store_pv[base + static_cast<uint64_t>(wa - wl)];
-                        pha = store_ph[base + static_cast<uint64_t>(wa - wl)];
+                        pva = spv[base + static_cast<uint64_t>(wa - wl)];
+                        pha = sph[base + static_cast<uint64_t>(wa - wl)];
                         have |= 1u;
                     }
                     if (wa - 1 >= wl && wa - 1 < wl + cnt) {
-                        pvb = store_pv[base + static_cast<uint64_t>(wa - 1 - wl)];
-                        phb = store_ph[base + static_cast<uint64_t>(wa - 1 - wl)];
+                        pvb = spv[base + static_cast<uint64_t>(wa - 1 - wl)];
+                        phb = sph[base + static_cast<uint64_t>(wa - 1 - wl)];
                         have |= 2u;
                     }
                 }
@@ -519,6 +542,130 @@ struct AlnWarp {
         *wpos = shfl(pos, 0);
         status = shfl(status, 0);
         syncwarp();
+    }
+
+
+    /* Two sibling leaves of the Hirschberg tree side by side, one per half-warp (their bands are a few words wide):
+     * leaf A (left child: peq_f, store set 1) in lanes 0-15, leaf B (right child: peq_r, store set 2) in lanes 16-31;
+     * each with its own n, m, k.  Same recurrence as band_pass_t in mode 2, single round, W = 16. */
+    RP_DEV void leaf_pair(const uint8_t* qa, uint32_t na, const uint8_t* ta, uint32_t ma, int32_t ka, const uint8_t* qb,
+                          uint32_t nb, const uint8_t* tb, uint32_t mb, int32_t kb, uint32_t* wpos) {
+        constexpr int W = 16;
+#if defined(RP_HOST_SIM)
+        if (lane == 0) ++g_sim_leaf_pairs;
+#endif
+        build_peq(peq_f, qa, na, false);
+        build_peq(peq_r, qb, nb, false);
+        const bool second = lane >= 16;
+        const uint64_t* peq = second ? peq_r : peq_f;
+        const uint8_t* t = second ? tb : ta;
+        const uint32_t n = second ? nb : na, m = second ? mb : ma;
+        const int32_t k = second ? kb : ka;
+        uint64_t* spv = second ? store2_pv : store_pv;
+        uint64_t* sph = second ? store2_ph : store_ph;
+        uint32_t* sfirst = second ? store2_first : store_first;
+        const int sl = lane & (W - 1), gbase = lane & ~(W - 1);
+        const int32_t delta = static_cast<int32_t>(n) - static_cast<int32_t>(m);
+        const int32_t dlo = -((k - delta) / 2), dhi = (k + delta) / 2;
+        const uint32_t nw = (n + 63) / 64;
+        const int32_t n1 = static_cast<int32_t>(n) - 1;
+        if (ballot(dhi < 0 || dlo > 0)) {
+            fail(kAlnInternal);
+            return;
+        }
+        uint64_t Pv = ~0ull, Mv = 0;
+        int32_t whi_prev = -1, sb = 0;
+        uint64_t store_pos = 0;
+        uint32_t sidx_next = lut[t[0]];
+        uint32_t tc_next = m > 1 ? t[1] : 0;
+        const uint32_t cols = ma > mb ? ma : mb;
+        int32_t whi = 0;
+        for (uint32_t j = 0; j < cols; ++j) {
+            const bool live = j < m;
+            int32_t rlo = static_cast<int32_t>(j) + dlo, rhi = static_cast<int32_t>(j) + dhi;
+            if (rlo < 0) rlo = 0;
+            if (rhi > n1) rhi = n1;
+            const int32_t wlo = rlo >> 6;
+            if (live) whi = rhi >> 6;
+            if (live) {
+                if (j == 0) {
+                    sb = 64 * (whi + 1);
+                } else if (whi != whi_prev) {
+                    sb += 64;
+                    if ((whi & (W - 1)) == sl) {
+                        Pv = ~0ull;
+                        Mv = 0;
+                    }
+                }
+            }
+            const uint32_t sidx = sidx_next;
+            sidx_next = lut[tc_next];
+            if (j + 2 < m) tc_next = t[j + 2];
+            const bool known = sidx < nsyms;
+            const uint64_t* peq_row = peq + static_cast<uint64_t>(known ? sidx : 0) * nw;
+            const int rot = wlo & (W - 1);
+            const int pos = (sl - rot) & (W - 1);
+            const int32_t w = wlo + pos;
+            const bool act = live && w <= whi;
+            const uint64_t Eq = (act && known) ? peq_row[w] : 0ull;
+            const uint64_t Eq1 = Eq | 1ull;
+            const uint64_t Xh0 = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            const uint64_t Xh1 = (((Eq1 & Pv) + Pv) ^ Pv) | Eq1;
+            const bool neg0 = act && ((Pv & Xh0) >> 63) != 0;
+            const bool neg1 = act && ((Pv & Xh1) >> 63) != 0;
+            const uint32_t gen = rotr_w(ballot(neg0) >> gbase, rot, W);
+            const uint32_t prop = rotr_w(ballot(neg1 && !neg0) >> gbase, rot, W);
+            const uint32_t negin = ((gen | prop) + gen) ^ prop;  // carry into the top word is +1: never negative
+            const bool hneg = ((negin >> pos) & 1u) != 0;
+            const uint64_t Xh = hneg ? Xh1 : Xh0;
+            const uint64_t Xv = Eq | Mv;
+            const uint64_t Ph = Mv | ~(Xh | Pv);
+            const uint64_t Mh = Pv & Xh;
+            const int32_t hout = act ? static_cast<int32_t>(Ph >> 63) - static_cast<int32_t>(Mh >> 63) : 0;
+            int32_t hin = shfl(hout, gbase | ((sl + W - 1) & (W - 1)));
+            if (pos == 0) hin = 1;
+            const uint64_t Phs = (Ph << 1) | (hin > 0 ? 1ull : 0ull);
+            const uint64_t Mhs = (Mh << 1) | (hneg ? 1ull : 0ull);
+            if (act) {
+                Pv = Mhs | ~(Xv | Phs);
+                Mv = Phs & Xv;
+                const uint64_t spos = store_pos + static_cast<uint64_t>(w - wlo);
+                if (spos < P->lim.store_words) {
+                    spv[spos] = Pv;
+                    sph[spos] = Ph;
+                } else {
+                    status = kAlnStoreLimit;
+                }
+            }
+            const int32_t last_hout = shfl(hout, gbase | (whi & (W - 1)));
+            if (live) {
+                if (sl == 0) sfirst[j] = (static_cast<uint32_t>(wlo) << 16) | static_cast<uint32_t>(whi - wlo + 1);
+                store_pos += static_cast<uint64_t>(whi - wlo + 1);
+                sb += last_hout;
+                whi_prev = whi;
+            }
+        }
+        if (ballot(status != kAlnOk)) {
+            fail(kAlnStoreLimit);
+            return;
+        }
+        /* each leaf must reproduce its known score: H[n-1][m-1] = bottom score minus the vertical deltas below row n-1 */
+        int32_t d = 0;
+        if (sl == ((n1 >> 6) & (W - 1))) {
+            const int bb = n1 & 63;
+            const uint64_t above = bb == 63 ? 0ull : (~0ull << (bb + 1));
+            d = sb - (popc64(Pv & above) - popc64(Mv & above));
+        }
+        d = shfl(d, gbase | ((n1 >> 6) & (W - 1)));
+        if (ballot(d != k)) {
+            fail(kAlnInternal);
+            return;
+        }
+        syncwarp();
+        /* operations are written backwards: the right leaf first */
+        walk_stored(nb, mb, store2_pv, store2_ph, store2_first, col_r, wpos);
+        if (status != kAlnOk) return;
+        walk_stored(na, ma, store_pv, store_ph, store_first, col_l, wpos);
     }
 
     RP_DEV void emit_run(uint8_t op, uint32_t count, uint32_t* wpos) {
@@ -649,6 +796,7 @@ struct AlnWarp {
         }
         int32_t best = -1;
         uint32_t n_out = 0;
+        bool direct = false;
         if (status == kAlnOk) {
             if (n == 0 || m == 0) {
                 best = static_cast<int32_t>(n + m);
@@ -658,12 +806,15 @@ struct AlnWarp {
                  * still fits one round (band = k + 1 rows); the distance found does not depend on the schedule */
                 int32_t k = 64 * 29;
                 const int32_t kmax = static_cast<int32_t>(n > m ? n : m);
+                /* a pair below edlib's 1 MiB rule is traced back from stored bit-vectors: store them right here
+                 * (any band that contains the optimal paths serves), so the pair needs no second pass */
+                direct = 20ull * ((n + 63) / 64) * m + 8ull * m < 1024ull * 1024ull;
                 for (;;) {
                     int32_t diff = static_cast<int32_t>(n) - static_cast<int32_t>(m);
                     if (diff < 0) diff = -diff;
                     if (k >= diff) {
                         int32_t kk = k < kmax ? k : kmax;
-                        int32_t d = band_pass(peq_f, n, t, m, false, kk, m - 1, 0, nullptr);
+                        int32_t d = band_pass(peq_f, n, t, m, false, kk, m - 1, direct ? 2 : 0, nullptr);
                         if (status != kAlnOk) break;
                         if (d <= kk) {
                             best = d;
@@ -706,7 +857,7 @@ struct AlnWarp {
                 const uint64_t blocks = (ql + 63) / 64;
                 const uint64_t data = 20ull * blocks * tl + 8ull * tl;  // edlib.cpp:1155-1157
                 if (data < 1024ull * 1024ull) {
-                    base_case(q + qo, ql, t + to, tl, b, &wpos);
+                    base_case(q + qo, ql, t + to, tl, b, &wpos, direct && ql == n && tl == m);
                     continue;
                 }
                 const uint32_t lw = tl / 2, rw = tl - lw;
@@ -748,6 +899,16 @@ struct AlnWarp {
                 if (sp + 2 > 120) {
                     fail(kAlnInternal);
                     break;
+                }
+                const uint32_t qa_n = ul, qb_n = ql - ul;
+                auto is_leaf = [](uint32_t qn, uint32_t tn) {
+                    return 20ull * ((qn + 63) / 64) * tn + 8ull * tn < 1024ull * 1024ull;  // edlib.cpp:1155-1157
+                };
+                if (qa_n > 0 && qb_n > 0 && lw > 0 && rw > 0 && is_leaf(qa_n, lw) && is_leaf(qb_n, rw) &&
+                    band_span(qa_n, lw, ls) <= 16 && band_span(qb_n, rw, rs) <= 16) {
+                    /* both children are base cases with narrow bands: fill them side by side, then walk right, left */
+                    leaf_pair(q + qo, qa_n, t + to, lw, ls, q + qo + ul, qb_n, t + to + lw, rw, rs, &wpos);
+                    continue;
                 }
                 push(qo, ul, to, lw, ls);
                 push(qo + ul, ql - ul, to + lw, rw, rs);  // popped first: operations are written backwards

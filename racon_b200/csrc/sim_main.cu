@@ -130,6 +130,8 @@ int rp_sim_aln_bp(uint32_t n_pairs, const uint8_t* bases, const uint32_t* q_off,
     return 0;
 }
 
+unsigned long rp_sim_leaf_pairs() { return rp::g_sim_leaf_pairs; }
+
 /* packing only (host-side cost of rp_poa_add_window): returns number of GPU windows packed */
 int rp_sim_pack_only(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
                      const uint8_t* seq_has_qual, const uint32_t* seq_begin, const uint32_t* seq_end,

@@ -39,10 +39,14 @@ def test_sim_aln_traceback_regime(n, err, count):
     _check([_pair(rng, n, err, skew=rng.choice([0.0, 0.2])) for _ in range(count)])
 
 
-@pytest.mark.parametrize("n,err", [(2500, 0.12), (3500, 0.05), (3000, 0.3)])
+@pytest.mark.parametrize("n,err", [(2500, 0.12), (3500, 0.05), (3000, 0.3), (5600, 0.1)])
 def test_sim_aln_hirschberg_regime(n, err):
     rng = np.random.default_rng(n + 7)
+    lib = simlib.lib()
+    lib.rp_sim_leaf_pairs.restype = __import__("ctypes").c_ulong
+    before = lib.rp_sim_leaf_pairs()
     _check([_pair(rng, n, err, skew=rng.choice([0.0, 0.15]))])
+    assert lib.rp_sim_leaf_pairs() > before   # sibling leaves were filled side by side (leaf_pair)
 
 
 def test_sim_aln_band_growth_multi_round():
