@@ -196,6 +196,18 @@ void BatchAligner::reset() {
     rp_aln_reset(aln_);
 }
 
+std::string format_fasta(const std::string& target_name, const PolishedSequence& s) {
+    std::string out;
+    out.reserve(target_name.size() + s.tags.size() + s.data.size() + 3);
+    out += '>';
+    out += target_name;
+    out += s.tags;
+    out += '\n';
+    out += s.data;
+    out += '\n';
+    return out;
+}
+
 /* ---- Polisher ---- */
 Polisher::Polisher(std::vector<SequenceView> sequences, uint64_t targets_size, WindowType window_type,
                    bool fragment_correction, uint32_t window_length, double quality_threshold, bool trim, int8_t match,
@@ -525,6 +537,15 @@ extern "C" uint64_t rp_mirror_polisher_polished(void* hv, uint32_t i, uint64_t* 
 }
 
 extern "C" void rp_mirror_polisher_close(void* hv) { delete static_cast<PolHandle*>(hv); }
+
+/* host-only: one FASTA record; returns its length (out may be NULL to size it) */
+extern "C" uint64_t rp_mirror_format_fasta(const char* name, const char* tags, const char* data, uint64_t data_len,
+                                           char* out, uint64_t cap) {
+    racon_b200::PolishedSequence s{0, tags, std::string(data, data_len)};
+    const std::string r = racon_b200::format_fasta(name, s);
+    if (out && r.size() <= cap) std::memcpy(out, r.data(), r.size());
+    return r.size();
+}
 
 /* Test hook: CUDAPolisher::find_overlap_breaking_points' batch loop (cudapolisher.cpp:100-213) over flat pairs:
  * fill a batch until addOverlap refuses, alignAll, generate_cigar_strings, reset, continue.  out: NUL-terminated

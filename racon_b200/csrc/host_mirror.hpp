@@ -155,6 +155,9 @@ struct PolishedSequence {
     std::string data;
 };
 
+/* One FASTA record as racon's main prints a polished sequence (src/main.cpp:159-161): ">name tags\ndata\n". */
+std::string format_fasta(const std::string& target_name, const PolishedSequence& s);
+
 class Polisher {
 public:
     /* sequences: the targets first (targets_size of them), then the reads — the order racon::Polisher::sequences_ has */

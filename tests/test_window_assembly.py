@@ -43,3 +43,21 @@ def test_windows_from_reference_breaking_points_fragment_correction():
         assert np.array_equal(got[k][:ns], ref[k]), k
     assert np.array_equal(got["seq_off"][:ns + 1], ref["seq_off"])
     assert np.array_equal(got["bases"][:nb], ref["bases"]) and np.array_equal(got["quals"][:nb], ref["quals"])
+
+
+def test_fasta_record_format_reproduces_racon_stdout():
+    """racon_b200::format_fasta on the reference's polished lambda contig + tags == racon's stdout (golden md5)."""
+    import ctypes as C
+    import hashlib
+    from racon_b200 import api
+    lib = api.load()
+    lib.rp_mirror_format_fasta.restype = C.c_uint64
+    lib.rp_mirror_format_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    ref = np.load(os.path.join(GOLD, "lambda_windows.npz"))
+    full = ref["polished_name"].tobytes()
+    cut = full.index(b" LN:i:")
+    name, tags, data = full[:cut], full[cut:], ref["polished"].tobytes()
+    n = lib.rp_mirror_format_fasta(name, tags, data, len(data), None, 0)
+    buf = C.create_string_buffer(n)
+    assert lib.rp_mirror_format_fasta(name, tags, data, len(data), buf, n) == n
+    assert hashlib.md5(buf.raw[:n]).hexdigest() == "b0e2a2788440a4982e544e2e9b3bf378"
