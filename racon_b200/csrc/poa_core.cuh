@@ -514,6 +514,22 @@ struct PoaWarp {
         }
     }
 
+    /* True iff no cell of the finished matrix can have left the range int16 arithmetic is exact in.  Every cell
+     * satisfies H[i][j] >= H[i][0] + j*g (the horizontal move is always a candidate), column 0 falls by exactly |g|
+     * per level along a shortest path (so it cannot jump over the limit unnoticed), and the largest value is bounded
+     * by match * min(rows, columns), checked by the caller.  Limit: spoa's own margin, -32768 + 1024. */
+    RP_DEV bool matrix_in_range(uint32_t nrows, uint32_t len, uint32_t lpa) {
+        int32_t mn = 0;
+        const uint32_t e0 = perm(0);
+        for (uint32_t i = 1 + lane; i <= nrows; i += 32) {
+            const int32_t v = H[static_cast<uint64_t>(i) * lpa + e0];
+            mn = v < mn ? v : mn;
+        }
+        mn = -warp_incl_max(-mn);
+        mn = shfl(mn, 31);
+        return mn + static_cast<int32_t>(len) * P->gap >= -32768 + 1024;
+    }
+
     RP_DEV void dp(const uint8_t* seq, uint32_t nrows, uint32_t len, uint32_t lpa, uint32_t ring_rows,
                    uint32_t* best_row, int32_t* best_score, uint32_t* n_best) {
         /* Row-synchronous: the whole warp computes one row (512-column chunk) at a time; lane l owns columns
@@ -1464,9 +1480,18 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
             if (W.status != kWinOk) break;
             nrows = W.build_dp_order_subgraph();
         }
+        /* spoa picks its int32 engine from a worst-case bound over ALL nodes of the graph (fits_int16).  That bound
+         * is far from what a real matrix holds (column 0 only falls by |g| per level of graph DEPTH), and exact
+         * arithmetic gives the same answer in either width, so a window that fails the bound is still computed in
+         * int16 and the finished matrix is checked for having stayed in range (matrix_in_range). */
+        bool verify_range = false;
         if (!fits_int16(P.match, P.gap, len, nrows)) {
-            W.fail(kWinNeedsInt32);
-            break;
+            const int64_t short_side = static_cast<int64_t>(len) + 8 < nrows ? static_cast<int64_t>(len) + 8 : nrows;
+            if (P.gap < -kMaxGapInt16 || static_cast<int64_t>(P.match) * short_side > 32767 - 1024) {
+                W.fail(kWinNeedsInt32);
+                break;
+            }
+            verify_range = true;
         }
         uint32_t lpa = (len + 1 + kChunkCols - 1) / kChunkCols * kChunkCols;
         /* shared memory split: profile rows first, the rest is the ring of recent DP rows */
@@ -1486,6 +1511,10 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         uint32_t best_row, n_best;
         int32_t best;
         W.dp(seq, nrows, len, lpa, ring_rows, &best_row, &best, &n_best);
+        if (verify_range && !W.matrix_in_range(nrows, len, lpa)) {
+            W.fail(kWinNeedsInt32);
+            break;
+        }
         if (n_best > 1) {
             best_row = W.resolve_sink_tie(nrows, len, lpa, best, sub);
             if (W.status != kWinOk) break;

@@ -176,3 +176,21 @@ def test_gpu_batch_object_protocol():
     info = b.info()
     assert info["launches"] >= 2 and info["workers"] >= 32
     b.close()
+
+
+def test_gpu_windows_beyond_spoa_int16_bound():
+    """Scores for which spoa's worst-case bound selects its int32 engine (steep gap; or w=1000 with g=-8 at depth 40):
+    computed in int16 with the finished matrix verified in range — results equal the oracle's (int32 throughout);
+    a matrix that really leaves int16 is reported as RP_WIN_NEEDS_INT32."""
+    from racon_b200 import api
+    ws = util.make_set(21, 24, wlen=200, depth=16, err=0.12, partial_frac=0.3, with_qual=True)
+    cons, pol, st = api.consensus(ws, match=3, mismatch=-5, gap=-60, window_length=200)
+    ora, opol, _ = ob.oracle_consensus(ws, 3, -5, -60, window_length=200, threads=8)
+    assert (st == 0).all() and cons == ora and (pol == opol).all()
+    big = util.make_set(25, 6, wlen=1000, depth=40, err=0.12)
+    cons, pol, st = api.consensus(big, match=5, mismatch=-4, gap=-8, window_length=1000)
+    ora, opol, _ = ob.oracle_consensus(big, 5, -4, -8, window_length=1000, threads=8)
+    assert (st == 0).all() and cons == ora and (pol == opol).all()
+    bad = util.make_set(23, 4, wlen=600, depth=5, err=0.1)
+    cons, pol, st = api.consensus(bad, match=3, mismatch=-5, gap=-64, window_length=600)
+    assert (st == 4).all() and not pol.any()

@@ -141,3 +141,35 @@ def test_sim_malformed_windows_are_rejected_not_crashed():
                 [(bb, None, 0, 0), (bb, None, 0, 25), (bb, None, 0, 19), (bb, None, 0, 19)]):     # end > backbone
         with pytest.raises(RuntimeError):
             simlib.sim_consensus(windows.from_lists([bad]))
+
+
+def _spoa_would_use_int32(m, g, length, nodes):
+    """spoa's engine choice (alignment_engine.cpp:101-110, simd impl :699-745)"""
+    i, j = length + 8, nodes
+    worst = min(-(m * min(i, j) + g * abs(i - j)), g * i + g * j)
+    return worst < -32768 + 1024
+
+
+def test_sim_windows_beyond_spoa_int16_bound_are_computed_exactly():
+    """A steep gap penalty makes spoa's worst-case bound fail (it would switch to its int32 engine) although the real
+    matrix stays far inside int16: such windows are computed in int16 and verified on the finished matrix — same
+    result as the oracle (which is int32 throughout), no RP_WIN_NEEDS_INT32."""
+    ws = util.make_set(21, 5, wlen=200, depth=16, err=0.12, partial_frac=0.3, with_qual=True)
+    scores = (3, -5, -60)
+    assert _spoa_would_use_int32(3, -60, 200, 500)
+    _check(ws, scores=scores)
+    ws2 = util.make_set(22, 3, wlen=250, depth=10, err=0.2)
+    _check(ws2, scores=(5, -4, -40))
+    if ob.have_ref():   # the unmodified spoa (its int32 engine here) agrees with both
+        assert ob.ref_consensus(ws, 3, -5, -60)[0] == simlib.sim_consensus(ws, 3, -5, -60)[0]
+        assert ob.ref_consensus(ws2, 5, -4, -40)[0] == simlib.sim_consensus(ws2, 5, -4, -40)[0]
+
+
+def test_sim_windows_whose_matrix_leaves_int16_are_reported():
+    """gap = -64 at 600 columns: column 0 alone reaches -38 000, so the range check must refuse the window."""
+    ws = util.make_set(23, 2, wlen=600, depth=5, err=0.1)
+    _, pol, st, _, _ = simlib.sim_consensus(ws, 3, -5, -64)
+    assert (st == 4).all() and not pol.any()     # RP_WIN_NEEDS_INT32
+    # and a gap beyond the packed-int16 design limit is refused up front
+    _, pol, st, _, _ = simlib.sim_consensus(util.make_set(24, 2, wlen=100, depth=5, err=0.1), 3, -5, -100)
+    assert (st == 4).all() and not pol.any()
