@@ -62,6 +62,28 @@ def test_sim_bp_device_code_vs_oracle_and_reference(lam):
         assert np.array_equal(bp, lam.expected_bp(k)), k
 
 
+def test_sim_bp_window_boundary_sweep():
+    """Tiny windows (7 bases) and every alignment of overlap start / end against the window grid, with indel-rich
+    pairs: device breaking points == oracle walk of the same CIGAR."""
+    from tests import simlib
+    rng = np.random.default_rng(8)
+    wl = 7
+    cases = []
+    for t_begin in range(0, 15):
+        n = int(rng.integers(1, 40))
+        t = bytes(util.BASES[i] for i in rng.integers(4, size=n))
+        q = util.mutate(rng, t, 0.35) or b"A"
+        cases.append((q, t, t_begin, int(rng.integers(0, 50))))
+    for n in (7, 14, 21):     # ends exactly on the grid
+        t = bytes(util.BASES[i] for i in rng.integers(4, size=n))
+        cases.append((util.mutate(rng, t, 0.2) or b"C", t, 7, 3))
+        cases.append((util.mutate(rng, t, 0.2) or b"C", t, 0, 0))
+    got, st = simlib.sim_align_bp(cases, wl)
+    assert (st == 0).all()
+    for (q, t, tb, qs), (cig, _, bp) in zip(cases, got):
+        assert np.array_equal(bp, ob.oracle_breaking_points(cig, tb, tb + len(t), qs, wl)), (tb, len(t), cig)
+
+
 @pytest.mark.gpu
 def test_gpu_bp_lambda(lam):
     """Real overlaps end to end on the device: CIGAR identical to edlib's, breaking points identical to the

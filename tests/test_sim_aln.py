@@ -65,3 +65,14 @@ def test_sim_aln_wide_alphabet():
     _check([(q, t)])
     got, st = simlib.sim_align([(bytes(range(65, 85)) * 4, bytes(range(65, 85)) * 4)])
     assert st[0] == 2 and got[0][0] == ""
+
+
+def test_sim_aln_short_query_long_target_boundary_splits():
+    """A 150-base query against an 8 kb target: Hirschberg regime (the 1 MiB rule depends on the target length) with
+    split rows at the matrix boundary (r = -1 / r = qlen-1, edlib.cpp:1304-1320) and empty children."""
+    rng = np.random.default_rng(123)
+    t = bytes(util.BASES[i] for i in rng.integers(4, size=8000))
+    for start in (0, 3900, 7850):
+        q = util.mutate(rng, t[start:start + 150], 0.1)
+        _check([(q, t)])
+    _check([(b"ACGT" * 30, b"T" * 9000), (b"A", t)])
