@@ -26,6 +26,16 @@ def test_bp_oracle_pinned_on_lambda(lam):
         assert np.array_equal(got, lam.expected_bp(k)), k
 
 
+def test_bp_oracle_pinned_on_lambda_fragment_correction():
+    """Same pin on the 7 780 all-vs-all overlaps (both strands) of the -f configuration (every 4th with the unmodified
+    edlib, every 200th with its restatement)."""
+    lam = LambdaOverlaps("lambda_frag_overlaps.npz")
+    for k in range(0, lam.n_overlaps(), 4 if ob.have_ref() else 200):
+        q, t, t_begin, t_end, q_start = lam.spans(k)
+        got = ob.oracle_breaking_points(_cigar(q, t), t_begin, t_end, q_start, lam.window_length)
+        assert np.array_equal(got, lam.expected_bp(k)), k
+
+
 def test_bp_oracle_small_cases():
     # one window, all matches: first match (t_begin, q_start), one past last match
     assert ob.oracle_breaking_points("10M", 0, 10, 0, 500).tolist() == [[0, 0], [10, 10]]
