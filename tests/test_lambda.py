@@ -121,3 +121,64 @@ def test_gpu_fragment_correction_windows():
     ws, ref = load_frag()
     cons, pol, st = api.consensus(ws, 1, -1, -1)
     assert (st == 0).all() and cons == ref
+
+
+# ---- two more of the reference's goldens (tests/golden/make_lambda_more.py) -----------------------------------
+def load_scores3():
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lambda_windows_scores3.npz"))
+    off = np.concatenate([[0], np.cumsum(z["cons_len"].astype(np.int64))])
+    return [z["cons_flat"][off[i]:off[i + 1]].tobytes() for i in range(len(z["cons_len"]))]
+
+
+def load_w1000():
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lambda_w1000_windows.npz"))
+    ws = windows.WindowSet(bases=z["bases"], quals=z["quals"], seq_off=z["seq_off"], seq_has_qual=z["seq_has_qual"],
+                           seq_begin=z["seq_begin"], seq_end=z["seq_end"], win_first=z["win_first"],
+                           win_type=z["win_type"])
+    off = np.concatenate([[0], np.cumsum(z["cons_len"].astype(np.int64))])
+    return ws, [z["cons_flat"][off[i]:off[i + 1]].tobytes() for i in range(len(z["cons_len"]))], z["polished"].tobytes()
+
+
+def test_oracle_on_real_windows_edit_distance_scores():
+    """1/-1/-1 on the w=500 windows: the reference run behind test/racon_test.cpp:202-223 (golden 1321)."""
+    ws, _, _, _ = load()
+    cons, _, _ = ob.oracle_consensus(ws, 1, -1, -1, threads=8)
+    assert cons == load_scores3()
+
+
+def test_oracle_on_real_larger_windows():
+    """w=1000, 5/-4/-8: the reference run behind test/racon_test.cpp:179-200 (golden 1289).  Graphs of ~2 700 nodes
+    with g=-8: several of these alignments are beyond spoa's worst-case int16 bound (its int32 engine)."""
+    ws, ref, polished = load_w1000()
+    assert ws.n_windows == 48 and b"".join(ref) == polished
+    cons, _, _ = ob.oracle_consensus(ws, 5, -4, -8, window_length=1000, threads=8)
+    assert cons == ref
+
+
+def test_sim_on_a_real_larger_window():
+    """Device code (warp simulation) on the shallowest real w=1000 window that is polished."""
+    from tests import simlib
+    ws, ref, _ = load_w1000()
+    depth = np.diff(ws.win_first.astype(np.int64))
+    w = int(np.argmin(np.where(depth >= 5, depth, 10 ** 6)))
+    cons, pol, st, _, _ = simlib.sim_consensus(ws.subset([w]), 5, -4, -8, nmax=6 * 1000 + 64, lmax=2 * 1000 + 23)
+    assert (st == 0).all() and cons == [ref[w]]
+
+
+@pytest.mark.gpu
+def test_gpu_real_windows_edit_distance_scores():
+    from racon_b200 import api
+    ws, _, _, _ = load()
+    cons, pol, st = api.consensus(ws, 1, -1, -1)
+    assert (st == 0).all() and cons == load_scores3()
+
+
+@pytest.mark.gpu
+def test_gpu_real_larger_windows():
+    from racon_b200 import api
+    ws, ref, polished = load_w1000()
+    cons, pol, st = api.consensus(ws, 5, -4, -8, window_length=1000)
+    assert (st == 0).all(), st
+    bad = [w for w in range(ws.n_windows) if cons[w] != ref[w]]
+    assert not bad, "windows differ: %s" % bad[:8]
+    assert b"".join(cons) == polished
