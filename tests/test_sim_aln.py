@@ -76,3 +76,12 @@ def test_sim_aln_short_query_long_target_boundary_splits():
         q = util.mutate(rng, t[start:start + 150], 0.1)
         _check([(q, t)])
     _check([(b"ACGT" * 30, b"T" * 9000), (b"A", t)])
+
+
+def test_sim_aln_stored_distance_pass_with_k_doubling():
+    """A pair below the 1 MiB rule whose distance exceeds the first threshold: the bit-vectors are stored during the
+    distance pass, and the pass is repeated (and re-stored) with doubled k until it succeeds."""
+    rng = np.random.default_rng(77)
+    t = bytes(util.BASES[i] for i in rng.integers(4, size=5000))
+    q = util.mutate(rng, t[2000:2064], 0.1)
+    _check([(q, t), (b"ACGTACGTAC", t[:4000])])
