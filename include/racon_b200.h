@@ -45,7 +45,8 @@ enum {
     RP_WIN_SEQ_TOO_LONG = 5,
     RP_WIN_STACK_LIMIT = 6,
     RP_WIN_ALPHABET_LIMIT = 7,
-    RP_WIN_INTERNAL = 8
+    RP_WIN_INTERNAL = 8,
+    RP_WIN_MATRIX_LIMIT = 9      /* score matrix larger than the per-window scratch even in the escalation pass */
 };
 
 enum { RP_WINDOW_NGS = 0, RP_WINDOW_TGS = 1 }; /* racon::WindowType, src/window.hpp:20-23 */
@@ -115,6 +116,11 @@ rp_status rp_poa_set_stream(rp_poa* p, void* cuda_stream);   /* use the caller's
  * [7] predecessor cells sum (L+1)*E (E = sum over rows of max(1, in-degree)) — SURVEY.md §8(d) byte model */
 rp_status rp_poa_info(rp_poa* p, uint64_t info[8]);
 rp_status rp_poa_enable_counters(rp_poa* p, int on);
+/* racon -b / --cuda-banded-alignment (createCUDABatch's `banded`, cudabatch.cpp:56-59): after a run,
+ * info[0] = 1 when the object is banded, [1] alignments tried inside the band, [2] alignments whose band result
+ * was refused by the device-side check and that were redone with the full matrix on the device, [3] band width
+ * in columns.  Banded and unbanded objects return identical results (tests/test_gpu_poa.py). */
+rp_status rp_poa_band_info(rp_poa* p, uint64_t info[4]);
 
 /* ------------------------------------------------------------------------------------------------
  * Pre-alignment batch — replaces racon::CUDABatchAligner (src/cuda/cudaaligner.hpp:21-92) and the

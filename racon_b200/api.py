@@ -70,6 +70,8 @@ def load(build_if_missing=True):
     lib.rp_poa_info.argtypes = [vp, vp]
     lib.rp_poa_enable_counters.restype = C.c_int32
     lib.rp_poa_enable_counters.argtypes = [vp, C.c_int]
+    lib.rp_poa_band_info.restype = C.c_int32
+    lib.rp_poa_band_info.argtypes = [vp, vp]
     _bind_aln(lib, C, vp, u32)
     if hasattr(lib, "rp_mirror_align"):
         lib.rp_mirror_align.restype = C.c_int
@@ -202,6 +204,13 @@ class PoaBatch:
         keys = ["launches", "h2d_bytes", "d2h_bytes", "workers", "scratch_bytes_per_worker", "alignments",
                 "dp_cells", "pred_cells"]
         return dict(zip(keys, [int(v) for v in a]))
+
+    def band_info(self):
+        """racon -b bookkeeping of the last run: alignments tried inside the band / redone with the full matrix."""
+        a = (C.c_uint64 * 4)()
+        _check(self.lib, self.lib.rp_poa_band_info(self.h, a), "rp_poa_band_info")
+        return {"banded": bool(a[0]), "band_alignments": int(a[1]), "band_redone_full": int(a[2]),
+                "band_width": int(a[3])}
 
     def fetch_all(self, stride):
         n = self.size()
@@ -444,11 +453,12 @@ class MirrorPolisher:
 
 
 def consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=500, device=0, want_coverage=False,
-              mem_bytes=0):
+              mem_bytes=0, banded=False, band_stats=None):
     """Convenience: whole WindowSet through PoaBatch (multiple batches if needed).
-    Returns (consensus list, polished bool array, status uint32 array[, coverages])."""
+    Returns (consensus list, polished bool array, status uint32 array[, coverages]).
+    band_stats: optional dict that receives the summed rp_poa_band_info counters."""
     batch = PoaBatch(device=device, mem_bytes=mem_bytes, match=match, mismatch=mismatch, gap=gap,
-                     window_length=window_length)
+                     window_length=window_length, banded=banded)
     n = ws.n_windows
     lens_in = np.diff(ws.seq_off.astype(np.int64))
     stride = int(2 * (lens_in.max() if len(lens_in) else 1) + 64)
@@ -463,6 +473,10 @@ def consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=500, de
             batch.run()
             batch.sync()
             out, lens, p, s = batch.fetch_all(stride)
+            if band_stats is not None:
+                for k, v in batch.band_info().items():
+                    band_stats[k] = v if k in ("banded", "band_width") else band_stats.get(k, 0) + v
+                band_stats["batches"] = band_stats.get("batches", 0) + 1
             for i in range(took):
                 cons.append(out[i, :lens[i]].tobytes())
                 if want_coverage:

@@ -34,7 +34,8 @@
 namespace rp {
 
 constexpr uint16_t kNone = 0xffffu;
-constexpr int kChunkCols = 512;          // columns per register-resident row chunk (32 lanes x 16)
+constexpr int kChunkCols = 512;          // padding unit of the row length limit (the widest chunk: 32 lanes x 16)
+constexpr int32_t kBandFloor = -32768 + 1024;   // banded rows: "minus infinity" of excluded cells = spoa's int16 legal minimum
 constexpr int32_t kNegDiag = -32640;     // "column -1" sentinel: + any int8 profile value stays >= INT16_MIN and
                                          // below every legal score (legal >= INT16_MIN + 1024, the int16 criterion)
 constexpr int32_t kNeg32 = -(1 << 28);
@@ -51,21 +52,23 @@ enum : uint32_t {
     kWinStackLimit = 6,
     kWinAlphabetLimit = 7,
     kWinInternal = 8,
+    kWinMatrixLimit = 9,   // score matrix larger than the per-window scratch (re-run by the escalation pass)
 };
 
 struct PoaLimits {
     uint32_t nmax;   // max graph nodes per window
     uint32_t lmax;   // max layer length
-    uint32_t lp;     // padded row length in int16 cells: multiple of kChunkCols, >= lmax + 1
+    uint32_t lp;     // padded row length in int16 cells: multiple of kCC, >= lmax + 1
     uint32_t ki;     // in-edge slots per node
     uint32_t ka;     // aligned-node slots per node
     uint32_t stack_cap;
+    uint32_t hcap;   // int16 cells of score-matrix scratch per window ((rows + 1) x padded row length must fit)
 };
 
 struct SlotLayout {
     uint64_t code, flags, in_cnt, al_cnt, cov, in_tail, in_w, al, order_a, order_b, rank_of, dp_order, dp_rank,
-        rec, pred_ovf, H, aln, cur, wts_unused, member, has_out_sub, score, cpred, sorder, srank, marks, stack,
-        newlist, ccarry, bytes;
+        rec, pred_ovf, H, aln, cur, member, has_out_sub, score, cpred, sorder, srank, marks, stack,
+        newlist, ccarry, bpos, bs, bytes;
 };
 
 RP_HD uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
@@ -94,10 +97,9 @@ RP_HD SlotLayout make_layout(const PoaLimits& L) {
     s.dp_rank = take(n * 2);
     s.rec = take((n + 1 + 160) * 16);
     s.pred_ovf = take((n + 1) * L.ki * 2);
-    s.H = take((n + 1) * static_cast<uint64_t>(L.lp) * 2);
+    s.H = take(static_cast<uint64_t>(L.hcap) * 2 + 64);
     s.aln = take((static_cast<uint64_t>(L.lmax) + 1) * 2);
     s.cur = take((static_cast<uint64_t>(L.lmax) + 1) * 2);
-    s.wts_unused = o;
     s.member = take(n);
     s.has_out_sub = take(n);
     s.score = take(n * 8);
@@ -108,6 +110,8 @@ RP_HD SlotLayout make_layout(const PoaLimits& L) {
     s.stack = take(static_cast<uint64_t>(L.stack_cap) * 2);
     s.newlist = take((static_cast<uint64_t>(L.lmax) + 1) * 4);
     s.ccarry = take((n + 2) * 2 * 2);
+    s.bpos = take(n * 2);
+    s.bs = take(n + 2 + 64);
     s.bytes = align_up(o, 4096);
     return s;
 }
@@ -140,9 +144,13 @@ struct PoaParams {
     uint8_t* scratch;
     PoaLimits lim;
     SlotLayout lay;
-    uint32_t smem_per_warp;       // bytes of shared memory owned by each warp
-    uint32_t tile_rows;           // traceback tile height in ranks (0 = default 96)
+    uint32_t smem_per_group;      // bytes of shared memory owned by each lane group (= one window in flight)
+    uint32_t tile_rows;           // traceback tile height in ranks (0 = as many as fit, at most 96)
     uint32_t debug_flags;         // tests only: bit0 = use the HBM-resident variants of the order DFS / bundle
+    uint32_t banded;              // 1: every alignment is first tried inside a diagonal band of 16*G columns
+                                  // (racon -b); a band result that cannot be trusted is redone with the full matrix
+    uint32_t band_margin;         // columns the traceback must keep from a cut band edge to be trusted
+    unsigned long long* band_stats;  // [0] alignments tried in the band, [1] redone with the full matrix (may be null)
 };
 
 /* Row layout.  A lane owns 16 consecutive columns; inside that 32-byte block register r (0..7) packs
@@ -175,8 +183,9 @@ struct alignas(16) U4 {
     uint32_t x, y, z, w;
 };
 
-RP_DEV Row8 load_row_smem(const int16_t* row, uint32_t chunk, int lane) {
-    uint32_t q0 = chunk * 64u + 2u * static_cast<uint32_t>(lane);
+/* A lane's 16 columns = two 16-byte granules 2*lane, 2*lane+1 of the row (chunk or band) it belongs to */
+RP_DEV Row8 load_row_smem(const int16_t* row, int lane) {
+    uint32_t q0 = 2u * static_cast<uint32_t>(lane);
     uint32_t p0 = q0 ^ ((q0 >> 3) & 1u);
     uint32_t p1 = (q0 + 1u) ^ (((q0 + 1u) >> 3) & 1u);
     const U4* b = reinterpret_cast<const U4*>(row);
@@ -186,30 +195,43 @@ RP_DEV Row8 load_row_smem(const int16_t* row, uint32_t chunk, int lane) {
     o.r[4] = c.x; o.r[5] = c.y; o.r[6] = c.z; o.r[7] = c.w;
     return o;
 }
-RP_DEV void store_row_smem(int16_t* row, uint32_t chunk, int lane, const Row8& v) {
-    uint32_t q0 = chunk * 64u + 2u * static_cast<uint32_t>(lane);
+RP_DEV void store_row_smem(int16_t* row, int lane, const Row8& v) {
+    uint32_t q0 = 2u * static_cast<uint32_t>(lane);
     uint32_t p0 = q0 ^ ((q0 >> 3) & 1u);
     uint32_t p1 = (q0 + 1u) ^ (((q0 + 1u) >> 3) & 1u);
     U4* b = reinterpret_cast<U4*>(row);
     b[p0] = U4{v.r[0], v.r[1], v.r[2], v.r[3]};
     b[p1] = U4{v.r[4], v.r[5], v.r[6], v.r[7]};
 }
-RP_DEV Row8 load_row_gmem(const int16_t* row, uint32_t chunk, int lane) {
-    const U4* b = reinterpret_cast<const U4*>(row) + chunk * 64u + 2u * static_cast<uint32_t>(lane);
+RP_DEV Row8 load_row_gmem(const int16_t* row, int lane) {
+    const U4* b = reinterpret_cast<const U4*>(row) + 2u * static_cast<uint32_t>(lane);
     U4 a = b[0], c = b[1];
     Row8 o;
     o.r[0] = a.x; o.r[1] = a.y; o.r[2] = a.z; o.r[3] = a.w;
     o.r[4] = c.x; o.r[5] = c.y; o.r[6] = c.z; o.r[7] = c.w;
     return o;
 }
-RP_DEV void store_row_gmem(int16_t* row, uint32_t chunk, int lane, const Row8& v) {
-    U4* b = reinterpret_cast<U4*>(row) + chunk * 64u + 2u * static_cast<uint32_t>(lane);
+RP_DEV void store_row_gmem(int16_t* row, int lane, const Row8& v) {
+    U4* b = reinterpret_cast<U4*>(row) + 2u * static_cast<uint32_t>(lane);
     b[0] = U4{v.r[0], v.r[1], v.r[2], v.r[3]};
     b[1] = U4{v.r[4], v.r[5], v.r[6], v.r[7]};
 }
 
-/* One warp's view of its scratch slot + shared memory. All scalar members are warp-uniform. */
+/* One lane group's view of its scratch slot + shared memory (G lanes = one window; rp_warp.cuh "lane groups").
+ * All scalar members are group-uniform.  The collectives the code below calls unqualified (syncwarp, ballot, shfl,
+ * ...) are the member versions declared here: they span the G lanes of this group only. */
+template <int G>
 struct PoaWarp {
+    static constexpr uint32_t kCC = 16u * G;   // columns of a register-resident row chunk (or of the band)
+    static RP_DEV void syncwarp() { gsync<G>(); }
+    static RP_DEV uint32_t ballot(bool p) { return gballot<G>(p); }
+    template <typename T> static RP_DEV T shfl(T v, int src) { return gshfl<G, T>(v, src); }
+    template <typename T> static RP_DEV T shfl_up(T v, int d) { return gshfl_up<G, T>(v, d); }
+    template <typename T> static RP_DEV T shfl_down(T v, int d) { return gshfl_down<G, T>(v, d); }
+    static RP_DEV uint32_t warp_rank(bool p, uint32_t* total) { return grank<G>(p, total); }
+    static RP_DEV uint32_t warp_incl_sum(uint32_t v) { return gincl_sum<G>(v); }
+    static RP_DEV int32_t warp_incl_max(int32_t v) { return gincl_max<G>(v); }
+
     const PoaParams* P;
     int lane;
     /* graph (HBM) */
@@ -222,6 +244,8 @@ struct PoaWarp {
     int64_t* score;
     uint32_t* newlist;
     int16_t* ccarry;
+    uint16_t* bpos;      // per node: backbone coordinate it sits at (band centre line)
+    uint8_t* bs;         // per DP row: first 16-column block of the row's band
     /* shared memory */
     int16_t* ring;       // ring_rows x lp_a
     int16_t* prof;       // ncodes x lp_a
@@ -237,7 +261,7 @@ struct PoaWarp {
 
     RP_DEV void bind(const PoaParams* p, uint8_t* slot, uint8_t* sm, uint32_t sm_bytes) {
         P = p;
-        lane = lane_id();
+        lane = glane<G>();
         const SlotLayout& y = p->lay;
         code = slot + y.code;
         flags = slot + y.flags;
@@ -267,6 +291,8 @@ struct PoaWarp {
         stack = reinterpret_cast<uint16_t*>(slot + y.stack);
         newlist = reinterpret_cast<uint32_t*>(slot + y.newlist);
         ccarry = reinterpret_cast<int16_t*>(slot + y.ccarry);
+        bpos = reinterpret_cast<uint16_t*>(slot + y.bpos);
+        bs = slot + y.bs;
         smem = sm;
         smem_bytes = sm_bytes;
         ki = p->lim.ki;
@@ -287,7 +313,7 @@ struct PoaWarp {
 
     /* ---------------------------------------------------------------- backbone (graph.cpp:186-190, 93-110) */
     RP_DEV void init_backbone(const uint8_t* seq, const uint8_t* w, uint32_t len) {
-        for (uint32_t v = lane; v < len; v += 32) {
+        for (uint32_t v = lane; v < len; v += G) {
             code[v] = seq[v];
             al_cnt[v] = 0;
             flags[v] = (v + 1 < len) ? 1 : 0;
@@ -301,6 +327,7 @@ struct PoaWarp {
             }
             order[v + 1] = static_cast<uint16_t>(v);
             rank_of[v] = static_cast<uint16_t>(v + 1);
+            bpos[v] = static_cast<uint16_t>(v);
         }
         if (lane == 0) order[0] = kNone;
         N = len;
@@ -313,9 +340,10 @@ struct PoaWarp {
      * Serial (lane 0); only partial-span layers take this path. */
     RP_DEV void mark_subgraph(uint32_t begin, uint32_t end) {
         const uint32_t npad = (N + 15) & ~15u;
-        const bool staged = ki <= 31 && ka == 8 && 2 * npad + 512 <= smem_bytes && !(P->debug_flags & 1);
+        bool staged = ki <= 31 && ka == 8 && 2 * npad + 512 <= smem_bytes && !(P->debug_flags & 1);
+        if (staged && !mark_subgraph_staged(begin, end, npad)) staged = false;  // stack outgrew shared memory
         if (!staged) {  /* HBM-resident variant */
-            for (uint32_t v = lane; v < N; v += 32) member[v] = 0;
+            for (uint32_t v = lane; v < N; v += G) member[v] = 0;
             syncwarp();
             if (lane == 0) {
                 uint32_t sp = 0;
@@ -336,10 +364,13 @@ struct PoaWarp {
             }
             status = shfl(status, 0);
             syncwarp();
-            return;
         }
-        /* membership bytes, per-node degrees, the first two in-edge tails of every node and the stack live in
-         * shared memory: a node costs an HBM round trip only if it has more than two in-edges or aligned nodes */
+    }
+
+    /* membership bytes, per-node degrees, the first two in-edge tails of every node and the stack live in
+     * shared memory: a node costs an HBM round trip only if it has more than two in-edges or aligned nodes.
+     * Returns false (nothing decided) when the stack does not fit. */
+    RP_DEV bool mark_subgraph_staged(uint32_t begin, uint32_t end, uint32_t npad) {
         uint8_t* smb = smem;
         uint8_t* sme = smem + npad;
         const bool have_t2 = 6 * npad + 1024 <= smem_bytes;
@@ -347,12 +378,13 @@ struct PoaWarp {
         const uint32_t fixed = have_t2 ? 6 * npad : 2 * npad;
         uint16_t* sst = reinterpret_cast<uint16_t*>(smem + fixed);
         const uint32_t cap = (smem_bytes - fixed) / 2;
-        for (uint32_t v = lane; v < N; v += 32) {
+        for (uint32_t v = lane; v < N; v += G) {
             smb[v] = 0;
             sme[v] = static_cast<uint8_t>(in_cnt[v] | (al_cnt[v] << 5));
             if (have_t2) st2[v] = *reinterpret_cast<const uint32_t*>(in_tail + v * ki);
         }
         syncwarp();
+        uint32_t ovf = 0;
         if (lane == 0) {
             uint32_t sp = 0;
             sst[sp++] = static_cast<uint16_t>(end);
@@ -369,7 +401,7 @@ struct PoaWarp {
                     a_hi = a8.z | (static_cast<uint64_t>(a8.w) << 32);
                 }
                 if (sp + ni + na > cap) {
-                    fail(kWinStackLimit);
+                    ovf = 1;
                     break;
                 }
                 for (uint32_t k = 0; k < ni; ++k) {
@@ -383,16 +415,18 @@ struct PoaWarp {
                 smb[c] = 1;
             }
         }
-        status = shfl(status, 0);
+        ovf = shfl(ovf, 0);
         syncwarp();
-        for (uint32_t v = lane; v < N; v += 32) member[v] = smb[v];
+        if (ovf) return false;
+        for (uint32_t v = lane; v < N; v += G) member[v] = smb[v];
         syncwarp();
+        return true;
     }
 
     /* Compact DP order over the member nodes (rank order preserved). Returns number of DP rows. */
     RP_DEV uint32_t build_dp_order_subgraph() {
         uint32_t base = 0;
-        for (uint32_t r0 = 1; r0 <= N; r0 += 32) {
+        for (uint32_t r0 = 1; r0 <= N; r0 += G) {
             uint32_t r = r0 + lane;
             uint32_t v = r <= N ? order[r] : 0;
             bool in = r <= N && member[v];
@@ -404,10 +438,10 @@ struct PoaWarp {
             }
             base += tot;
         }
-        for (uint32_t v = lane; v < N; v += 32) has_out_sub[v] = 0;
+        for (uint32_t v = lane; v < N; v += G) has_out_sub[v] = 0;
         syncwarp();
         /* sinks of the subgraph: members without an out-edge to another member (graph.cpp:575-580) */
-        for (uint32_t v = lane; v < N; v += 32) {
+        for (uint32_t v = lane; v < N; v += G) {
             if (!member[v]) continue;
             uint32_t ni = in_cnt[v];
             for (uint32_t k = 0; k < ni; ++k) {
@@ -422,21 +456,27 @@ struct PoaWarp {
     /* ---------------------------------------------------------------- DP program (one 8-byte record per row)
      * byte0 code index, byte1 = npred(7 bits) | sink<<7, bytes2..7 = first three predecessor DP ranks
      * (0 = virtual root row).  Further predecessors spill to pred_ovf. */
-    RP_DEV uint32_t build_program(uint32_t nrows, bool sub) {
+    /* With `band`, also the first 16-column block bs[r] of every row's band: the band (16*G columns) is centred on
+     * the column the node's backbone coordinate maps to, (bpos - b0) * (len + 1) / span, and never moves left
+     * along the processing order. */
+    RP_DEV uint32_t build_program(uint32_t nrows, bool sub, bool band, uint32_t len, uint32_t b0, uint32_t span) {
         const uint16_t* ord = sub ? dp_order : order;
         const uint16_t* rk = sub ? dp_rank : rank_of;
         uint32_t pred_rows = 0;
+        const uint32_t nblk = (len + 16) >> 4;            // blocks holding columns 0..len
+        const int32_t smax = static_cast<int32_t>(nblk) - G;
+        int32_t brun = 0;
         /* The graph lives in HBM, so every level of the chain row -> node -> in-edges -> ranks costs a full
          * memory latency.  Rows are handled kU per lane at a time with all loads of one level issued together. */
         constexpr int kU = 4;
-        for (uint32_t r0 = 1; r0 <= nrows; r0 += 32 * kU) {
-            uint32_t r[kU], v[kU], ni[kU], cd[kU], fl[kU];
+        for (uint32_t r0 = 1; r0 <= nrows; r0 += G * kU) {
+            uint32_t r[kU], v[kU], ni[kU], cd[kU], fl[kU], bp[kU];
             uint64_t t4[kU];
             uint32_t pk[kU][3];
             bool use[kU][3];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                r[u] = r0 + u * 32 + lane;
+                r[u] = r0 + u * G + lane;
                 v[u] = r[u] <= nrows ? ord[r[u]] : ord[1];
             }
 #pragma unroll
@@ -445,6 +485,23 @@ struct PoaWarp {
                 cd[u] = code[v[u]];
                 fl[u] = sub ? has_out_sub[v[u]] : (flags[v[u]] & 1u);
                 t4[u] = *reinterpret_cast<const uint64_t*>(in_tail + v[u] * ki);  // first four in-edge tails
+                bp[u] = band ? bpos[v[u]] : 0u;
+            }
+            if (band) {
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    uint32_t x = bp[u] > b0 ? bp[u] - b0 : 0u;
+                    if (x >= span) x = span - 1;
+                    const int32_t cc = static_cast<int32_t>((x * (len + 1)) / span);
+                    int32_t t = (cc + 8) / 16 - G / 2;
+                    t = t > smax ? smax : t;
+                    t = t < 0 ? 0 : t;
+                    if (r[u] > nrows) t = 0;
+                    int32_t inc = warp_incl_max(t);
+                    inc = inc < brun ? brun : inc;
+                    if (r[u] <= nrows) bs[r[u]] = static_cast<uint8_t>(inc);
+                    brun = shfl(inc, G - 1);
+                }
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u)
@@ -489,7 +546,10 @@ struct PoaWarp {
                 pred_rows += np ? np : 1;
             }
         }
-        if (lane == 0) rec[0] = Rec{0, 0};
+        if (lane == 0) {
+            rec[0] = Rec{0, 0};
+            bs[0] = 0;
+        }
         syncwarp();
         return pred_rows;  // per-lane partial sum (only summed when the device counters are on)
     }
@@ -504,9 +564,9 @@ struct PoaWarp {
         int32_t m = P->match, x = P->mismatch;
         for (uint32_t k = 0; k < ncodes; ++k) {
             uint8_t c = static_cast<uint8_t>(alpha >> (8 * k));
-            int16_t* row = prof + k * kChunkCols;
-            for (uint32_t cc = lane; cc < kChunkCols; cc += 32) {
-                uint32_t col = ch * kChunkCols + cc;
+            int16_t* row = prof + k * kCC;
+            for (uint32_t cc = lane; cc < kCC; cc += G) {
+                uint32_t col = ch * kCC + cc;
                 int16_t v = static_cast<int16_t>(x);
                 if (col >= 1 && col <= len && seq[col - 1] == c) v = static_cast<int16_t>(m);
                 row[swz(cc)] = v;
@@ -521,12 +581,12 @@ struct PoaWarp {
     RP_DEV bool matrix_in_range(uint32_t nrows, uint32_t len, uint32_t lpa) {
         int32_t mn = 0;
         const uint32_t e0 = perm(0);
-        for (uint32_t i = 1 + lane; i <= nrows; i += 32) {
+        for (uint32_t i = 1 + lane; i <= nrows; i += G) {
             const int32_t v = H[static_cast<uint64_t>(i) * lpa + e0];
             mn = v < mn ? v : mn;
         }
         mn = -warp_incl_max(-mn);
-        mn = shfl(mn, 31);
+        mn = shfl(mn, G - 1);
         return mn + static_cast<int32_t>(len) * P->gap >= -32768 + 1024;
     }
 
@@ -538,7 +598,7 @@ struct PoaWarp {
          * chunk: the profile chunk and a ring of the last `ring_rows` rows. */
         const int32_t g = P->gap;
         const uint32_t g2 = pack16(g, g);
-        const uint32_t nch = lpa / kChunkCols;
+        const uint32_t nch = lpa / kCC;
         const int32_t negsafe = -32768 - 16 * g;  // see kMaxGapInt16
         uint32_t gb[8], gc[8];  // bridge / carry offsets per register
 #pragma unroll
@@ -546,8 +606,8 @@ struct PoaWarp {
             gb[r] = pack16(0, (r + 1) * g);
             gc[r] = pack16((r + 1) * g, (r + 9) * g);
         }
-        for (uint32_t col = lane; col < lpa; col += 32) H[perm(col)] = static_cast<int16_t>(static_cast<int32_t>(col) * g);
-        const uint32_t sink_ch = len / kChunkCols, sink_e = swz(len % kChunkCols);
+        for (uint32_t col = lane; col < lpa; col += G) H[perm(col)] = static_cast<int16_t>(static_cast<int32_t>(col) * g);
+        const uint32_t sink_ch = len / kCC, sink_e = swz(len % kCC);
         int32_t best = kNeg32;
         uint32_t bi = 0, nb = 0;
         int16_t* cc_prev = ccarry;        // last column of the previous chunk, per row (multi-chunk rows only)
@@ -555,16 +615,16 @@ struct PoaWarp {
         const uint32_t lanem = static_cast<uint32_t>(lane);
         for (uint32_t ch = 0; ch < nch; ++ch) {
             build_profile(seq, len, ch);
-            for (uint32_t c = lane; c < kChunkCols; c += 32)  // root row (rank 0) -> ring slot 0
-                ring[swz(c)] = static_cast<int16_t>(static_cast<int32_t>(ch * kChunkCols + c) * g);
+            for (uint32_t c = lane; c < kCC; c += G)  // root row (rank 0) -> ring slot 0
+                ring[swz(c)] = static_cast<int16_t>(static_cast<int32_t>(ch * kCC + c) * g);
             syncwarp();
             const bool multi = ch > 0;
             uint32_t rec_a_lo = 0, rec_a_hi = 0, rec_b_lo = 0, rec_b_hi = 0;
-            int16_t* hrow = H + static_cast<uint64_t>(ch) * kChunkCols;  // row i of this chunk = hrow + i*lpa
+            int16_t* hrow = H + static_cast<uint64_t>(ch) * kCC;  // row i of this chunk = hrow + i*lpa
             uint32_t myslot = 0;  // i % ring_rows, kept incrementally (any ring size, no division)
             for (uint32_t i = 1; i <= nrows; ++i) {
                 myslot = myslot + 1 == ring_rows ? 0u : myslot + 1;
-                const uint32_t ti = (i - 1) & 31u;
+                const uint32_t ti = (i - 1) & (G - 1);
                 if (ti == 0) {
                     Rec t = rec[i + lane];  // rec[] is padded
                     rec_a_lo = static_cast<uint32_t>(t.a);
@@ -576,7 +636,7 @@ struct PoaWarp {
                 const uint32_t cidx = lo & 0xff;
                 const uint32_t np = (lo >> 8) & 0x7f;
                 const bool sink = (lo >> 15) & 1;
-                const Row8 pf = load_row_smem(prof + cidx * kChunkCols, 0, lane);
+                const Row8 pf = load_row_smem(prof + cidx * kCC, lane);
                 /* max over predecessors distributes over both terms of the recurrence:
                  *   max_p(H[p][c-1] + s(c), H[p][c] + g) = max(max_p H[p][c-1] + s(c), max_p H[p][c] + g),
                  * so predecessor rows are first combined with a packed max (8 ops per extra predecessor) and the
@@ -587,9 +647,9 @@ struct PoaWarp {
                     const uint32_t dist = i - p;
                     if (dist < ring_rows) {  // warp-uniform
                         const uint32_t slot = myslot >= dist ? myslot - dist : myslot + ring_rows - dist;
-                        pr = load_row_smem(ring + slot * kChunkCols, 0, lane);
+                        pr = load_row_smem(ring + slot * kCC, lane);
                     } else
-                        pr = load_row_gmem(hrow + static_cast<uint64_t>(p) * lpa, 0, lane);
+                        pr = load_row_gmem(hrow + static_cast<uint64_t>(p) * lpa, lane);
                     if (multi) {
                         int32_t lv = cc_prev[p];
                         lvm = lv > lvm ? lv : lvm;
@@ -601,20 +661,22 @@ struct PoaWarp {
 #pragma unroll
                     for (int r = 0; r < 8; ++r) pm.r[r] = vmax_s16x2(pm.r[r], pr.r[r]);
                 };
-                if (np <= 1) {
-                    load_pred(np ? (lo >> 16) : 0u, pm);
-                } else {
+                /* the first predecessor is loaded by every group of the warp together; only the groups whose row has
+                 * more predecessors enter the nested part */
+                load_pred(np ? (lo >> 16) : 0u, pm);
+                if (np > 1) {
                     const uint32_t hi = shfl(rec_a_hi, ti);
-                    load_pred(lo >> 16, pm);
                     more(hi & 0xffff);
-                    if (np > 2) more(hi >> 16);
-                    if (np > 3) {
-                        const uint32_t blo = shfl(rec_b_lo, ti), bhi = shfl(rec_b_hi, ti);
-                        more(blo & 0xffff);
-                        if (np > 4) more(blo >> 16);
-                        if (np > 5) more(bhi & 0xffff);
-                        if (np > 6) more(bhi >> 16);
-                        for (uint32_t k = 7; k < np; ++k) more(pred_ovf[i * ki + k]);
+                    if (np > 2) {
+                        more(hi >> 16);
+                        if (np > 3) {
+                            const uint32_t blo = shfl(rec_b_lo, ti), bhi = shfl(rec_b_hi, ti);
+                            more(blo & 0xffff);
+                            if (np > 4) more(blo >> 16);
+                            if (np > 5) more(bhi & 0xffff);
+                            if (np > 6) more(bhi >> 16);
+                            for (uint32_t k = 7; k < np; ++k) more(pred_ovf[i * ki + k]);
+                        }
                     }
                 }
                 uint32_t acc[8];
@@ -642,7 +704,7 @@ struct PoaWarp {
                 int32_t t = hi16(acc[7]);
                 t = viaddmax_s32(lanem == 0 ? chunk_carry : kNeg32, 16 * g, t);
 #pragma unroll
-                for (int dd = 1; dd < 32; dd <<= 1) {
+                for (int dd = 1; dd < G; dd <<= 1) {
                     int32_t o = shfl_up(t, dd);
                     t = viaddmax_s32(lanem >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * 16 * g, t);
                 }
@@ -655,10 +717,10 @@ struct PoaWarp {
                 Row8 out;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) out.r[r] = acc[r];
-                int16_t* myrow_s = ring + myslot * kChunkCols;
-                store_row_smem(myrow_s, 0, lane, out);
-                store_row_gmem(hrow + static_cast<uint64_t>(i) * lpa, 0, lane, out);
-                if (nch > 1 && lanem == 31) cc_cur[i] = static_cast<int16_t>(hi16(acc[7]));
+                int16_t* myrow_s = ring + myslot * kCC;
+                store_row_smem(myrow_s, lane, out);
+                store_row_gmem(hrow + static_cast<uint64_t>(i) * lpa, lane, out);
+                if (nch > 1 && lanem == G - 1) cc_cur[i] = static_cast<int16_t>(hi16(acc[7]));
                 syncwarp();
                 if (sink && ch == sink_ch) {  // warp-uniform
                     int32_t sc = myrow_s[sink_e];
@@ -672,7 +734,7 @@ struct PoaWarp {
                 }
             }
             if (nch > 1) {
-                if (lane == 0) cc_cur[0] = static_cast<int16_t>((ch + 1) * kChunkCols * g - g);  // root row, last column
+                if (lane == 0) cc_cur[0] = static_cast<int16_t>((ch + 1) * kCC * g - g);  // root row, last column
                 int16_t* tmp = cc_prev;
                 cc_prev = cc_cur;
                 cc_cur = tmp;
@@ -685,11 +747,197 @@ struct PoaWarp {
         syncwarp();
     }
 
+    /* ---------------------------------------------------------------- banded DP (racon -b)
+     * Row i only computes the 16*G columns of its band, blocks [bs[i], bs[i] + G).  A 16-column block cb always
+     * lives in lane cb mod G — in registers, in the shared-memory ring and in the HBM copy (row pitch = band
+     * width) — so when the band slides right only the lane whose block left the band changes its columns, and a
+     * predecessor row lines up with the current row without any data movement.  Cells outside a row's band count
+     * as minus infinity (kBandFloor, also the floor of every stored cell, so excluded regions cannot wrap around
+     * int16): banded values are <= the full matrix's and equal to them on every cell of an optimal path that lies
+     * inside the band.  traceback<true> decides whether the result can be trusted. */
+    RP_DEV void build_profile_block(const uint8_t* seq, uint32_t len, uint32_t cb) {
+        const int32_t m = P->match, x = P->mismatch;
+        uint8_t ch[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const uint32_t col = cb * 16u + c;
+            ch[c] = (col >= 1 && col <= len) ? seq[col - 1] : 0;   // 0 never is a window character
+        }
+        for (uint32_t k = 0; k < ncodes; ++k) {
+            const uint8_t c = static_cast<uint8_t>(alpha >> (8 * k));
+            Row8 v;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v.r[r] = pack16(ch[r] == c ? m : x, ch[8 + r] == c ? m : x);
+            store_row_smem(prof + k * kCC, lane, v);
+        }
+    }
+
+    RP_DEV void dp_band(const uint8_t* seq, uint32_t nrows, uint32_t len, uint32_t ring_rows, uint32_t* best_row,
+                        int32_t* best_score, uint32_t* n_best) {
+        const int32_t g = P->gap;
+        const uint32_t g2 = pack16(g, g);
+        const int32_t negsafe = -32768 - 16 * g;
+        const uint32_t floor2 = pack16(kBandFloor, kBandFloor);
+        uint32_t gb[8], gc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            gb[r] = pack16(0, (r + 1) * g);
+            gc[r] = pack16((r + 1) * g, (r + 9) * g);
+        }
+        const uint32_t lanem = static_cast<uint32_t>(lane);
+        const uint32_t lane_left = (lanem + G - 1) & (G - 1);   // the lane that holds the block to the left
+        const uint32_t sink_blk = len >> 4;
+        const uint32_t sink_e = swz(((sink_blk & (G - 1)) << 4) | (len & 15u));
+        int32_t best = kNeg32;
+        uint32_t bi = 0, nb = 0;
+        /* rows with the same band start form a segment; predecessors from before the segment need a validity test */
+        uint32_t s_cur = 0xffffffffu, seg_i0 = 1, s_prev = 0, prev_i0 = 1;
+        uint32_t cb = 0, pos = 0;          // this lane's block and its position inside the band
+        uint32_t pcb = 0xffffffffu;        // block whose profile this lane's profile slot holds
+        uint32_t rec_a_lo = 0, rec_a_hi = 0, rec_b_lo = 0, rec_b_hi = 0, bsv = 0;
+        uint32_t myslot = 0;
+        syncwarp();
+        for (uint32_t i = 1; i <= nrows; ++i) {
+            myslot = myslot + 1 == ring_rows ? 0u : myslot + 1;
+            const uint32_t ti = (i - 1) & (G - 1);
+            if (ti == 0) {
+                Rec t = rec[i + lane];  // rec[] and bs[] are padded
+                rec_a_lo = static_cast<uint32_t>(t.a);
+                rec_a_hi = static_cast<uint32_t>(t.a >> 32);
+                rec_b_lo = static_cast<uint32_t>(t.b);
+                rec_b_hi = static_cast<uint32_t>(t.b >> 32);
+                bsv = bs[i + lane];
+            }
+            const uint32_t lo = shfl(rec_a_lo, ti);
+            const uint32_t s_i = shfl(bsv, ti);
+            if (s_i != s_cur) {  // group-uniform: the band slides
+                s_prev = s_cur;
+                prev_i0 = seg_i0;
+                s_cur = s_i;
+                seg_i0 = i;
+                pos = (lanem - s_cur) & (G - 1);
+                cb = s_cur + pos;
+                if (cb != pcb) {  // only the lanes whose block changed
+                    build_profile_block(seq, len, cb);
+                    pcb = cb;
+                }
+            }
+            const uint32_t cidx = lo & 0xff;
+            const uint32_t np = (lo >> 8) & 0x7f;
+            const bool sink = (lo >> 15) & 1;
+            const Row8 pf = load_row_smem(prof + cidx * kCC, lane);
+            Row8 pm;
+            auto load_pred = [&](uint32_t p, Row8& pr) {
+                if (p == 0) {  // virtual root row: H[0][j] = j * g
+                    const int32_t base = static_cast<int32_t>(cb * 16u) * g;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) pr.r[r] = pack16(base + r * g, base + (8 + r) * g);
+                    return;
+                }
+                const uint32_t dist = i - p;
+                if (dist < ring_rows) {  // group-uniform
+                    const uint32_t slot = myslot >= dist ? myslot - dist : myslot + ring_rows - dist;
+                    pr = load_row_smem(ring + slot * kCC, lane);
+                } else {
+                    pr = load_row_gmem(H + static_cast<uint64_t>(p) * kCC, lane);
+                }
+                if (p < seg_i0) {  // from an earlier segment: its band may not hold this lane's block
+                    const uint32_t sp = p >= prev_i0 ? s_prev : static_cast<uint32_t>(bs[p]);
+                    if (cb - sp >= G) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) pr.r[r] = floor2;
+                    }
+                }
+            };
+            auto more = [&](uint32_t p) {
+                Row8 pr;
+                load_pred(p, pr);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) pm.r[r] = vmax_s16x2(pm.r[r], pr.r[r]);
+            };
+            load_pred(np ? (lo >> 16) : 0u, pm);
+            if (np > 1) {
+                const uint32_t hi = shfl(rec_a_hi, ti);
+                more(hi & 0xffff);
+                if (np > 2) {
+                    more(hi >> 16);
+                    if (np > 3) {
+                        const uint32_t blo = shfl(rec_b_lo, ti), bhi = shfl(rec_b_hi, ti);
+                        more(blo & 0xffff);
+                        if (np > 4) more(blo >> 16);
+                        if (np > 5) more(bhi & 0xffff);
+                        if (np > 6) more(bhi >> 16);
+                        for (uint32_t k = 7; k < np; ++k) more(pred_ovf[i * ki + k]);
+                    }
+                }
+            }
+            uint32_t acc[8];
+            {
+                uint32_t left = shfl(pm.r[7], lane_left);  // hi half = last column of the block to the left
+                left = pos == 0 ? floor2 : left;           // first block of the band: nothing to its left
+                const uint32_t d0 = byte_perm(left, pm.r[7], 0x5432);
+                acc[0] = viaddmax_s16x2(pm.r[0], g2, viaddmax_s16x2(d0, pf.r[0], floor2));
+#pragma unroll
+                for (int r = 1; r < 8; ++r)
+                    acc[r] = viaddmax_s16x2(pm.r[r], g2, viaddmax_s16x2(pm.r[r - 1], pf.r[r], floor2));
+            }
+#pragma unroll
+            for (int r = 1; r < 8; ++r) acc[r] = viaddmax_s16x2(acc[r - 1], g2, acc[r]);
+            const uint32_t bridge = byte_perm(acc[7], 0x80008000u, 0x1076);  // lo = INT16_MIN, hi = acc[7].lo
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[r] = viaddmax_s16x2(bridge, gb[r], acc[r]);
+            /* max-plus scan of the lane totals in band order (the band starts at lane s_cur mod G) */
+            int32_t t = hi16(acc[7]);
+#pragma unroll
+            for (int dd = 1; dd < G; dd <<= 1) {
+                const int32_t o = shfl(t, (lanem - dd) & (G - 1));
+                t = viaddmax_s32(pos >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * 16 * g, t);
+            }
+            int32_t carry = shfl(t, lane_left);
+            carry = pos == 0 ? kNeg32 : carry;
+            carry = carry < negsafe ? negsafe : carry;
+            const uint32_t c2 = pack16(carry, carry);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[r] = viaddmax_s16x2(c2, gc[r], acc[r]);
+            Row8 out;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) out.r[r] = acc[r];
+            int16_t* myrow_s = ring + myslot * kCC;
+            store_row_smem(myrow_s, lane, out);
+            store_row_gmem(H + static_cast<uint64_t>(i) * kCC, lane, out);
+            syncwarp();
+            if (sink && sink_blk - s_cur < G) {  // group-uniform
+                const int32_t sc = myrow_s[sink_e];
+                if (sc > best) {
+                    best = sc;
+                    bi = i;
+                    nb = 1;
+                } else if (sc == best) {
+                    ++nb;
+                }
+            }
+        }
+        *best_row = bi;
+        *best_score = best;
+        *n_best = nb;
+        syncwarp();
+    }
+
+    /* H[r][c] of the last DP, whichever layout it used (full rows of pitch lpa, or band rows) */
+    template <bool BAND>
+    RP_DEV int32_t hcell(uint32_t lpa, uint32_t r, uint32_t c) const {
+        if (!BAND) return H[static_cast<uint64_t>(r) * lpa + perm(c)];
+        if (r == 0) return static_cast<int32_t>(c) * P->gap;
+        const uint32_t cbk = c >> 4;
+        if (cbk - bs[r] >= G) return kBandFloor;
+        return H[static_cast<uint64_t>(r) * kCC + ((cbk & (G - 1)) << 4) + (perm(c) & 15u)];
+    }
+
     /* ---------------------------------------------------------------- spoa's DFS order (graph.cpp:249-303)
      * Serial (lane 0).  With `sub`, runs on the subgraph exactly as spoa would on Graph::Subgraph():
      * nodes in ascending id, in-edges/aligned nodes filtered to members, original list orders kept. */
     RP_DEV void spoa_sort_hbm(bool sub) {
-        for (uint32_t v = lane; v < N; v += 32) marks[v] = 0;  // bits0-1 mark, bit2 ignored
+        for (uint32_t v = lane; v < N; v += G) marks[v] = 0;  // bits0-1 mark, bit2 ignored
         syncwarp();
         if (lane == 0) {
             const uint32_t cap = P->lim.stack_cap;
@@ -756,10 +1004,12 @@ struct PoaWarp {
      * in-edge tails and aligned list are fetched together) instead of five dependent ones. */
     RP_DEV void spoa_sort(bool sub) {
         const uint32_t npad = (N + 15) & ~15u;
-        if (ki > 31 || ka != 8 || 2 * npad + 512 > smem_bytes || (P->debug_flags & 1)) {
+        if (ki > 31 || ka != 8 || 2 * npad + 512 > smem_bytes || (P->debug_flags & 1) ||
+            !spoa_sort_staged(sub, npad))
             spoa_sort_hbm(sub);
-            return;
-        }
+    }
+
+    RP_DEV bool spoa_sort_staged(bool sub, uint32_t npad) {
         uint8_t* smk = smem;          // bits0-1 mark, bit2 ignored, bit3 member
         uint8_t* sme = smem + npad;   // in_cnt | al_cnt << 5
         /* the first two in-edge tails of every node too, when they fit: a node then costs an HBM round trip
@@ -769,15 +1019,16 @@ struct PoaWarp {
         const uint32_t fixed = have_t2 ? 6 * npad : 2 * npad;
         uint16_t* sst = reinterpret_cast<uint16_t*>(smem + fixed);
         const uint32_t cap = (smem_bytes - fixed) / 2;
-        for (uint32_t v = lane; v < N; v += 32) {
+        for (uint32_t v = lane; v < N; v += G) {
             smk[v] = (!sub || member[v]) ? 8 : 0;
             sme[v] = static_cast<uint8_t>(in_cnt[v] | (al_cnt[v] << 5));
             if (have_t2) st2[v] = *reinterpret_cast<const uint32_t*>(in_tail + v * ki);
         }
         syncwarp();
+        uint32_t ovf = 0;
         if (lane == 0) {
             uint32_t out = 0, sp = 0;
-            for (uint32_t root = 0; root < N && status == kWinOk; ++root) {
+            for (uint32_t root = 0; root < N && !ovf; ++root) {
                 if (smk[root] != 8) continue;  // not a member, or already marked
                 sst[sp++] = static_cast<uint16_t>(root);
                 while (sp > 0) {
@@ -795,7 +1046,7 @@ struct PoaWarp {
                             a_hi = a8.z | (static_cast<uint64_t>(a8.w) << 32);
                         }
                         if (sp + ni + na > cap) {
-                            fail(kWinStackLimit);
+                            ovf = 1;
                             break;
                         }
                         for (uint32_t k = 0; k < ni; ++k) {
@@ -841,23 +1092,25 @@ struct PoaWarp {
                 }
             }
         }
-        status = shfl(status, 0);
+        ovf = shfl(ovf, 0);
         syncwarp();
+        return !ovf;
     }
 
     /* Among sink rows whose last-column score equals `best`, the one spoa visits first (sisd :353-355). */
+    template <bool BAND>
     RP_DEV uint32_t resolve_sink_tie(uint32_t nrows, uint32_t len, uint32_t lpa, int32_t best, bool sub) {
         spoa_sort(sub);
         const uint16_t* ord = sub ? dp_order : order;
         uint32_t bestkey = 0xffffffffu;
-        for (uint32_t r = 1 + lane; r <= nrows; r += 32) {
+        for (uint32_t r = 1 + lane; r <= nrows; r += G) {
             uint64_t rc = rec[r].a;
             if (!((rc >> 15) & 1)) continue;
-            if (H[static_cast<uint64_t>(r) * lpa + perm(len)] != best) continue;
+            if (hcell<BAND>(lpa, r, len) != best) continue;
             uint32_t key = (static_cast<uint32_t>(srank[ord[r]]) << 16) | r;
             if (key < bestkey) bestkey = key;
         }
-        for (int d = 16; d > 0; d >>= 1) {
+        for (int d = G / 2; d > 0; d >>= 1) {
             uint32_t o = shfl_down(bestkey, d);
             if (o < bestkey) bestkey = o;
         }
@@ -868,26 +1121,34 @@ struct PoaWarp {
     /* ---------------------------------------------------------------- traceback (sisd :366-459)
      * Priority: diagonal over predecessors in in-edge order, then vertical in the same order, then
      * horizontal.  Lanes test predecessors in parallel; the lowest lane that matches wins.
-     * The walk is a chain of dependent reads of H, so it runs out of a shared-memory TILE: the warp
-     * copies kTileRows ranks x 32 columns of H (plus those rows' program records) from HBM with one
-     * coalesced burst, walks until the path leaves the tile (about 30-40 steps), and re-anchors.
-     * Predecessors below the tile (rare long edges) are read from HBM directly.
-     * Output: aln[j] = node aligned to read position j, or kNone (new node). */
-    /* > 32 predecessors (escalated windows only): every diagonal candidate of every group outranks any
+     * The walk is a chain of dependent reads of H, so it runs out of a shared-memory TILE: the group
+     * copies tile_rows ranks x 32 columns of H (plus those rows' program records) from HBM with one
+     * coalesced burst, walks until the path leaves the tile, and re-anchors.  Predecessors below the tile
+     * (rare long edges) are read from HBM directly.
+     * Output: aln[j] = node aligned to read position j, or kNone (new node).
+     *
+     * BAND: the matrix is the banded one (dp_band).  The result is accepted — the function returns true — only if
+     * every cell of the path (i) keeps `band_margin` columns away from every band edge that really cuts the matrix
+     * (an edge at column 0 or at the last column cuts nothing) and (ii) holds a value a real alignment can have
+     * (>= worst: anything derived from an excluded cell is below that, see poa_window).  Otherwise false is
+     * returned and the caller repeats the alignment with the full matrix.  Why an accepted result equals the
+     * full-matrix result: banded values never exceed the full ones and are equal wherever an optimal path lies
+     * inside the band, so every equality test of the walk has the same outcome as in the full matrix as long as
+     * the optimal paths stay inside; the margin test is the (heuristic) evidence that they do. */
+    /* > G predecessors (escalated windows only): every diagonal candidate of every batch outranks any
      * vertical one.  Reads straight from the HBM copy; kept out of line so the common loop stays small. */
-    static RP_DEV_NOINLINE int traceback_step_wide(const int16_t* H, const Rec* rec, const uint16_t* pred_ovf, uint32_t ki,
-                                                   int lane, int32_t g, uint32_t i, uint32_t j, uint32_t npe,
-                                                   int32_t hij, int32_t mc, uint32_t lpa, uint32_t* found) {
+    RP_DEV_NOINLINE int traceback_step_wide(uint32_t i, uint32_t j, uint32_t npe, int32_t hij, int32_t mc,
+                                            uint32_t lpa, uint32_t* found) {
+        const int32_t g = P->gap;
         for (int pass = 1; pass <= 2; ++pass) {
             if (pass == 1 && j == 0) continue;
-            for (uint32_t k0 = 0; k0 < npe; k0 += 32) {
+            for (uint32_t k0 = 0; k0 < npe; k0 += G) {
                 const uint32_t k = k0 + lane;
                 uint32_t p = 0;
                 bool ok = false;
                 if (k < npe) {
                     p = k < 7 ? rec_pred(rec[i], k) : pred_ovf[i * ki + k];
-                    const int16_t* pr = H + static_cast<uint64_t>(p) * lpa;
-                    ok = pass == 1 ? (hij == pr[perm(j - 1)] + mc) : (hij == pr[perm(j)] + g);
+                    ok = pass == 1 ? (hij == hcell<false>(lpa, p, j - 1) + mc) : (hij == hcell<false>(lpa, p, j) + g);
                 }
                 const uint32_t msk = ballot(ok);
                 if (msk) {
@@ -900,34 +1161,65 @@ struct PoaWarp {
     }
 
     static constexpr uint32_t kTileCols = 32;
+    static constexpr uint32_t kTileRowBytes = kTileCols * 2 + 16 + 1;   // H cells | record | band start
 
-    RP_DEV void traceback(uint32_t best_row, uint32_t len, uint32_t lpa, const uint8_t* seq, bool sub) {
+    template <bool BAND>
+    RP_DEV bool traceback(uint32_t best_row, uint32_t len, uint32_t lpa, const uint8_t* seq, bool sub, int32_t worst) {
         const int32_t g = P->gap, m = P->match, x = P->mismatch;
         const uint16_t* ord = sub ? dp_order : order;
-        const uint32_t kTileRows = P->tile_rows ? P->tile_rows : 96;
+        uint32_t kTileRows = (smem_bytes - 16 - len) / kTileRowBytes;
+        if (kTileRows > 96) kTileRows = 96;
+        if (P->tile_rows && P->tile_rows < kTileRows) kTileRows = P->tile_rows;
+        kTileRows &= ~1u;
         int16_t* tile = reinterpret_cast<int16_t*>(smem);                                        // [kTileRows][32]
         Rec* trec = reinterpret_cast<Rec*>(smem + kTileRows * kTileCols * 2);                      // [kTileRows]
-        uint16_t* tnode = reinterpret_cast<uint16_t*>(smem + kTileRows * kTileCols * 2 + kTileRows * 16);
-        uint8_t* tseq = smem + kTileRows * kTileCols * 2 + kTileRows * 16 + ((kTileRows * 2 + 15) & ~15u);
-        for (uint32_t c = lane; c < len; c += 32) tseq[c] = seq[c];  // the walk reads seq[j-1] every step
+        uint8_t* tbs = smem + kTileRows * (kTileCols * 2 + 16);                                    // [kTileRows]
+        uint8_t* tseq = tbs + ((kTileRows + 15) & ~15u);
+        for (uint32_t c = lane; c < len; c += G) tseq[c] = seq[c];  // the walk reads seq[j-1] every step
+        const uint32_t nblk = (len + 16) >> 4;
+        const uint32_t margin = P->band_margin;
+        const U4 f4 = U4{pack16(kBandFloor, kBandFloor), pack16(kBandFloor, kBandFloor), pack16(kBandFloor, kBandFloor),
+                         pack16(kBandFloor, kBandFloor)};
         uint32_t i = best_row, j = len;
         uint32_t t_top = 0, t_rows = 0, t_col0 = 0;  // tile covers ranks (t_top - t_rows, t_top], cols [t_col0, t_col0+32)
-        bool have_tile = false;
+        bool have_tile = false, bad = false;
         while (i != 0) {
-            if (!have_tile || i + t_rows <= t_top || (j > 0 && j - 1 < t_col0)) {
+            bool need = !have_tile || i + t_rows <= t_top || (j > 0 && j - 1 < t_col0);
+            /* when a group that runs in lock step with this one refills, refill too: the groups of a warp then
+             * stall for one refill instead of one each (a fresh tile is never wrong) */
+            if (G < 32 && any_converged_peer<G>(need)) need = true;
+            if (need) {
                 syncwarp();
                 t_top = i;
                 t_rows = i + 1 < kTileRows ? i + 1 : kTileRows;  // down to rank 0 at most
-                uint32_t cb = j >> 4;
-                t_col0 = (cb ? cb - 1 : 0) << 4;
-                for (uint32_t q = lane; q < t_rows; q += 32) {
-                    uint32_t rk = t_top - q;
-                    const U4* src = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0);
+                const uint32_t cbj = j >> 4;
+                const uint32_t cba = cbj ? cbj - 1 : 0;
+                t_col0 = cba << 4;
+                for (uint32_t q = lane; q < t_rows; q += G) {
+                    const uint32_t rk = t_top - q;
                     U4* dst = reinterpret_cast<U4*>(tile + q * kTileCols);
-                    U4 a = src[0], b = src[1], c = src[2], d = src[3];
-                    dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+                    if (BAND) {
+                        const uint32_t sr = bs[rk];
+                        if (rk == 0) {
+                            for (uint32_t c = 0; c < kTileCols; ++c)
+                                tile[q * kTileCols + perm(t_col0 + c) - t_col0] =
+                                    static_cast<int16_t>(static_cast<int32_t>(t_col0 + c) * g);
+                        } else {
+                            const int16_t* rowb = H + static_cast<uint64_t>(rk) * kCC;
+                            const U4* sa = reinterpret_cast<const U4*>(rowb + ((cba & (G - 1)) << 4));
+                            const U4* sb = reinterpret_cast<const U4*>(rowb + (((cba + 1) & (G - 1)) << 4));
+                            U4 a = sa[0], b = sa[1], c = sb[0], d = sb[1];
+                            if (cba - sr >= G) a = b = f4;
+                            if (cba + 1 - sr >= G) c = d = f4;
+                            dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+                        }
+                        tbs[q] = static_cast<uint8_t>(sr);
+                    } else {
+                        const U4* src = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0);
+                        U4 a = src[0], b = src[1], c = src[2], d = src[3];
+                        dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+                    }
                     trec[q] = rec[rk];
-                    tnode[q] = ord[rk];
                 }
                 have_tile = true;
                 syncwarp();
@@ -935,17 +1227,24 @@ struct PoaWarp {
             const uint32_t q = t_top - i;
             const Rec rc = trec[q];
             const uint32_t lo = static_cast<uint32_t>(rc.a);
-            const uint32_t node = tnode[q];
             const uint32_t cidx = lo & 0xff, np = (lo >> 8) & 0x7f;
             const uint32_t npe = np ? np : 1;
             const uint32_t ej = perm(j) - t_col0;                      // element of column j inside a tile row
             const uint32_t ejm = j > 0 ? perm(j - 1) - t_col0 : 0;     // column j-1
             const int32_t hij = tile[q * kTileCols + ej];
+            if (BAND) {
+                const uint32_t si = tbs[q];
+                const uint32_t dl = j - 16u * si, dr = 16u * (si + G) - 1u - j;
+                if ((si > 0 && dl < margin) || (si + G < nblk && dr < margin) || hij < worst) {  // group-uniform
+                    bad = true;
+                    break;
+                }
+            }
             int32_t mc = 0;
             if (j > 0) mc = (static_cast<uint8_t>(alpha >> (8 * cidx)) == tseq[j - 1]) ? m : x;
             uint32_t found_p = 0;
             int move = 0;  // 1 diag, 2 vert, 3 horiz
-            if (npe <= 32) {
+            if (npe <= G) {
                 /* one predecessor per lane; all diagonal candidates outrank any vertical one (sisd :392-442) */
                 uint32_t p = 0;
                 bool okd = false, okv = false;
@@ -957,9 +1256,8 @@ struct PoaWarp {
                         a = pr[ejm];
                         b = pr[ej];
                     } else {
-                        const int16_t* pr = H + static_cast<uint64_t>(p) * lpa;
-                        a = pr[perm(j > 0 ? j - 1 : 0)];
-                        b = pr[perm(j)];
+                        a = hcell<BAND>(lpa, p, j > 0 ? j - 1 : 0);
+                        b = hcell<BAND>(lpa, p, j);
                     }
                     okd = j > 0 && hij == a + mc;
                     okv = hij == b + g;
@@ -972,32 +1270,46 @@ struct PoaWarp {
                     move = md ? 1 : 2;
                 }
             } else {
-                move = traceback_step_wide(H, rec, pred_ovf, ki, lane, g, i, j, npe, hij, mc, lpa, &found_p);
+                move = traceback_step_wide(i, j, npe, hij, mc, lpa, &found_p);
             }
             if (!move) move = 3;
             if (move == 1) {
-                if (lane == 0) aln[j - 1] = static_cast<uint16_t>(node);
+                if (lane == 0) aln[j - 1] = static_cast<uint16_t>(i);   // rank for now, node below
                 i = found_p;
                 --j;
             } else if (move == 2) {
                 i = found_p;
             } else {
                 if (j == 0) {  // unreachable for a consistent matrix (column 0 always has a vertical move)
-                    fail(kWinInternal);
+                    if (BAND)
+                        bad = true;
+                    else
+                        fail(kWinInternal);
                     break;
                 }
                 if (lane == 0) aln[j - 1] = kNone;
                 --j;
             }
         }
-        /* row 0: remaining columns are horizontal moves (insertions at the start of the read) */
-        for (uint32_t c = lane; c < j; c += 32) aln[c] = kNone;
         syncwarp();
+        if (bad) return false;
+        /* row 0: remaining columns are horizontal moves (insertions at the start of the read); matched positions
+         * hold the DP rank of their row: turn it into the node */
+        for (uint32_t c = lane; c < len; c += G) {
+            if (c < j) {
+                aln[c] = kNone;
+            } else {
+                const uint32_t r = aln[c];
+                if (r != kNone) aln[c] = ord[r];
+            }
+        }
+        syncwarp();
+        return true;
     }
 
     /* ---------------------------------------------------------------- graph merge (graph.cpp:155-247) +
      * incremental order update.  aln[j] = aligned node or kNone for every read position j. */
-    RP_DEV void add_alignment(const uint8_t* seq, const uint8_t* w, uint32_t len) {
+    RP_DEV void add_alignment(const uint8_t* seq, const uint8_t* w, uint32_t len, uint32_t b0) {
         const uint32_t n_old = N;
         uint16_t* delta = reinterpret_cast<uint16_t*>(smem);  // n_old + 2 counters (ring is idle now)
         /* All phases handle kU positions per lane at a time with the loads of one dependency level issued
@@ -1005,11 +1317,11 @@ struct PoaWarp {
         constexpr int kU = 4;
         /* Phase A: target node per position (existing node, aligned sibling with the same character, or new) */
         uint32_t n_new = 0;
-        for (uint32_t j0 = 0; j0 < len; j0 += 32 * kU) {
+        for (uint32_t j0 = 0; j0 < len; j0 += G * kU) {
             uint32_t a[kU], c[kU], ca[kU], na[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                uint32_t j = j0 + u * 32 + lane;
+                uint32_t j = j0 + u * G + lane;
                 a[u] = j < len ? aln[j] : kNone;
                 c[u] = j < len ? seq[j] : 0;
             }
@@ -1020,7 +1332,7 @@ struct PoaWarp {
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                uint32_t j = j0 + u * 32 + lane;
+                uint32_t j = j0 + u * G + lane;
                 bool is_new = false;
                 uint32_t tgt = kNone, anchor = kNone;
                 if (j < len) {
@@ -1067,7 +1379,7 @@ struct PoaWarp {
         syncwarp();
         /* Phase B: aligned-cluster membership of new nodes (graph.cpp:221-229) */
         bool lim_a = false;
-        for (uint32_t k0 = 0; k0 < n_new; k0 += 32) {
+        for (uint32_t k0 = 0; k0 < n_new; k0 += G) {
             uint32_t k = k0 + lane;
             if (k < n_new) {
                 uint32_t e = newlist[k];
@@ -1101,12 +1413,14 @@ struct PoaWarp {
         /* order keys K_j (non-decreasing along the read): for an old target, or the anchor of an aligned new
          * node, the last rank of its aligned-cluster block; an unaligned insertion inherits K_{j-1} */
         int32_t run = 0;  // K_{-1} = 0: right after the root
-        for (uint32_t j0 = 0; j0 < len; j0 += 32 * kU) {
-            uint32_t bn[kU], rk0[kU], nal[kU];
+        int32_t runb = static_cast<int32_t>(b0);  // backbone coordinate an insertion at the very start inherits
+        for (uint32_t j0 = 0; j0 < len; j0 += G * kU) {
+            uint32_t bn[kU], rk0[kU], nal[kU], cj[kU], bpv[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                uint32_t j = j0 + u * 32 + lane;
+                uint32_t j = j0 + u * G + lane;
                 bn[u] = j < len ? cur[j] : kNone;
+                cj[u] = bn[u];
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u)
@@ -1115,10 +1429,21 @@ struct PoaWarp {
             for (int u = 0; u < kU; ++u) {
                 rk0[u] = bn[u] != kNone ? rank_of[bn[u]] : 0;
                 nal[u] = bn[u] != kNone ? al_cnt[bn[u]] : 0;
+                bpv[u] = bn[u] != kNone ? bpos[bn[u]] : 0;
+            }
+            /* backbone coordinate of every new node (band centre line only, never affects a result): an aligned
+             * new node sits where its anchor sits, an insertion where the path was before it */
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                int32_t incb = warp_incl_max(static_cast<int32_t>(bpv[u]));
+                if (incb < runb) incb = runb;
+                if (cj[u] != kNone && cj[u] >= n_old)
+                    bpos[cj[u]] = static_cast<uint16_t>(bn[u] != kNone ? bpv[u] : static_cast<uint32_t>(incb));
+                runb = shfl(incb, G - 1);
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                uint32_t j = j0 + u * 32 + lane;
+                uint32_t j = j0 + u * G + lane;
                 uint32_t rmax = rk0[u];
                 for (uint32_t q = 0; q < nal[u]; ++q) {
                     uint32_t sb = al[bn[u] * ka + q];
@@ -1130,19 +1455,19 @@ struct PoaWarp {
                 int32_t inc = warp_incl_max(static_cast<int32_t>(rmax));
                 if (inc < run) inc = run;
                 if (j < len) aln[j] = static_cast<uint16_t>(inc);  // aln now holds K_j
-                run = shfl(inc, 31);
+                run = shfl(inc, G - 1);
             }
         }
         syncwarp();
         /* Phase C: edges (graph.cpp:81-91,236-243) + per-node sequence counters (Node::Coverage, :32-47) */
         bool lim_e = false;
-        for (uint32_t j0 = 0; j0 < len; j0 += 32 * kU) {
+        for (uint32_t j0 = 0; j0 < len; j0 += G * kU) {
             uint32_t c[kU], pv[kU], ni[kU], cv[kU];
             int32_t wt[kU];
             uint64_t t4[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                uint32_t j = j0 + u * 32 + lane;
+                uint32_t j = j0 + u * G + lane;
                 c[u] = j < len ? cur[j] : kNone;
                 pv[u] = (j < len && j > 0) ? cur[j - 1] : kNone;
                 wt[u] = (j < len && j > 0) ? static_cast<int32_t>(w[j - 1]) + static_cast<int32_t>(w[j]) : 0;
@@ -1187,9 +1512,9 @@ struct PoaWarp {
                 fail(kWinNodeLimit);
                 return;
             }
-            for (uint32_t q = lane; q < n_old + 2; q += 32) delta[q] = 0;
+            for (uint32_t q = lane; q < n_old + 2; q += G) delta[q] = 0;
             syncwarp();
-            for (uint32_t k = lane; k < n_new; k += 32) {
+            for (uint32_t k = lane; k < n_new; k += G) {
                 uint32_t j = newlist[k] >> 16;
                 uint32_t key = aln[j];  // aligned new node: end of its cluster block; insertion: K_{j-1}
                 uint32_t id = n_old + k;
@@ -1205,25 +1530,25 @@ struct PoaWarp {
             syncwarp();
             /* inclusive prefix of the counters in shared memory, then a remap pass whose HBM loads are batched */
             uint32_t carry = 0;
-            for (uint32_t q0 = 1; q0 <= n_old; q0 += 32) {
+            for (uint32_t q0 = 1; q0 <= n_old; q0 += G) {
                 uint32_t q = q0 + lane;
                 uint32_t d = q <= n_old ? delta[q] : 0;
                 uint32_t inc = warp_incl_sum(d) + carry;
                 if (q <= n_old) delta[q] = static_cast<uint16_t>(inc);
-                carry = shfl(inc, 31);
+                carry = shfl(inc, G - 1);
             }
             syncwarp();
             constexpr int kV = 8;
-            for (uint32_t q0 = 1; q0 <= n_old; q0 += 32 * kV) {
+            for (uint32_t q0 = 1; q0 <= n_old; q0 += G * kV) {
                 uint32_t v[kV];
 #pragma unroll
                 for (int u = 0; u < kV; ++u) {
-                    uint32_t q = q0 + u * 32 + lane;
+                    uint32_t q = q0 + u * G + lane;
                     v[u] = q <= n_old ? order[q] : 0;
                 }
 #pragma unroll
                 for (int u = 0; u < kV; ++u) {
-                    uint32_t q = q0 + u * 32 + lane;
+                    uint32_t q = q0 + u * G + lane;
                     if (q <= n_old) {
                         uint32_t nr = q + delta[q];
                         order_nxt[nr] = static_cast<uint16_t>(v[u]);
@@ -1267,7 +1592,7 @@ struct PoaWarp {
     template <typename ScoreT>
     RP_DEV uint32_t bundle_pass(ScoreT* sc, uint16_t* cp, CStage* stg, uint32_t r_begin, bool skip_dead) {
         uint32_t mx = kNone;
-        for (uint32_t r0 = r_begin; r0 < N; r0 += 32) {
+        for (uint32_t r0 = r_begin; r0 < N; r0 += G) {
             const uint32_t r = r0 + lane;
             if (r < N) {
                 const uint32_t it = sorder[r];
@@ -1286,7 +1611,7 @@ struct PoaWarp {
             }
             syncwarp();
             if (lane == 0) {
-                const uint32_t cnt = N - r0 < 32 ? N - r0 : 32;
+                const uint32_t cnt = N - r0 < G ? N - r0 : G;
                 for (uint32_t q = 0; q < cnt; ++q) {
                     const CStage& e = stg[q];
                     const uint32_t it = e.it;
@@ -1311,7 +1636,7 @@ struct PoaWarp {
 
     template <typename ScoreT>
     RP_DEV uint32_t bundle(ScoreT* sc, uint16_t* cp, CStage* stg) {
-        for (uint32_t v = lane; v < N; v += 32) {
+        for (uint32_t v = lane; v < N; v += G) {
             sc[v] = -1;
             cp[v] = kNone;
         }
@@ -1320,7 +1645,7 @@ struct PoaWarp {
         /* branch completion (graph.cpp:478-516) while the best node still has out-edges */
         while (flags[mx] & 1) {
             /* heads of mx's out-edges = nodes with an in-edge from mx; their other tails are invalidated */
-            for (uint32_t v = lane; v < N; v += 32) {
+            for (uint32_t v = lane; v < N; v += G) {
                 uint32_t ni = in_cnt[v];
                 bool hit = false;
                 for (uint32_t k = 0; k < ni; ++k) hit |= (in_tail[v * ki + k] == mx);
@@ -1337,7 +1662,7 @@ struct PoaWarp {
         }
         /* hand the predecessor chain over in the HBM array the emitter reads */
         if (cp != cpred)
-            for (uint32_t v = lane; v < N; v += 32) cpred[v] = cp[v];
+            for (uint32_t v = lane; v < N; v += G) cpred[v] = cp[v];
         syncwarp();
         return mx;
     }
@@ -1347,15 +1672,15 @@ struct PoaWarp {
         if (status != kWinOk) return 0;
         /* int32 scores in shared memory are exact iff the total edge weight fits */
         uint64_t wsum = 0;
-        for (uint32_t v = lane; v < N; v += 32) {
+        for (uint32_t v = lane; v < N; v += G) {
             uint32_t ni = in_cnt[v];
             for (uint32_t k = 0; k < ni; ++k) wsum += static_cast<uint32_t>(in_w[v * ki + k]);
         }
-        for (int d = 16; d > 0; d >>= 1) wsum += shfl_down(wsum, d);
+        for (int d = G / 2; d > 0; d >>= 1) wsum += shfl_down(wsum, d);
         wsum = shfl(wsum, 0);
         const uint32_t npad = (N + 7) & ~7u;
         uint32_t mx;
-        if (wsum < 0x7fffffffull && npad * 6 + sizeof(CStage) * 32 <= smem_bytes && !(P->debug_flags & 1)) {
+        if (wsum < 0x7fffffffull && npad * 6 + sizeof(CStage) * G <= smem_bytes && !(P->debug_flags & 1)) {
             int32_t* sc = reinterpret_cast<int32_t*>(smem);
             uint16_t* cp = reinterpret_cast<uint16_t*>(smem + npad * 4);
             CStage* stg = reinterpret_cast<CStage*>(smem + npad * 6);
@@ -1377,7 +1702,7 @@ struct PoaWarp {
         /* coverage (graph.cpp:388-394): node + its aligned nodes, counted as sequences through the node */
         uint32_t thr = (n_seq - 1) / 2;
         uint32_t first = 0xffffffffu, last = 0;
-        for (uint32_t k = lane; k < clen; k += 32) {
+        for (uint32_t k = lane; k < clen; k += G) {
             uint32_t v = stack[clen - 1 - k];
             uint32_t c = cov[v];
             uint32_t na = al_cnt[v];
@@ -1394,7 +1719,7 @@ struct PoaWarp {
 
     RP_DEV uint32_t finish_consensus(uint8_t* out, uint16_t* out_cov, uint32_t out_cap, bool trim, uint32_t clen,
                                       uint32_t first, uint32_t last) {
-        for (int d = 16; d > 0; d >>= 1) {
+        for (int d = G / 2; d > 0; d >>= 1) {
             uint32_t of = shfl_down(first, d), ol = shfl_down(last, d);
             if (of < first) first = of;
             if (ol > last) last = ol;
@@ -1415,7 +1740,7 @@ struct PoaWarp {
             fail(kWinInternal);
             return 0;
         }
-        for (uint32_t k = b + lane; k < e; k += 32) {
+        for (uint32_t k = b + lane; k < e; k += G) {
             uint32_t v = stack[clen - 1 - k];
             out[k - b] = code[v];
             out_cov[k - b] = cur_cov(k);
@@ -1427,22 +1752,27 @@ struct PoaWarp {
     RP_DEV uint16_t cur_cov(uint32_t k) const { return dp_rank[k]; }
 };
 
-/* int16 is safe iff spoa's own criterion holds (alignment_engine.cpp:101-110, simd impl :699-745) */
-RP_DEV bool fits_int16(int32_t m, int32_t g, int64_t len, int64_t nodes) {
-    if (g < -kMaxGapInt16) return false;
+/* spoa's worst-case alignment score (alignment_engine.cpp:101-110); int16 is safe iff it stays above
+ * INT16_MIN + 1024 (simd impl :699-745) */
+RP_DEV int64_t worst_case_score(int32_t m, int32_t g, int64_t len, int64_t nodes) {
     int64_t i = len + 8, j = nodes;
     int64_t mn = i < j ? i : j;
     int64_t df = i > j ? i - j : j - i;
     int64_t a = -1 * (m * mn + g * df);
     int64_t b = g * i + g * j;
-    int64_t worst = a < b ? a : b;
-    return worst >= static_cast<int64_t>(-32768 + 1024);
+    return a < b ? a : b;
+}
+RP_DEV bool fits_int16(int32_t m, int32_t g, int64_t len, int64_t nodes) {
+    if (g < -kMaxGapInt16) return false;
+    return worst_case_score(m, g, len, nodes) >= static_cast<int64_t>(-32768 + 1024);
 }
 
-/* Processes one window end to end. `slot`: this warp's HBM scratch, `smem`: this warp's shared memory. */
+/* Processes one window end to end. `slot`: this group's HBM scratch, `smem`: this group's shared memory. */
+template <int G>
 RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* smem) {
-    PoaWarp W;
-    W.bind(&P, slot, smem, P.smem_per_warp);
+    constexpr uint32_t kCC = PoaWarp<G>::kCC;
+    PoaWarp<G> W;
+    W.bind(&P, slot, smem, P.smem_per_group);
     W.status = kWinOk;
     const uint32_t s0 = P.win_first[w], s1 = P.win_first[w + 1];
     W.alpha = P.win_alpha[w];
@@ -1475,8 +1805,12 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         }
         bool sub = !(P.seq_flags[s] & 1);
         uint32_t nrows = W.N;
+        uint32_t b0 = 0, span = blen;   // backbone interval the layer covers (band centre line)
         if (sub) {
-            W.mark_subgraph(P.seq_begin[s], P.seq_end[s]);
+            b0 = P.seq_begin[s];
+            const uint32_t e0 = P.seq_end[s];
+            span = e0 >= b0 ? e0 - b0 + 1 : 1;
+            W.mark_subgraph(b0, e0);
             if (W.status != kWinOk) break;
             nrows = W.build_dp_order_subgraph();
         }
@@ -1485,7 +1819,9 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
          * arithmetic gives the same answer in either width, so a window that fails the bound is still computed in
          * int16 and the finished matrix is checked for having stayed in range (matrix_in_range). */
         bool verify_range = false;
-        if (!fits_int16(P.match, P.gap, len, nrows)) {
+        const int64_t worst = worst_case_score(P.match, P.gap, len, nrows);
+        const bool fits = P.gap >= -kMaxGapInt16 && worst >= static_cast<int64_t>(-32768 + 1024);
+        if (!fits) {
             const int64_t short_side = static_cast<int64_t>(len) + 8 < nrows ? static_cast<int64_t>(len) + 8 : nrows;
             if (P.gap < -kMaxGapInt16 || static_cast<int64_t>(P.match) * short_side > 32767 - 1024) {
                 W.fail(kWinNeedsInt32);
@@ -1493,48 +1829,78 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
             }
             verify_range = true;
         }
-        uint32_t lpa = (len + 1 + kChunkCols - 1) / kChunkCols * kChunkCols;
-        /* shared memory split: profile rows first, the rest is the ring of recent DP rows */
-        /* shared memory (chunk-local): profile chunk | ring of the last R DP rows */
-        const uint32_t prof_bytes = W.ncodes * kChunkCols * 2;
-        const uint32_t tile_rows = P.tile_rows ? P.tile_rows : 96;
-        const uint32_t tb_bytes = tile_rows * (64 + 16 + 2) + 16 + len;  // traceback: H tile | records | nodes | read
-        if (prof_bytes + 2 * kChunkCols * 2 > P.smem_per_warp || tb_bytes > P.smem_per_warp) {
+        const uint32_t lpa = (len + 1 + kCC - 1) / kCC * kCC;
+        /* shared memory (chunk-local): profile chunk | ring of the last R DP rows; the traceback re-uses it */
+        const uint32_t prof_bytes = W.ncodes * kCC * 2;
+        const uint32_t tb_bytes = 8 * PoaWarp<G>::kTileRowBytes + 32 + len;  // at least 8 tile rows + the read
+        if (prof_bytes + 2 * kCC * 2 > P.smem_per_group || tb_bytes > P.smem_per_group) {
             W.fail(kWinSeqTooLong);
             break;
         }
-        uint32_t ring_rows = (P.smem_per_warp - prof_bytes) / (kChunkCols * 2);
+        uint32_t ring_rows = (P.smem_per_group - prof_bytes) / (kCC * 2);
         if (ring_rows > 32) ring_rows = 32;
         W.prof = reinterpret_cast<int16_t*>(smem);
         W.ring = reinterpret_cast<int16_t*>(smem + prof_bytes);
-        uint32_t pred_rows = W.build_program(nrows, sub);
+        /* racon -b: the alignment is first tried inside a band of 16*G columns.  Preconditions: the row is longer
+         * than the band, band starts fit a byte, the band rows fit the matrix scratch, and real scores are
+         * separated from anything derived from an excluded cell (worst > kBandFloor + match * len). */
+        const uint32_t nblk = (len + 16) >> 4;
+        const bool band = P.banded && nblk > static_cast<uint32_t>(G) && nblk - G <= 255u && fits &&
+                          worst > static_cast<int64_t>(kBandFloor) + static_cast<int64_t>(P.match > 0 ? P.match : 0) * (len + 8) &&
+                          static_cast<uint64_t>(nrows + 1) * kCC <= P.lim.hcap;
+        uint32_t pred_rows = W.build_program(nrows, sub, band, len, b0, span);
         uint32_t best_row, n_best;
         int32_t best;
-        W.dp(seq, nrows, len, lpa, ring_rows, &best_row, &best, &n_best);
-        if (verify_range && !W.matrix_in_range(nrows, len, lpa)) {
-            W.fail(kWinNeedsInt32);
-            break;
-        }
-        if (n_best > 1) {
-            best_row = W.resolve_sink_tie(nrows, len, lpa, best, sub);
+        bool done = false;
+        if (band) {
+            W.dp_band(seq, nrows, len, ring_rows, &best_row, &best, &n_best);
+            done = best_row != 0;
+            if (done && n_best > 1) {
+                best_row = W.template resolve_sink_tie<true>(nrows, len, lpa, best, sub);
+                if (W.status != kWinOk) break;
+            }
+            if (done) done = W.template traceback<true>(best_row, len, lpa, seq, sub, static_cast<int32_t>(worst));
+            if (P.band_stats && lane == 0) {
+#if !defined(RP_HOST_SIM)
+                atomicAdd(P.band_stats, 1ull);
+                if (!done) atomicAdd(P.band_stats + 1, 1ull);
+#else
+                P.band_stats[0] += 1;
+                if (!done) P.band_stats[1] += 1;
+#endif
+            }
             if (W.status != kWinOk) break;
         }
-        W.traceback(best_row, len, lpa, seq, sub);
-        W.add_alignment(seq, wts, len);
-        if (P.stats) pred_rows = warp_incl_sum(pred_rows);
-        if (P.stats) pred_rows = shfl(pred_rows, 31);
+        if (!done) {
+            if (static_cast<uint64_t>(nrows + 1) * lpa > P.lim.hcap) {
+                W.fail(kWinMatrixLimit);
+                break;
+            }
+            W.dp(seq, nrows, len, lpa, ring_rows, &best_row, &best, &n_best);
+            if (verify_range && !W.matrix_in_range(nrows, len, lpa)) {
+                W.fail(kWinNeedsInt32);
+                break;
+            }
+            if (n_best > 1) {
+                best_row = W.template resolve_sink_tie<false>(nrows, len, lpa, best, sub);
+                if (W.status != kWinOk) break;
+            }
+            W.template traceback<false>(best_row, len, lpa, seq, sub, 0);
+        }
+        W.add_alignment(seq, wts, len, b0);
+        if (P.stats) pred_rows = W.warp_incl_sum(pred_rows);
+        if (P.stats) pred_rows = W.shfl(pred_rows, G - 1);
         if (P.stats && lane == 0) {
+            const unsigned long long cols = (band && done) ? kCC : len + 1;   // columns the accepted DP computed per row
 #if !defined(RP_HOST_SIM)
-            atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 3),
-                      static_cast<unsigned long long>(pred_rows) * (len + 1));
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 3), static_cast<unsigned long long>(pred_rows) * cols);
             atomicAdd(reinterpret_cast<unsigned long long*>(P.stats), 1ull);
-            atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 1),
-                      static_cast<unsigned long long>(nrows + 1) * (len + 1));
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 1), static_cast<unsigned long long>(nrows + 1) * cols);
             if (n_best > 1) atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 2), 1ull);
 #else
             P.stats[0] += 1;
-            P.stats[3] += static_cast<uint64_t>(pred_rows) * (len + 1);
-            P.stats[1] += static_cast<uint64_t>(nrows + 1) * (len + 1);
+            P.stats[3] += static_cast<uint64_t>(pred_rows) * cols;
+            P.stats[1] += static_cast<uint64_t>(nrows + 1) * cols;
             if (n_best > 1) P.stats[2] += 1;
 #endif
         }
@@ -1545,7 +1911,7 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         P.status[w] = W.status;
         P.cons_len[w] = W.status == kWinOk ? clen : 0;
     }
-    syncwarp();
+    W.syncwarp();
 }
 
 }  // namespace rp

@@ -77,7 +77,8 @@ struct PackedBatch {
     std::vector<uint32_t> cost;            // per GPU window: total bases (queue ordering)
     uint64_t out_total = 0;
     /* limits */
-    uint64_t max_bases = 0xfff00000ull;    // uint32 offsets
+    uint64_t max_bases = 0xfff00000ull;    // uint32 offsets; rp_poa_create lowers these to the object's memory budget
+    uint64_t max_out = 0xfff00000ull;      // consensus bytes reserved (uint32 out_off)
     uint32_t max_windows = 1u << 22;
     uint32_t max_seq_len = 65000;
 
@@ -199,22 +200,38 @@ struct PackedBatch {
             trivial.emplace_back();
             return kPackOk;
         }
-        if (bases.size + pr.tot > max_bases || n_gpu() >= max_windows) return kPackFull;
+        const uint32_t cap = 2 * pr.blen + 64;
+        /* the batch limits (memory budget, uint32 offsets) make a batch FULL; an empty batch takes any window so
+         * that the caller's add-until-full loop always makes progress (cudabatch.cpp:126-132) */
+        if (n_gpu() > 0 && (bases.size + pr.tot > max_bases || n_gpu() >= max_windows || out_total + cap > max_out))
+            return kPackFull;
+        if (bases.size + pr.tot > 0xfff00000ull || out_total + cap > 0xfff00000ull) return kPackFull;
+        /* reserve everything first: a failed allocation must leave the batch as it was */
+        const size_t ns = pr.order.size();
+        if (!bases.reserve(bases.size + pr.tot) || !weights.reserve(weights.size + pr.tot) ||
+            !seq_off.reserve(seq_off.size + ns) || !seq_begin.reserve(seq_begin.size + ns) ||
+            !seq_end.reserve(seq_end.size + ns) || !seq_flags.reserve(seq_flags.size + ns) ||
+            !win_first.reserve(win_first.size + 1) || !win_flags.reserve(win_flags.size + 1) ||
+            !win_alpha.reserve(win_alpha.size + 1) || !out_off.reserve(out_off.size + 1) ||
+            !out_cap.reserve(out_cap.size + 1))
+            return kPackNoMem;
         pr.base_off = bases.size;
-        if (!bases.extend(pr.tot) || !weights.extend(pr.tot)) return kPackNoMem;
+        bases.extend(pr.tot);
+        weights.extend(pr.tot);
         uint32_t off = seq_off.data[seq_off.size - 1];
-        for (uint32_t i = 0; i < pr.order.size(); ++i) {
+        for (uint32_t i = 0; i < ns; ++i) {
             uint32_t k = pr.order[i];
             off += len[k];
-            if (!seq_off.push(off) || !seq_begin.push(i ? begin[k] : 0) || !seq_end.push(i ? end[k] : 0) ||
-                !seq_flags.push(pr.full[i]))
-                return kPackNoMem;
+            seq_off.push(off);
+            seq_begin.push(i ? begin[k] : 0);
+            seq_end.push(i ? end[k] : 0);
+            seq_flags.push(pr.full[i]);
         }
-        uint32_t cap = 2 * pr.blen + 64;
-        if (!win_first.push(static_cast<uint32_t>(seq_off.size - 1)) ||
-            !win_flags.push((window_type == 1 && trim) ? 1 : 0) || !win_alpha.push(pr.alpha) ||
-            !out_off.push(static_cast<uint32_t>(out_total)) || !out_cap.push(cap))
-            return kPackNoMem;
+        win_first.push(static_cast<uint32_t>(seq_off.size - 1));
+        win_flags.push((window_type == 1 && trim) ? 1 : 0);
+        win_alpha.push(pr.alpha);
+        out_off.push(static_cast<uint32_t>(out_total));
+        out_cap.push(cap);
         out_total += cap;
         gpu_index.push_back(static_cast<int32_t>(n_gpu() - 1));
         trivial.emplace_back();

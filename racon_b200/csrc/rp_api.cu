@@ -54,8 +54,8 @@ struct DevBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr;
-        size_t nc = cap ? cap : 4096;
-        while (nc < n) nc *= 2;
+        size_t nc = n + n / 8 + 4096;          // modest head room: the object works inside a memory budget
+        nc = (nc + 0xffffu) & ~static_cast<size_t>(0xffffu);
         cudaError_t e = cudaMalloc(&p, nc);
         cap = e == cudaSuccess ? nc : 0;
         return e;
@@ -69,32 +69,41 @@ struct DevBuf {
 
 constexpr int kWarpsPerBlock = 4;
 
-/* Persistent kernel: each warp is an independent worker that pulls windows from an atomic queue.
- * Compiled for several occupancy points (blocks per SM -> register cap); RP_BLOCKS_PER_SM selects one. */
-template <int kBlocksPerSm>
+/* Persistent kernel: every GROUP of G lanes (G = 8, 16, 32; rp_warp.cuh) is an independent worker that pulls
+ * windows from an atomic queue — 32/G windows in flight per warp, advancing together wherever their control
+ * flow agrees.  Compiled for several group widths and occupancy points (blocks per SM -> register cap);
+ * RP_POA_GROUP / RP_BLOCKS_PER_SM select one (defaults in rp_poa_create). */
+template <int G, int kBlocksPerSm>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kernel(rp::PoaParams P) {
     extern __shared__ __align__(16) uint8_t smem_all[];
-    const int warp = threadIdx.x >> 5;
-    const uint32_t worker = blockIdx.x * (blockDim.x >> 5) + warp;
+    const uint32_t grp = threadIdx.x / G;
+    const uint32_t worker = blockIdx.x * (blockDim.x / G) + grp;
     uint8_t* slot = P.scratch + static_cast<uint64_t>(worker) * P.lay.bytes;
-    uint8_t* smem = smem_all + static_cast<uint32_t>(warp) * P.smem_per_warp;
+    uint8_t* smem = smem_all + grp * P.smem_per_group;
     for (;;) {
         uint32_t q = 0;
-        if ((threadIdx.x & 31) == 0) q = atomicAdd(P.queue_head, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
+        if (rp::glane<G>() == 0) q = atomicAdd(P.queue_head, 1u);
+        q = rp::gshfl<G>(q, 0);
         if (q >= P.n_windows) break;
-        rp::poa_window(P, P.queue[q], slot, smem);
+        rp::poa_window<G>(P, P.queue[q], slot, smem);
     }
 }
 
 typedef void (*PoaKernel)(rp::PoaParams);
-PoaKernel pick_kernel(int blocks_per_sm) {
+template <int G>
+PoaKernel pick_kernel_g(int blocks_per_sm) {
     switch (blocks_per_sm) {
-        case 3: return rp_poa_kernel<3>;
-        case 5: return rp_poa_kernel<5>;
-        case 6: return rp_poa_kernel<6>;
-        case 8: return rp_poa_kernel<8>;
-        default: return rp_poa_kernel<4>;
+        case 2: return rp_poa_kernel<G, 2>;
+        case 3: return rp_poa_kernel<G, 3>;
+        case 6: return rp_poa_kernel<G, 6>;
+        default: return rp_poa_kernel<G, 4>;
+    }
+}
+PoaKernel pick_kernel(int group, int blocks_per_sm) {
+    switch (group) {
+        case 8: return pick_kernel_g<8>(blocks_per_sm);
+        case 16: return pick_kernel_g<16>(blocks_per_sm);
+        default: return pick_kernel_g<32>(blocks_per_sm);
     }
 }
 
@@ -161,15 +170,18 @@ struct rp_poa {
     rp::GrowBuf<uint16_t> h_cov;
     rp::GrowBuf<uint32_t> h_len, h_status;
     uint64_t h_stats[8] = {0};
-    uint32_t workers = 0;
+    uint32_t workers = 0;          // lane groups = windows in flight
     int grid = 0;
     uint32_t smem_block = 0;
     PoaKernel kernel = nullptr;
     int blocks_per_sm = 4;
+    int group = 32;                // lanes per window
+    uint32_t groups_per_block = 4;
     bool uploaded = false, launched = false, downloaded = false, synced = false;
     bool counters = false;
     uint64_t launches = 0, last_h2d = 0, last_d2h = 0;
     int banded = 0;
+    uint64_t h_band[2] = {0, 0};   // alignments tried in the band / redone with the full matrix (last launch)
     /* escalation pass for windows that exceeded a device limit (never a CPU re-run) */
     DevBuf d_scratch_big, d_queue_big;
     rp::PoaLimits lim_big;
@@ -241,24 +253,30 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     lim.ki = 16;
     lim.ka = 8;
     lim.stack_cap = lim.nmax * 4 + 64;
-    p->P.lim = lim;
-    p->P.lay = rp::make_layout(lim);
     p->P.match = match;
     p->P.mismatch = mismatch;
     p->P.gap = gap;
+    p->P.banded = banded ? 1 : 0;
+    p->P.band_margin = 16;
+    if (const char* e_m = getenv("RP_BAND_MARGIN")) p->P.band_margin = static_cast<uint32_t>(atoi(e_m));
 
-    /* launch shape: persistent blocks of 4 independent warps, kBlocksPerSm blocks per SM */
+    /* launch shape: persistent blocks of 4 warps = 128/G lane groups, kBlocksPerSm blocks per SM */
+    int group = banded ? 8 : 16;
+    if (const char* e_g = getenv("RP_POA_GROUP")) group = atoi(e_g);
+    if (group != 8 && group != 16 && group != 32) group = banded ? 8 : 16;
     int bps = 4;
     if (const char* e_bps = getenv("RP_BLOCKS_PER_SM")) bps = atoi(e_bps);
-    if (bps != 3 && bps != 5 && bps != 6 && bps != 8) bps = 4;
+    if (bps != 2 && bps != 3 && bps != 6) bps = 4;
+    p->group = group;
+    p->groups_per_block = kWarpsPerBlock * 32 / group;
     p->blocks_per_sm = bps;
-    p->kernel = pick_kernel(bps);
+    p->kernel = pick_kernel(group, bps);
     uint32_t smem_per_sm = static_cast<uint32_t>(prop.sharedMemPerMultiprocessor);
     uint32_t per_block = smem_per_sm / bps - 1024;                              // 1 KB reserved per block
     if (per_block > prop.sharedMemPerBlockOptin) per_block = static_cast<uint32_t>(prop.sharedMemPerBlockOptin);
-    uint32_t per_warp = (per_block / kWarpsPerBlock) & ~255u;
-    p->P.smem_per_warp = per_warp;
-    p->smem_block = per_warp * kWarpsPerBlock;
+    uint32_t per_group = (per_block / p->groups_per_block) & ~255u;
+    p->P.smem_per_group = per_group;
+    p->smem_block = per_group * p->groups_per_block;
     e = cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(p->smem_block));
     int occ = 0;
     if (e == cudaSuccess)
@@ -267,16 +285,37 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
         rp_poa_destroy(p);
         return fail(RP_ERR_CUDA, std::string("kernel configuration: ") + cudaGetErrorString(e));
     }
-    uint64_t max_workers = static_cast<uint64_t>(prop.multiProcessorCount) * occ * kWarpsPerBlock;
-    uint64_t scratch_budget = mem_bytes / 2;
+    /* Device-memory budget of this object (cudabatch.cpp:23-72 passes 0.9 * free / batches): half for the
+     * per-window scratch of the workers, a quarter for the lazily allocated escalation pass, a quarter for the
+     * batch itself (inputs + outputs) — the batch limits below are what makes add_window return RP_BATCH_FULL. */
+    const uint64_t max_workers = static_cast<uint64_t>(prop.multiProcessorCount) * occ * p->groups_per_block;
+    const uint64_t scratch_budget = mem_bytes / 2;
+    /* score-matrix scratch per window: the whole (nmax + 1) x padded-lmax matrix when the budget allows it for
+     * every worker, otherwise down to what a window 4x deeper than its length needs (larger windows are re-run
+     * by the escalation pass); only then fewer workers */
+    const uint64_t hcap_full = static_cast<uint64_t>(lim.nmax + 1) * lim.lp;
+    const uint64_t hcap_min = std::min<uint64_t>(
+        hcap_full, static_cast<uint64_t>(4 * wl + 64) * (((wl + wl / 4 + wl / 32 + 1) + 127) / 128 * 128));
+    lim.hcap = 0;
+    const uint64_t fixed_bytes = rp::make_layout(lim).bytes;
+    uint64_t hcap = hcap_full;
+    if (max_workers * (fixed_bytes + hcap * 2) > scratch_budget) {
+        const uint64_t per = scratch_budget / max_workers;
+        hcap = per > fixed_bytes + 4096 ? (per - fixed_bytes - 4096) / 2 : 0;
+        hcap = std::max(hcap_min, std::min(hcap, hcap_full));
+    }
+    if (const char* e_h = getenv("RP_POA_HCAP")) hcap = std::max<uint64_t>(1024, strtoull(e_h, nullptr, 10));
+    lim.hcap = static_cast<uint32_t>(std::min<uint64_t>(hcap, 0xfffffff0ull));
+    p->P.lim = lim;
+    p->P.lay = rp::make_layout(lim);
     uint64_t fit = scratch_budget / p->P.lay.bytes;
-    if (fit < kWarpsPerBlock) {
+    if (fit < p->groups_per_block) {
         rp_poa_destroy(p);
         return fail(RP_ERR_NOMEM, "memory budget too small for one block of POA workers");
     }
-    uint64_t workers = std::min(max_workers, fit) / kWarpsPerBlock * kWarpsPerBlock;
+    uint64_t workers = std::min(max_workers, fit) / p->groups_per_block * p->groups_per_block;
     p->workers = static_cast<uint32_t>(workers);
-    p->grid = static_cast<int>(workers / kWarpsPerBlock);
+    p->grid = static_cast<int>(workers / p->groups_per_block);
     e = p->d_scratch.reserve(workers * p->P.lay.bytes);
     if (e == cudaSuccess) e = p->d_head.reserve(256);
     if (e == cudaSuccess) e = p->d_stats.reserve(256);
@@ -287,6 +326,10 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     cudaMemsetAsync(p->d_stats.p, 0, 256, p->stream);
     p->batch.max_seq_len = 65000;
     p->mem_budget = mem_bytes;
+    const uint64_t io_budget = mem_bytes / 4;
+    p->batch.max_bases = std::min<uint64_t>(0xfff00000ull, std::max<uint64_t>(io_budget / 4, 1u << 16));
+    p->batch.max_out = std::min<uint64_t>(0xfff00000ull, std::max<uint64_t>(io_budget / 8, 1u << 14));
+    p->batch.max_windows = static_cast<uint32_t>(std::min<uint64_t>(1u << 22, std::max<uint64_t>(io_budget / 4096, 16)));
     p->lim_big = lim;
     p->lim_big.nmax = std::min<uint32_t>(65000, lim.nmax * 8);
     p->lim_big.lmax = std::min<uint32_t>(16000, lim.lmax * 4);
@@ -294,6 +337,8 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     p->lim_big.ki = 96;
     p->lim_big.ka = 8;
     p->lim_big.stack_cap = p->lim_big.nmax * 6 + 64;
+    p->lim_big.hcap = static_cast<uint32_t>(
+        std::min<uint64_t>(0xfffffff0ull, static_cast<uint64_t>(p->lim_big.nmax + 1) * p->lim_big.lp));
     p->lay_big = rp::make_layout(p->lim_big);
     *out = p;
     return RP_OK;
@@ -469,8 +514,12 @@ rp_status rp_poa_launch(rp_poa* p) {
     RP_CUDA(cudaSetDevice(p->device));
     if (p->P.n_windows > 0) {
         RP_CUDA(cudaMemsetAsync(p->d_head.p, 0, 4, p->stream));
+        RP_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(p->d_stats.p) + 128, 0, 16, p->stream));
         p->P.stats = p->counters ? static_cast<uint64_t*>(p->d_stats.p) : nullptr;
-        p->kernel<<<p->grid, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(p->P);
+        p->P.band_stats = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(p->d_stats.p) + 128);
+        const uint32_t need_blocks = (p->P.n_windows + p->groups_per_block - 1) / p->groups_per_block;
+        const uint32_t blocks = std::min<uint32_t>(static_cast<uint32_t>(p->grid), need_blocks);
+        p->kernel<<<blocks, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(p->P);
         RP_CUDA(cudaGetLastError());
         p->launches += 1;
     }
@@ -495,6 +544,9 @@ rp_status rp_poa_download(rp_poa* p) {
     }
     if (p->counters)
         RP_CUDA(cudaMemcpyAsync(p->h_stats, p->d_stats.p, 64, cudaMemcpyDeviceToHost, p->stream));
+    if (p->banded && n > 0)
+        RP_CUDA(cudaMemcpyAsync(p->h_band, static_cast<uint8_t*>(p->d_stats.p) + 128, 16, cudaMemcpyDeviceToHost,
+                                p->stream));
     p->last_d2h = d2h;
     p->downloaded = true;
     p->synced = false;
@@ -517,14 +569,15 @@ static rp_status escalate(rp_poa* p) {
     std::vector<uint32_t> redo;
     for (uint32_t w = 0; w < n; ++w) {
         uint32_t st = p->h_status.data[w];
-        if (st == rp::kWinNodeLimit || st == rp::kWinEdgeLimit || st == rp::kWinSeqTooLong || st == rp::kWinStackLimit)
+        if (st == rp::kWinNodeLimit || st == rp::kWinEdgeLimit || st == rp::kWinSeqTooLong ||
+            st == rp::kWinStackLimit || st == rp::kWinMatrixLimit)
             redo.push_back(w);
     }
     if (redo.empty()) return RP_OK;
     if (p->workers_big == 0) {
         uint64_t fit = (p->mem_budget / 4) / p->lay_big.bytes;
-        uint64_t workers = std::min<uint64_t>(p->workers, fit) / kWarpsPerBlock * kWarpsPerBlock;
-        if (workers < kWarpsPerBlock) return RP_OK;  // no room: the soft status stays
+        uint64_t workers = std::min<uint64_t>(p->workers, fit) / p->groups_per_block * p->groups_per_block;
+        if (workers < p->groups_per_block) return RP_OK;  // no room: the soft status stays
         cudaError_t e = p->d_scratch_big.reserve(workers * p->lay_big.bytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -542,8 +595,10 @@ static rp_status escalate(rp_poa* p) {
     P.lim = p->lim_big;
     P.lay = p->lay_big;
     P.stats = nullptr;
-    uint32_t blocks = std::min<uint32_t>(p->workers_big / kWarpsPerBlock,
-                                         (static_cast<uint32_t>(redo.size()) + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    P.banded = 0;
+    P.band_stats = nullptr;
+    uint32_t blocks = std::min<uint32_t>(p->workers_big / p->groups_per_block,
+                                         (static_cast<uint32_t>(redo.size()) + p->groups_per_block - 1) / p->groups_per_block);
     p->kernel<<<blocks, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(P);
     RP_CUDA(cudaGetLastError());
     p->launches += 1;
@@ -650,6 +705,17 @@ rp_status rp_poa_info(rp_poa* p, uint64_t info[8]) {
     info[5] = p->h_stats[0];
     info[6] = p->h_stats[1];
     info[7] = p->h_stats[3];
+    return RP_OK;
+}
+
+rp_status rp_poa_band_info(rp_poa* p, uint64_t info[4]) {
+    if (!p || !info) return fail(RP_ERR_INVALID, "null argument");
+    rp_status s = ensure_results(p);
+    if (s != RP_OK) return s;
+    info[0] = p->banded ? 1 : 0;
+    info[1] = p->h_band[0];
+    info[2] = p->h_band[1];
+    info[3] = static_cast<uint64_t>(p->group) * 16;
     return RP_OK;
 }
 

@@ -46,6 +46,7 @@ struct Warp {
     int arrived = 0;
     uint64_t gen = 0;
     int cur = 0;
+    int n = 32;          // lanes of this simulated warp (32, or one 8/16-lane group of the POA kernel)
     void (*fn)(void*) = nullptr;
     void* arg = nullptr;
 };
@@ -63,15 +64,16 @@ inline void trampoline() {
     w->done[w->cur] = true;
     swapcontext(&w->ctx[w->cur], &w->main);
 }
-/* Runs fn(arg) as 32 lock-step-at-collectives fibres. */
-inline void run_warp(void (*fn)(void*), void* arg, size_t stack_bytes = 256 * 1024) {
+/* Runs fn(arg) as n (default 32) lock-step-at-collectives fibres. */
+inline void run_warp(void (*fn)(void*), void* arg, size_t stack_bytes = 256 * 1024, int n = 32) {
     Warp w;
     w.fn = fn;
     w.arg = arg;
+    w.n = n;
     w.stacks = static_cast<char*>(malloc(stack_bytes * 32));
     Warp* saved = current();
     current() = &w;
-    for (int l = 0; l < 32; ++l) {
+    for (int l = 0; l < n; ++l) {
         w.done[l] = false;
         getcontext(&w.ctx[l]);
         w.ctx[l].uc_stack.ss_sp = w.stacks + static_cast<size_t>(l) * stack_bytes;
@@ -81,7 +83,7 @@ inline void run_warp(void (*fn)(void*), void* arg, size_t stack_bytes = 256 * 10
     }
     for (;;) {
         int alive = 0;
-        for (int l = 0; l < 32; ++l) {
+        for (int l = 0; l < n; ++l) {
             if (w.done[l]) continue;
             ++alive;
             w.cur = l;
@@ -89,8 +91,8 @@ inline void run_warp(void (*fn)(void*), void* arg, size_t stack_bytes = 256 * 10
         }
         if (!alive) break;
         int finished = 0;
-        for (int l = 0; l < 32; ++l) finished += w.done[l] ? 1 : 0;
-        if (finished > 0 && finished < 32 && w.arrived > 0 && w.arrived + finished == 32) {
+        for (int l = 0; l < n; ++l) finished += w.done[l] ? 1 : 0;
+        if (finished > 0 && finished < n && w.arrived > 0 && w.arrived + finished == n) {
             fprintf(stderr, "[rp::sim] deadlock: %d lanes wait at a collective, %d lanes already returned\n",
                     w.arrived, finished);
             abort();
@@ -104,7 +106,7 @@ inline uint64_t collective(uint64_t v, int src_or_neg /* -1: return own slot tab
     int me = w->cur;
     w->slot[me] = v;
     uint64_t my_gen = w->gen;
-    if (++w->arrived == 32) {
+    if (++w->arrived == w->n) {
         memcpy(w->result, w->slot, sizeof(w->slot));
         w->arrived = 0;
         w->gen++;
@@ -114,7 +116,8 @@ inline uint64_t collective(uint64_t v, int src_or_neg /* -1: return own slot tab
     (void)src_or_neg;
     return 0;
 }
-inline uint64_t result_of(int lane) { return current()->result[lane & 31]; }
+inline uint64_t result_of(int lane) { return current()->result[lane & (current()->n - 1)]; }
+inline int lanes() { return current()->n; }
 }  // namespace sim
 
 inline int lane_id() { return sim::current()->cur; }
@@ -122,7 +125,7 @@ inline void syncwarp() { sim::collective(0, 0); }
 inline uint32_t ballot(bool p) {
     sim::collective(p ? 1 : 0, 0);
     uint32_t m = 0;
-    for (int l = 0; l < 32; ++l) m |= (sim::result_of(l) ? 1u : 0u) << l;
+    for (int l = 0; l < sim::lanes(); ++l) m |= (sim::result_of(l) ? 1u : 0u) << l;
     return m;
 }
 template <typename T>
@@ -145,7 +148,7 @@ inline T shfl_up(T v, int d) {
 template <typename T>
 inline T shfl_down(T v, int d) {
     int me = lane_id();
-    T got = shfl(v, me + d > 31 ? me : me + d);
+    T got = shfl(v, me + d > sim::lanes() - 1 ? me : me + d);
     return got;
 }
 inline uint32_t atomic_add(uint32_t* p, uint32_t v) {
@@ -243,6 +246,63 @@ RP_DEV int32_t warp_incl_max(int32_t v) {
     int l = lane_id();
     for (int d = 1; d < 32; d <<= 1) {
         int32_t o = shfl_up(v, d);
+        if (l >= d && o > v) v = o;
+    }
+    return v;
+}
+
+/* ------------------------------------------------------------------ lane groups
+ * The POA kernel runs one window per GROUP of G lanes (G = 8, 16 or 32), 32/G independent windows per warp:
+ * the groups of a warp execute the same instruction stream, so one issued instruction advances 32/G windows
+ * wherever their control flow agrees (SIMT), and every collective below only names the lanes of its own group,
+ * which keeps it legal when the groups have diverged.  In the host simulation a group is simply a simulated
+ * warp of G fibres. */
+#if defined(RP_HOST_SIM)
+template <int G> RP_DEV int glane() { return lane_id(); }
+template <int G> RP_DEV void gsync() { syncwarp(); }
+template <int G> RP_DEV uint32_t gballot(bool p) { return ballot(p); }
+template <int G, typename T> RP_DEV T gshfl(T v, int src) { return shfl(v, src); }
+template <int G, typename T> RP_DEV T gshfl_up(T v, int d) { return shfl_up(v, d); }
+template <int G, typename T> RP_DEV T gshfl_down(T v, int d) { return shfl_down(v, d); }
+/* true when any group that currently executes together with this one votes yes (a hint, never needed for
+ * correctness): the simulation knows only its own group */
+template <int G> RP_DEV bool any_converged_peer(bool p) { return ballot(p) != 0; }
+#else
+template <int G> RP_DEV int glane() { return static_cast<int>(threadIdx.x & (G - 1)); }
+template <int G> RP_DEV uint32_t gbase() { return (threadIdx.x & 31u) & ~static_cast<uint32_t>(G - 1); }
+template <int G> RP_DEV uint32_t gmask() {
+    return G == 32 ? kFull : (((1u << (G & 31)) - 1u) << gbase<G>());
+}
+template <int G> RP_DEV void gsync() { __syncwarp(gmask<G>()); }
+template <int G> RP_DEV uint32_t gballot(bool p) { return __ballot_sync(gmask<G>(), p) >> gbase<G>(); }
+template <int G, typename T> RP_DEV T gshfl(T v, int src) { return __shfl_sync(gmask<G>(), v, src, G); }
+template <int G, typename T> RP_DEV T gshfl_up(T v, int d) { return __shfl_up_sync(gmask<G>(), v, d, G); }
+template <int G, typename T> RP_DEV T gshfl_down(T v, int d) { return __shfl_down_sync(gmask<G>(), v, d, G); }
+template <int G> RP_DEV bool any_converged_peer(bool p) {
+    const uint32_t act = __activemask();        // whoever happens to execute this together with me
+    return __ballot_sync(act, p) != 0;
+}
+#endif
+
+template <int G> RP_DEV uint32_t grank(bool p, uint32_t* total) {
+    const uint32_t m = gballot<G>(p);
+    *total = static_cast<uint32_t>(popc(m));
+    return static_cast<uint32_t>(popc(m & ((1u << glane<G>()) - 1u)));
+}
+template <int G> RP_DEV uint32_t gincl_sum(uint32_t v) {
+    const int l = glane<G>();
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        uint32_t o = gshfl_up<G>(v, d);
+        if (l >= d) v += o;
+    }
+    return v;
+}
+template <int G> RP_DEV int32_t gincl_max(int32_t v) {
+    const int l = glane<G>();
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        int32_t o = gshfl_up<G>(v, d);
         if (l >= d && o > v) v = o;
     }
     return v;

@@ -40,9 +40,10 @@ void aln_entry(void* arg) {
     rp::aln_pair(*j->P, j->p, j->slot);
 }
 
-void warp_entry(void* arg) {
+template <int G>
+void group_entry(void* arg) {
     Job* j = static_cast<Job*>(arg);
-    rp::poa_window(*j->P, j->w, j->slot, j->smem);
+    rp::poa_window<G>(*j->P, j->w, j->slot, j->smem);
 }
 
 }  // namespace
@@ -155,7 +156,9 @@ int rp_sim_pack_only(uint32_t n_windows, const char* bases, const char* quals, c
     return static_cast<int>(pb.n_gpu());
 }
 
-/* Flat window set in, consensus out.  limits: {nmax, lmax, ki, ka, smem_per_warp, tile_rows, debug_flags}.  Returns 0 or <0. */
+/* Flat window set in, consensus out.  limits: {nmax, lmax, ki, ka, smem_per_group, tile_rows, debug_flags,
+ * lanes per group (8/16/32), banded, band margin, matrix scratch cells (0 = nmax x padded lmax)}.  With banded,
+ * stats[4] = alignments tried in the band, stats[5] = redone with the full matrix.  Returns 0 or <0. */
 int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
                const uint8_t* seq_has_qual, const uint32_t* seq_begin, const uint32_t* seq_end,
                const uint32_t* win_first, const uint8_t* win_type, int8_t match, int8_t mismatch, int8_t gap,
@@ -213,19 +216,29 @@ int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const u
     P.lim.ki = limits[2];
     P.lim.ka = limits[3];
     P.lim.stack_cap = limits[0] * 4 + 64;
+    P.lim.hcap = limits[10] ? limits[10] : (limits[0] + 1) * P.lim.lp;
     P.lay = rp::make_layout(P.lim);
-    P.smem_per_warp = limits[4];
+    P.smem_per_group = limits[4];
     P.tile_rows = limits[5];
     P.debug_flags = limits[6];
+    const uint32_t lanes = limits[7] ? limits[7] : 32;
+    P.banded = limits[8];
+    P.band_margin = limits[9];
+    P.band_stats = (stats && P.banded) ? reinterpret_cast<unsigned long long*>(stats + 4) : nullptr;
     std::vector<uint8_t> slot(P.lay.bytes + 64);
-    std::vector<uint8_t> smem(P.smem_per_warp + 64);
+    std::vector<uint8_t> smem(P.smem_per_group + 64);
     uint8_t* slot_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(slot.data()) + 15) & ~uintptr_t(15));
     uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
     P.scratch = slot_al;
 
     for (uint32_t q = 0; q < pb.n_gpu(); ++q) {
         Job job{&P, pb.queue.data[q], slot_al, smem_al};
-        rp::sim::run_warp(warp_entry, &job);
+        if (lanes == 8)
+            rp::sim::run_warp(group_entry<8>, &job, 256 * 1024, 8);
+        else if (lanes == 16)
+            rp::sim::run_warp(group_entry<16>, &job, 256 * 1024, 16);
+        else
+            rp::sim::run_warp(group_entry<32>, &job, 256 * 1024, 32);
     }
 
     for (uint32_t w = 0; w < n_windows; ++w) {

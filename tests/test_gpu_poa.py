@@ -35,9 +35,10 @@ def _mk(name, seed):
     return ws
 
 
-def _compare(ws, scores=(3, -5, -4), trim=True, window_length=500):
+def _compare(ws, scores=(3, -5, -4), trim=True, window_length=500, banded=False, band_stats=None):
     m, x, g = scores
-    cons, pol, st, covs = api.consensus(ws, m, x, g, trim=trim, window_length=window_length, want_coverage=True)
+    cons, pol, st, covs = api.consensus(ws, m, x, g, trim=trim, window_length=window_length, want_coverage=True,
+                                        banded=banded, band_stats=band_stats)
     ora, opol, _, ocov = ob.oracle_consensus(ws, m, x, g, trim=trim, threads=os.cpu_count() or 4, want_coverage=True)
     assert (st == 0).all(), "device limit statuses: %s" % np.unique(st)
     bad = [w for w in range(ws.n_windows) if cons[w] != ora[w]]
@@ -48,15 +49,60 @@ def _compare(ws, scores=(3, -5, -4), trim=True, window_length=500):
             assert (covs[w].astype(np.uint32) == ocov[w]).all(), "coverage differs on window %d" % w
 
 
+@pytest.mark.parametrize("banded", [False, True], ids=["full", "banded"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_gpu_equals_oracle(name):
-    _compare(_mk(name, seed=101), window_length=1000 if name == "long_layers" else 500)
+def test_gpu_equals_oracle(name, banded):
+    """racon -b (banded=True) must return exactly what the full matrix returns: every alignment whose band result the
+    device-side check refuses is redone with the full matrix on the device."""
+    _compare(_mk(name, seed=101), window_length=1000 if name == "long_layers" else 500, banded=banded)
 
 
+@pytest.mark.parametrize("banded", [False, True], ids=["full", "banded"])
 @pytest.mark.parametrize("scores", [(5, -4, -8), (1, -1, -1)])
-def test_gpu_equals_oracle_other_scores(scores):
-    _compare(_mk("partial_qual", seed=55), scores=scores)
-    _compare(_mk("higherr", seed=56), scores=scores)
+def test_gpu_equals_oracle_other_scores(scores, banded):
+    _compare(_mk("partial_qual", seed=55), scores=scores, banded=banded)
+    _compare(_mk("higherr", seed=56), scores=scores, banded=banded)
+
+
+@pytest.mark.parametrize("banded", [False, True], ids=["full", "banded"])
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_gpu_every_group_width(lanes, banded, monkeypatch):
+    """The kernel is compiled for 8, 16 and 32 lanes per window (RP_POA_GROUP); all of them, banded or not, are exact."""
+    monkeypatch.setenv("RP_POA_GROUP", str(lanes))
+    stats = {}
+    _compare(_mk("partial", seed=33), banded=banded, band_stats=stats)
+    _compare(_mk("fullspan", seed=34), banded=banded, band_stats=stats)
+    if banded:
+        assert stats["band_alignments"] > 0 and stats["band_width"] == 16 * lanes
+
+
+def test_gpu_band_refusals_are_redone_with_the_full_matrix(monkeypatch):
+    """Layers with 110-base deletions / 120-base insertions leave a 128-column band: the device-side check must refuse
+    those band results (counted), redo them with the full matrix, and the consensus must still equal the oracle's.  A
+    margin wider than the band refuses everything."""
+    rng = np.random.default_rng(5)
+    wins = []
+    for _ in range(24):
+        truth = bytes(b"ACGT"[i] for i in rng.integers(4, size=500))
+        bb = util.mutate(rng, truth, 0.1)[:500]
+        win = [(bb, None, 0, 0)]
+        for d in range(12):
+            r = util.mutate(rng, truth, 0.1)
+            if d % 3 == 0:
+                r = r[:150] + r[260:]
+            if d % 3 == 1:
+                r = r[:200] + bytes(b"ACGT"[i] for i in rng.integers(4, size=120)) + r[200:]
+            win.append((r, None, 0, len(bb) - 1))
+        wins.append(win)
+    ws = windows.from_lists(wins)
+    monkeypatch.setenv("RP_POA_GROUP", "8")
+    stats = {}
+    _compare(ws, banded=True, band_stats=stats)
+    assert 0 < stats["band_redone_full"] < stats["band_alignments"]
+    monkeypatch.setenv("RP_BAND_MARGIN", "60")
+    stats = {}
+    _compare(_mk("fullspan", seed=35), banded=True, band_stats=stats)
+    assert stats["band_redone_full"] == stats["band_alignments"] > 0
 
 
 def test_gpu_no_trim_and_trivial_windows():
@@ -66,11 +112,12 @@ def test_gpu_no_trim_and_trivial_windows():
     assert cons == [b"ACGTACGT", b"AC"] and not pol.any() and (st == 0).all()
 
 
+@pytest.mark.parametrize("banded", [False, True], ids=["full", "banded"])
 @pytest.mark.parametrize("err,n,expect", KAT)
-def test_gpu_known_answer_checksums_of_the_reference(err, n, expect):
+def test_gpu_known_answer_checksums_of_the_reference(err, n, expect, banded):
     """FNV-1a-64 over the consensus of the SURVEY.md §8(d) synthetic windows, as produced by the reference."""
     ws, _ = windows.synth_windows(n, err=err)
-    cons, pol, st = api.consensus(ws)
+    cons, pol, st = api.consensus(ws, banded=banded)
     assert (st == 0).all() and pol.all()
     assert "%016x" % windows.fnv1a64(cons) == expect
 

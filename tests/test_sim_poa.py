@@ -173,3 +173,68 @@ def test_sim_windows_whose_matrix_leaves_int16_are_reported():
     # and a gap beyond the packed-int16 design limit is refused up front
     _, pol, st, _, _ = simlib.sim_consensus(util.make_set(24, 2, wlen=100, depth=5, err=0.1), 3, -5, -100)
     assert (st == 4).all() and not pol.any()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# lane groups (8 / 16 lanes per window) and the banded DP of racon -b, same device code, same oracle
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lanes", [8, 16])
+@pytest.mark.parametrize("name", ["fullspan_small", "partial_qual", "higherr_ties", "multichunk", "ngs"])
+def test_sim_lane_groups_equal_oracle(name, lanes):
+    _check(_mk(name, seed=11), lanes=lanes, smem=14336 * lanes // 32)
+
+
+BAND_CASES = {
+    "w300": dict(n=2, wlen=300, depth=12, err=0.12),
+    "w500_partial_qual": dict(n=2, wlen=500, depth=16, err=0.12, partial_frac=0.4, with_qual=True),
+    "w200_higherr": dict(n=3, wlen=200, depth=16, err=0.3),
+    "w1000": dict(n=1, wlen=1000, depth=8, err=0.10, partial_frac=0.2),
+}
+
+
+@pytest.mark.parametrize("lanes", [8, 16])
+@pytest.mark.parametrize("name", sorted(BAND_CASES))
+def test_sim_banded_equals_oracle(name, lanes):
+    kw = dict(BAND_CASES[name])
+    ws = util.make_set(7, kw.pop("n"), **kw)
+    stats = _check(ws, lanes=lanes, smem=14336 * lanes // 32, banded=1, nmax=8192, lmax=2047)
+    if 16 * lanes < kw["wlen"] // 2:
+        assert stats[4] > 0, "no alignment went through the band"
+
+
+@pytest.mark.parametrize("scores", [(5, -4, -8), (1, -1, -1)])
+def test_sim_banded_other_scores(scores):
+    ws = util.make_set(8, 2, wlen=400, depth=12, err=0.15, partial_frac=0.3, with_qual=True)
+    _check(ws, scores=scores, lanes=8, smem=3584, banded=1)
+
+
+def test_sim_band_refusal_redoes_the_alignment_with_the_full_matrix():
+    """(a) a margin wider than the band refuses every band result; (b) layers with a 110-base deletion or a 120-base
+    insertion leave a 128-column band.  Both must fall back to the full matrix on the spot and stay exact."""
+    ws = util.make_set(9, 2, wlen=400, depth=10, err=0.12, partial_frac=0.3)
+    stats = _check(ws, lanes=8, smem=3584, banded=1, band_margin=56)
+    assert stats[4] > 0 and stats[5] == stats[4]
+    rng = np.random.default_rng(5)
+    wins = []
+    for _ in range(2):
+        truth = bytes(b"ACGT"[i] for i in rng.integers(4, size=500))
+        bb = util.mutate(rng, truth, 0.1)[:500]
+        win = [(bb, None, 0, 0)]
+        for d in range(9):
+            r = util.mutate(rng, truth, 0.1)
+            if d % 3 == 0:
+                r = r[:150] + r[260:]
+            if d % 3 == 1:
+                r = r[:200] + bytes(b"ACGT"[i] for i in rng.integers(4, size=120)) + r[200:]
+            win.append((r, None, 0, len(bb) - 1))
+        wins.append(win)
+    from racon_b200 import windows
+    stats = _check(windows.from_lists(wins), lanes=8, smem=3584, banded=1, nmax=8192, lmax=2047)
+    assert 0 < stats[5] < stats[4]
+
+
+def test_sim_matrix_scratch_limit_is_reported():
+    """A score matrix larger than the per-window scratch gets RP_WIN_MATRIX_LIMIT (the GPU escalation pass re-runs it)."""
+    ws = _mk("fullspan_small", seed=4)
+    _, pol, st, _, _ = simlib.sim_consensus(ws, hcap=20000)
+    assert (st == 9).all() and not pol.any()
