@@ -119,8 +119,10 @@ rp_status rp_poa_enable_counters(rp_poa* p, int on);
 /* racon -b / --cuda-banded-alignment (createCUDABatch's `banded`, cudabatch.cpp:56-59): after a run,
  * info[0] = 1 when the object is banded, [1] alignments tried inside the band, [2] alignments whose band result
  * was refused by the device-side check and that were redone with the full matrix on the device, [3] band width
- * in columns.  Banded and unbanded objects return identical results (tests/test_gpu_poa.py). */
-rp_status rp_poa_band_info(rp_poa* p, uint64_t info[4]);
+ * in columns, [4] (only with the environment variable RP_BAND_AUDIT=1, a test mode that recomputes every accepted
+ * band result with the full matrix) accepted band alignments that differ from the full-matrix alignment.
+ * Banded and unbanded objects return identical results (tests/test_gpu_poa.py). */
+rp_status rp_poa_band_info(rp_poa* p, uint64_t info[8]);
 
 /* ------------------------------------------------------------------------------------------------
  * Pre-alignment batch — replaces racon::CUDABatchAligner (src/cuda/cudaaligner.hpp:21-92) and the

@@ -21,7 +21,7 @@ class RaconB200Error(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(build.LIBDIR, "libracon_b200.so")
+    return os.environ.get("RACON_B200_LIB") or os.path.join(build.LIBDIR, "libracon_b200.so")
 
 
 def load(build_if_missing=True):
@@ -30,7 +30,7 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing:
+    if build_if_missing and not os.environ.get("RACON_B200_LIB"):
         try:
             path = build.build_cuda()
         except Exception:
@@ -207,10 +207,10 @@ class PoaBatch:
 
     def band_info(self):
         """racon -b bookkeeping of the last run: alignments tried inside the band / redone with the full matrix."""
-        a = (C.c_uint64 * 4)()
+        a = (C.c_uint64 * 8)()
         _check(self.lib, self.lib.rp_poa_band_info(self.h, a), "rp_poa_band_info")
         return {"banded": bool(a[0]), "band_alignments": int(a[1]), "band_redone_full": int(a[2]),
-                "band_width": int(a[3])}
+                "band_width": int(a[3]), "band_audit_mismatches": int(a[4])}
 
     def fetch_all(self, stride):
         n = self.size()

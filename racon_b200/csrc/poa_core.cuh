@@ -926,11 +926,7 @@ struct PoaWarp {
     /* H[r][c] of the last DP, whichever layout it used (full rows of pitch lpa, or band rows) */
     template <bool BAND>
     RP_DEV int32_t hcell(uint32_t lpa, uint32_t r, uint32_t c) const {
-        if (!BAND) return H[static_cast<uint64_t>(r) * lpa + perm(c)];
-        if (r == 0) return static_cast<int32_t>(c) * P->gap;
-        const uint32_t cbk = c >> 4;
-        if (cbk - bs[r] >= G) return kBandFloor;
-        return H[static_cast<uint64_t>(r) * kCC + ((cbk & (G - 1)) << 4) + (perm(c) & 15u)];
+        return hcell_at<BAND>(H, bs, P->gap, lpa, r, c);
     }
 
     /* ---------------------------------------------------------------- spoa's DFS order (graph.cpp:249-303)
@@ -1137,9 +1133,21 @@ struct PoaWarp {
      * the optimal paths stay inside; the margin test is the (heuristic) evidence that they do. */
     /* > G predecessors (escalated windows only): every diagonal candidate of every batch outranks any
      * vertical one.  Reads straight from the HBM copy; kept out of line so the common loop stays small. */
-    RP_DEV_NOINLINE int traceback_step_wide(uint32_t i, uint32_t j, uint32_t npe, int32_t hij, int32_t mc,
-                                            uint32_t lpa, uint32_t* found) {
-        const int32_t g = P->gap;
+    /* static + explicit arguments: a non-inlined MEMBER would take `this`, forcing the whole PoaWarp into local memory */
+    template <bool BAND>
+    static RP_DEV int32_t hcell_at(const int16_t* H, const uint8_t* bs, int32_t g, uint32_t lpa, uint32_t r, uint32_t c) {
+        if (!BAND) return H[static_cast<uint64_t>(r) * lpa + perm(c)];
+        if (r == 0) return static_cast<int32_t>(c) * g;
+        const uint32_t cbk = c >> 4;
+        if (cbk - bs[r] >= G) return kBandFloor;
+        return H[static_cast<uint64_t>(r) * kCC + ((cbk & (G - 1)) << 4) + (perm(c) & 15u)];
+    }
+
+    template <bool BAND>
+    static RP_DEV_NOINLINE int traceback_step_wide(const int16_t* H, const uint8_t* bs, const Rec* rec,
+                                                   const uint16_t* pred_ovf, uint32_t ki, int lane, int32_t g, uint32_t i,
+                                                   uint32_t j, uint32_t npe, int32_t hij, int32_t mc, uint32_t lpa,
+                                                   uint32_t* found) {
         for (int pass = 1; pass <= 2; ++pass) {
             if (pass == 1 && j == 0) continue;
             for (uint32_t k0 = 0; k0 < npe; k0 += G) {
@@ -1148,16 +1156,39 @@ struct PoaWarp {
                 bool ok = false;
                 if (k < npe) {
                     p = k < 7 ? rec_pred(rec[i], k) : pred_ovf[i * ki + k];
-                    ok = pass == 1 ? (hij == hcell<false>(lpa, p, j - 1) + mc) : (hij == hcell<false>(lpa, p, j) + g);
+                    ok = pass == 1 ? (hij == hcell_at<BAND>(H, bs, g, lpa, p, j - 1) + mc)
+                                   : (hij == hcell_at<BAND>(H, bs, g, lpa, p, j) + g);
                 }
-                const uint32_t msk = ballot(ok);
+                const uint32_t msk = gballot<G>(ok);
                 if (msk) {
-                    *found = shfl(p, ffs_(msk) - 1);
+                    *found = gshfl<G>(p, ffs_(msk) - 1);
                     return pass;
                 }
             }
         }
         return 0;
+    }
+
+    /* banded walk, more predecessors than lanes: true when some candidate cell is closer than the margin to an edge
+     * that cuts its own row's band (see traceback) */
+    static RP_DEV_NOINLINE bool wide_candidates_unsure(const uint8_t* bs, const Rec* rec, const uint16_t* pred_ovf,
+                                                       uint32_t ki, int lane, uint32_t i, uint32_t j, uint32_t npe,
+                                                       uint32_t nblk, uint32_t margin) {
+        bool unsure = false;
+        for (uint32_t k0 = 0; k0 < npe; k0 += G) {
+            const uint32_t k = k0 + lane;
+            if (k < npe) {
+                const uint32_t p = k < 7 ? rec_pred(rec[i], k) : pred_ovf[i * ki + k];
+                if (p != 0) {
+                    const uint32_t sp = bs[p];
+                    const int32_t dlp = static_cast<int32_t>(j) - 1 - static_cast<int32_t>(16u * sp);
+                    const int32_t drp = static_cast<int32_t>(16u * (sp + G)) - 1 - static_cast<int32_t>(j);
+                    unsure |= (sp > 0 && dlp < static_cast<int32_t>(margin)) ||
+                              (sp + G < nblk && drp < static_cast<int32_t>(margin));
+                }
+            }
+        }
+        return gballot<G>(unsure) != 0;
     }
 
     static constexpr uint32_t kTileCols = 32;
@@ -1247,20 +1278,36 @@ struct PoaWarp {
             if (npe <= G) {
                 /* one predecessor per lane; all diagonal candidates outrank any vertical one (sisd :392-442) */
                 uint32_t p = 0;
-                bool okd = false, okv = false;
+                bool okd = false, okv = false, unsure = false;
                 if (static_cast<uint32_t>(lane) < npe) {
                     if (np) p = static_cast<uint32_t>(lane) < 7 ? rec_pred(rc, lane) : pred_ovf[i * ki + lane];
                     int32_t a = 0, b;
+                    uint32_t sp = 0;
                     if (p + t_rows > t_top) {  // predecessor row is inside the tile
                         const int16_t* pr = tile + (t_top - p) * kTileCols;
                         a = pr[ejm];
                         b = pr[ej];
+                        if (BAND) sp = tbs[t_top - p];
                     } else {
                         a = hcell<BAND>(lpa, p, j > 0 ? j - 1 : 0);
                         b = hcell<BAND>(lpa, p, j);
+                        if (BAND) sp = bs[p];
                     }
                     okd = j > 0 && hij == a + mc;
                     okv = hij == b + g;
+                    if (BAND && p != 0) {
+                        /* the candidate cells (p, j-1), (p, j) must be trustworthy too: a predecessor whose own band is
+                         * cut closer than the margin to these columns (or does not hold them at all) could hide a tie
+                         * the full matrix would have resolved the other way */
+                        const int32_t dlp = static_cast<int32_t>(j) - 1 - static_cast<int32_t>(16u * sp);
+                        const int32_t drp = static_cast<int32_t>(16u * (sp + G)) - 1 - static_cast<int32_t>(j);
+                        unsure = (sp > 0 && dlp < static_cast<int32_t>(margin)) ||
+                                 (sp + G < nblk && drp < static_cast<int32_t>(margin));
+                    }
+                }
+                if (BAND && ballot(unsure)) {  // group-uniform
+                    bad = true;
+                    break;
                 }
                 const uint32_t md = ballot(okd);
                 const uint32_t mv = ballot(okv);
@@ -1270,7 +1317,11 @@ struct PoaWarp {
                     move = md ? 1 : 2;
                 }
             } else {
-                move = traceback_step_wide(i, j, npe, hij, mc, lpa, &found_p);
+                if (BAND && wide_candidates_unsure(bs, rec, pred_ovf, ki, lane, i, j, npe, nblk, margin)) {
+                    bad = true;
+                    break;
+                }
+                move = traceback_step_wide<BAND>(H, bs, rec, pred_ovf, ki, lane, g, i, j, npe, hij, mc, lpa, &found_p);
             }
             if (!move) move = 3;
             if (move == 1) {
@@ -1871,6 +1922,13 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
             }
             if (W.status != kWinOk) break;
         }
+        /* tests only (debug_flags bit 1): every accepted band result is recomputed with the full matrix and compared */
+        const bool audit = done && (P.debug_flags & 2u) && static_cast<uint64_t>(nrows + 1) * lpa <= P.lim.hcap;
+        if (audit) {
+            for (uint32_t c = lane; c < len; c += G) W.cur[c] = W.aln[c];
+            W.syncwarp();
+            done = false;
+        }
         if (!done) {
             if (static_cast<uint64_t>(nrows + 1) * lpa > P.lim.hcap) {
                 W.fail(kWinMatrixLimit);
@@ -1886,6 +1944,17 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
                 if (W.status != kWinOk) break;
             }
             W.template traceback<false>(best_row, len, lpa, seq, sub, 0);
+            if (audit) {
+                bool diff = false;
+                for (uint32_t c = lane; c < len; c += G) diff |= W.cur[c] != W.aln[c];
+                if (W.ballot(diff) && lane == 0 && P.band_stats) {
+#if !defined(RP_HOST_SIM)
+                    atomicAdd(P.band_stats + 2, 1ull);
+#else
+                    P.band_stats[2] += 1;
+#endif
+                }
+            }
         }
         W.add_alignment(seq, wts, len, b0);
         if (P.stats) pred_rows = W.warp_incl_sum(pred_rows);

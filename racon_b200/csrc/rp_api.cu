@@ -181,7 +181,8 @@ struct rp_poa {
     bool counters = false;
     uint64_t launches = 0, last_h2d = 0, last_d2h = 0;
     int banded = 0;
-    uint64_t h_band[2] = {0, 0};   // alignments tried in the band / redone with the full matrix (last launch)
+    uint32_t configured_wl = 0;    // window length the scratch is sized for (0 = not yet: sized at the first upload)
+    uint64_t h_band[4] = {0, 0, 0, 0};   // alignments tried in the band / redone with the full matrix (last launch)
     /* escalation pass for windows that exceeded a device limit (never a CPU re-run) */
     DevBuf d_scratch_big, d_queue_big;
     rp::PoaLimits lim_big;
@@ -196,6 +197,8 @@ struct rp_poa {
 };
 
 extern "C" {
+
+static rp_status configure(rp_poa* p, uint32_t wl);
 
 const char* rp_strerror(rp_status s) {
     switch (s) {
@@ -239,13 +242,50 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
         delete p;
         return fail(RP_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, device);
+    p->P.match = match;
+    p->P.mismatch = mismatch;
+    p->P.gap = gap;
+    p->P.banded = banded ? 1 : 0;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (mem_bytes == 0 || mem_bytes > free_b) mem_bytes = static_cast<size_t>(free_b * 0.8);
+    p->mem_budget = mem_bytes;
+    /* batch limits from the budget (a quarter of it holds the batch's inputs and outputs on the device) */
+    const uint64_t io_budget = mem_bytes / 4;
+    p->batch.max_seq_len = 65000;
+    p->batch.max_bases = std::min<uint64_t>(0xfff00000ull, std::max<uint64_t>(io_budget / 4, 1u << 16));
+    p->batch.max_out = std::min<uint64_t>(0xfff00000ull, std::max<uint64_t>(io_budget / 8, 1u << 14));
+    p->batch.max_windows = static_cast<uint32_t>(std::min<uint64_t>(1u << 22, std::max<uint64_t>(io_budget / 4096, 16)));
+    e = p->d_head.reserve(256);
+    if (e == cudaSuccess) e = p->d_stats.reserve(256);
+    if (e != cudaSuccess) {
+        rp_poa_destroy(p);
+        return fail(RP_ERR_NOMEM, std::string("allocation: ") + cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(p->d_stats.p, 0, 256, p->stream);
+    /* window_len_hint == 0: the per-window scratch is sized at the first upload from the longest backbone seen
+     * (racon's createCUDABatch does not pass -w, cudabatch.cpp:23-72) */
+    if (window_len_hint) {
+        rp_status cs = configure(p, window_len_hint);
+        if (cs != RP_OK) {
+            rp_poa_destroy(p);
+            return cs;
+        }
+    }
+    *out = p;
+    return RP_OK;
+}
 
-    const uint32_t wl = window_len_hint ? window_len_hint : 500;
+/* Sizes the per-window limits, the launch shape and the workers' scratch for windows of length wl. */
+static rp_status configure(rp_poa* p, uint32_t wl) {
+    cudaError_t e = cudaSuccess;
+    const size_t mem_bytes = p->mem_budget;
+    const int banded = p->banded;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, p->device);
+    p->d_scratch.release();
+    p->d_scratch_big.release();
+    p->workers_big = 0;
     rp::PoaLimits lim;
     lim.nmax = std::min<uint32_t>(65000, std::max<uint32_t>(1024, 6 * wl + 64));
     lim.lmax = std::min<uint32_t>(16000, 2 * wl + 23);
@@ -253,18 +293,18 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     lim.ki = 16;
     lim.ka = 8;
     lim.stack_cap = lim.nmax * 4 + 64;
-    p->P.match = match;
-    p->P.mismatch = mismatch;
-    p->P.gap = gap;
-    p->P.banded = banded ? 1 : 0;
     p->P.band_margin = 16;
     if (const char* e_m = getenv("RP_BAND_MARGIN")) p->P.band_margin = static_cast<uint32_t>(atoi(e_m));
+    /* tests only: recompute every accepted band result with the full matrix and count the differences */
+    if (const char* e_a = getenv("RP_BAND_AUDIT")) p->P.debug_flags = atoi(e_a) ? 2u : 0u;
 
     /* launch shape: persistent blocks of 4 warps = 128/G lane groups, kBlocksPerSm blocks per SM */
-    int group = banded ? 8 : 16;
+    int group = banded ? 8 : 32;
     if (const char* e_g = getenv("RP_POA_GROUP")) group = atoi(e_g);
-    if (group != 8 && group != 16 && group != 32) group = banded ? 8 : 16;
-    int bps = 4;
+    if (group != 8 && group != 16 && group != 32) group = banded ? 8 : 32;
+    /* measured on B200 (profiles/README.md, round 2): full matrix: 32 lanes per window, 4 blocks/SM; banded: 8 lanes per
+     * window (128-column band), 3 blocks/SM */
+    int bps = (banded && group == 8) ? 3 : 4;
     if (const char* e_bps = getenv("RP_BLOCKS_PER_SM")) bps = atoi(e_bps);
     if (bps != 2 && bps != 3 && bps != 6) bps = 4;
     p->group = group;
@@ -281,10 +321,8 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     int occ = 0;
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, p->kernel, kWarpsPerBlock * 32, p->smem_block);
-    if (e != cudaSuccess || occ < 1) {
-        rp_poa_destroy(p);
+    if (e != cudaSuccess || occ < 1)
         return fail(RP_ERR_CUDA, std::string("kernel configuration: ") + cudaGetErrorString(e));
-    }
     /* Device-memory budget of this object (cudabatch.cpp:23-72 passes 0.9 * free / batches): half for the
      * per-window scratch of the workers, a quarter for the lazily allocated escalation pass, a quarter for the
      * batch itself (inputs + outputs) — the batch limits below are what makes add_window return RP_BATCH_FULL. */
@@ -309,27 +347,15 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     p->P.lim = lim;
     p->P.lay = rp::make_layout(lim);
     uint64_t fit = scratch_budget / p->P.lay.bytes;
-    if (fit < p->groups_per_block) {
-        rp_poa_destroy(p);
-        return fail(RP_ERR_NOMEM, "memory budget too small for one block of POA workers");
-    }
+    if (fit < p->groups_per_block) return fail(RP_ERR_NOMEM, "memory budget too small for one block of POA workers");
     uint64_t workers = std::min(max_workers, fit) / p->groups_per_block * p->groups_per_block;
     p->workers = static_cast<uint32_t>(workers);
     p->grid = static_cast<int>(workers / p->groups_per_block);
     e = p->d_scratch.reserve(workers * p->P.lay.bytes);
-    if (e == cudaSuccess) e = p->d_head.reserve(256);
-    if (e == cudaSuccess) e = p->d_stats.reserve(256);
     if (e != cudaSuccess) {
-        rp_poa_destroy(p);
+        cudaGetLastError();
         return fail(RP_ERR_NOMEM, std::string("scratch allocation: ") + cudaGetErrorString(e));
     }
-    cudaMemsetAsync(p->d_stats.p, 0, 256, p->stream);
-    p->batch.max_seq_len = 65000;
-    p->mem_budget = mem_bytes;
-    const uint64_t io_budget = mem_bytes / 4;
-    p->batch.max_bases = std::min<uint64_t>(0xfff00000ull, std::max<uint64_t>(io_budget / 4, 1u << 16));
-    p->batch.max_out = std::min<uint64_t>(0xfff00000ull, std::max<uint64_t>(io_budget / 8, 1u << 14));
-    p->batch.max_windows = static_cast<uint32_t>(std::min<uint64_t>(1u << 22, std::max<uint64_t>(io_budget / 4096, 16)));
     p->lim_big = lim;
     p->lim_big.nmax = std::min<uint32_t>(65000, lim.nmax * 8);
     p->lim_big.lmax = std::min<uint32_t>(16000, lim.lmax * 4);
@@ -340,7 +366,7 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     p->lim_big.hcap = static_cast<uint32_t>(
         std::min<uint64_t>(0xfffffff0ull, static_cast<uint64_t>(p->lim_big.nmax + 1) * p->lim_big.lp));
     p->lay_big = rp::make_layout(p->lim_big);
-    *out = p;
+    p->configured_wl = wl;
     return RP_OK;
 }
 
@@ -455,6 +481,16 @@ rp_status rp_poa_upload(rp_poa* p) {
     rp::PackedBatch& b = p->batch;
     if (!b.build_queue()) return fail(RP_ERR_NOMEM, "queue allocation failed");
     const uint32_t n = b.n_gpu();
+    if (!p->configured_wl) {
+        uint32_t wl = 0;
+        for (uint32_t w = 0; w < n; ++w) {
+            const uint32_t s0 = b.win_first.data[w];
+            wl = std::max(wl, b.seq_off.data[s0 + 1] - b.seq_off.data[s0]);
+        }
+        wl = std::max<uint32_t>(100, (wl + 99) / 100 * 100);
+        rp_status cs = configure(p, wl);
+        if (cs != RP_OK) return cs;
+    }
     uint64_t h2d = 0;
     auto up = [&](DevBuf& d, const void* src, size_t bytes) -> cudaError_t {
         cudaError_t e = d.reserve(bytes ? bytes : 16);
@@ -514,7 +550,7 @@ rp_status rp_poa_launch(rp_poa* p) {
     RP_CUDA(cudaSetDevice(p->device));
     if (p->P.n_windows > 0) {
         RP_CUDA(cudaMemsetAsync(p->d_head.p, 0, 4, p->stream));
-        RP_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(p->d_stats.p) + 128, 0, 16, p->stream));
+        RP_CUDA(cudaMemsetAsync(static_cast<uint8_t*>(p->d_stats.p) + 128, 0, 32, p->stream));
         p->P.stats = p->counters ? static_cast<uint64_t*>(p->d_stats.p) : nullptr;
         p->P.band_stats = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(p->d_stats.p) + 128);
         const uint32_t need_blocks = (p->P.n_windows + p->groups_per_block - 1) / p->groups_per_block;
@@ -545,7 +581,7 @@ rp_status rp_poa_download(rp_poa* p) {
     if (p->counters)
         RP_CUDA(cudaMemcpyAsync(p->h_stats, p->d_stats.p, 64, cudaMemcpyDeviceToHost, p->stream));
     if (p->banded && n > 0)
-        RP_CUDA(cudaMemcpyAsync(p->h_band, static_cast<uint8_t*>(p->d_stats.p) + 128, 16, cudaMemcpyDeviceToHost,
+        RP_CUDA(cudaMemcpyAsync(p->h_band, static_cast<uint8_t*>(p->d_stats.p) + 128, 32, cudaMemcpyDeviceToHost,
                                 p->stream));
     p->last_d2h = d2h;
     p->downloaded = true;
@@ -708,14 +744,16 @@ rp_status rp_poa_info(rp_poa* p, uint64_t info[8]) {
     return RP_OK;
 }
 
-rp_status rp_poa_band_info(rp_poa* p, uint64_t info[4]) {
+rp_status rp_poa_band_info(rp_poa* p, uint64_t info[8]) {
     if (!p || !info) return fail(RP_ERR_INVALID, "null argument");
     rp_status s = ensure_results(p);
     if (s != RP_OK) return s;
+    std::memset(info, 0, 8 * sizeof(uint64_t));
     info[0] = p->banded ? 1 : 0;
     info[1] = p->h_band[0];
     info[2] = p->h_band[1];
     info[3] = static_cast<uint64_t>(p->group) * 16;
+    info[4] = p->h_band[2];
     return RP_OK;
 }
 

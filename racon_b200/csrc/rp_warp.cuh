@@ -271,10 +271,16 @@ template <int G> RP_DEV bool any_converged_peer(bool p) { return ballot(p) != 0;
 template <int G> RP_DEV int glane() { return static_cast<int>(threadIdx.x & (G - 1)); }
 template <int G> RP_DEV uint32_t gbase() { return (threadIdx.x & 31u) & ~static_cast<uint32_t>(G - 1); }
 template <int G> RP_DEV uint32_t gmask() {
+#if defined(RP_EXPERIMENT_FULLMASK)
+    return kFull;   // experiment only: legal only while all groups of a warp follow the same control flow
+#else
     return G == 32 ? kFull : (((1u << (G & 31)) - 1u) << gbase<G>());
+#endif
 }
 template <int G> RP_DEV void gsync() { __syncwarp(gmask<G>()); }
-template <int G> RP_DEV uint32_t gballot(bool p) { return __ballot_sync(gmask<G>(), p) >> gbase<G>(); }
+template <int G> RP_DEV uint32_t gballot(bool p) {
+    return (__ballot_sync(gmask<G>(), p) >> gbase<G>()) & (G == 32 ? kFull : ((1u << (G & 31)) - 1u));
+}
 template <int G, typename T> RP_DEV T gshfl(T v, int src) { return __shfl_sync(gmask<G>(), v, src, G); }
 template <int G, typename T> RP_DEV T gshfl_up(T v, int d) { return __shfl_up_sync(gmask<G>(), v, d, G); }
 template <int G, typename T> RP_DEV T gshfl_down(T v, int d) { return __shfl_down_sync(gmask<G>(), v, d, G); }

@@ -16,6 +16,7 @@ ap.add_argument("--windows", type=int, default=4736)
 ap.add_argument("--launches", type=int, default=1)
 ap.add_argument("--err", type=float, default=0.12)
 ap.add_argument("--shape", default="ont", choices=["ont", "ngs", "real"])
+ap.add_argument("--banded", type=int, default=0)
 args = ap.parse_args()
 wl = 500
 if args.shape == "ont":
@@ -32,7 +33,7 @@ else:
                               backbone_qual=True)
     idx = np.arange(args.windows) % base
     ws = small.subset(idx)
-b = api.PoaBatch(window_length=wl)
+b = api.PoaBatch(window_length=wl, banded=bool(args.banded), mem_bytes=int(60e9))
 assert b.add_window_set(ws) == args.windows
 b.upload()
 b.launch()

@@ -15,11 +15,14 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--configs", default="0,32,4;0,16,4;0,8,4;1,16,4;1,8,4;1,8,3;1,8,2;0,8,3;0,16,3;1,16,3")
     ap.add_argument("--two-streams", action="store_true", help="also time launches alternating between two objects")
+    ap.add_argument("--replicate", type=int, default=1, help="every window this many times in a row (lock-step experiment)")
     args = ap.parse_args()
     import torch
     from racon_b200 import api, windows
-    ws, _ = windows.synth_windows(args.windows, err=0.12)
+    ws, _ = windows.synth_windows(args.windows // args.replicate, err=0.12)
     import numpy as np
+    if args.replicate > 1:
+        ws = ws.subset(np.repeat(np.arange(ws.n_windows), args.replicate))
     stride = int(2 * np.diff(ws.seq_off.astype(np.int64)).max() + 64)
     ref = None
     for cfg in args.configs.split(";"):
