@@ -1,18 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — 500-bp POA windows/s at 32x coverage (BASELINE.json metric), one process per GPU.
+"""bench.py — POA windows/s (BASELINE.json metric) on B200, one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (sm_100a kernels via the C ABI)
-  python bench.py --impl reference ...                           the reference's own CPU path (oracle/_ref)
-  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   one rank per GPU, windows sharded (weak scaling)
+  python bench.py [--config 2|3|4|5] [--gpus N] [--steps K] [--warmup W]   our arm (sm_100a kernels via the C ABI)
+  python bench.py --impl reference [--config ...] ...                      the reference's own CPU path (oracle/_ref)
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N             one rank per GPU
 
-A "step" = one pass of the hot path over one batch: BASELINE config 2, 10 000 synthetic windows, w=500,
-32 layers, 12 % ONT-like error, scores 3/-5/-4 (SURVEY.md §8d generator, seed 42).
-  value      : windows/s with the batch resident in HBM (kernel launches only), CUDA-event timed
-  e2e        : windows/s through the whole plugin call: add windows (host buffers -> pinned staging), rp_poa_run
-               (H2D + kernel + D2H), rp_poa_fetch_all
-  roofline   : algorithmic bytes (2 B x sum (L+1)[(N+1)+E], counted by the kernel's own
-               device counters in a separate untimed launch) / kernel time, against the measured HBM peak
-  cpu_baseline: the unmodified reference (oracle/_ref) on the host cores, bounded sample (rank 0, N=1)
+Workloads (BASELINE.json `configs`; the default is config 2, the one the metric is quoted on at one GPU):
+  2  synthetic 10k windows per GPU, w=500, 32 layers, 12 % ONT-like error, 3/-5/-4, full matrix   (weak scaling)
+  3  synthetic 100k windows IN TOTAL, same shape, racon -b (banded), one stream cut into contiguous cost-balanced
+     ranges, one per rank                                                          (strong scaling)
+  4  Illumina mode: w=200, 60 pieces of 150-base reads per window (partial-span => Subgraph path), qualities, kNGS;
+     50k windows per GPU                                                                           (weak scaling)
+  5  fragment correction (-f): 10-kb reads against themselves: batched pre-alignment (rp_aln_*, edlib-identical) ->
+     breaking points -> w=500 windows -> consensus; reports windows/s of the consensus stage and, under "aligner",
+     pairs/s and GCUPS of the pre-alignment kernel                                                 (weak scaling)
+
+A "step" = one pass of the hot path over the rank's batch.
+  value      : windows/s with the batch resident in HBM (kernel launches only), CUDA-event timed, max over ranks
+  e2e        : windows/s through the whole plugin call with HOST buffers: add windows (-> pinned staging), rp_poa_run
+               (H2D + kernel + D2H), rp_poa_fetch_all; at N > 1 plus the NCCL gather of the consensus
+  roofline   : algorithmic bytes (2 B x sum (L+1)[(N+1)+E], counted by the kernel's own device counters
+               in a separate untimed launch) / isolated kernel time, against the measured HBM peak
+  cpu_baseline: the unmodified reference (oracle/_ref) on the host cores, bounded sample (rank 0); its `gpu_reference`
+               is the reference's own CUDA path (GenomeWorks cudapoa, unmodified) on the SAME number of GPUs
 """
 import argparse
 import json
@@ -25,8 +35,23 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "synthetic 10k windows, w=500, 32x ONT-error reads (12%), m/x/g=3/-5/-4, seed 42"
-METRIC = "500-bp POA windows/sec at 32x coverage"
+CONFIGS = {
+    2: dict(workload="synthetic 10k windows, w=500, 32x ONT-error reads (12%), m/x/g=3/-5/-4, seed 42",
+            metric="500-bp POA windows/sec at 32x coverage", banded=False, windows=10000, scaling="weak", wl=500,
+            shape="ont"),
+    3: dict(workload="synthetic 100k windows in total, w=500, 32x ONT-error reads (12%), m/x/g=3/-5/-4, seed 42, "
+                     "--cuda-banded-alignment (-b), cost-balanced contiguous ranges per rank",
+            metric="500-bp POA windows/sec at 32x coverage", banded=True, windows=100000, scaling="strong", wl=500,
+            shape="ont"),
+    4: dict(workload="Illumina mode: w=200, 60 pieces of 150-base reads per window (0.5% substitutions, Phred 30-40, "
+                     "all partial-span), kNGS, m/x/g=3/-5/-4; 50k windows per GPU",
+            metric="200-bp POA windows/sec at 60x short-read coverage", banded=False, windows=50000, scaling="weak",
+            wl=200, shape="ngs"),
+    5: dict(workload="fragment correction (-f): synthetic 10-kb reads (12% error) overlapped with themselves, "
+                     "device pre-alignment + breaking points -> w=500 windows -> consensus",
+            metric="500-bp POA windows/sec, fragment correction", banded=False, windows=0, scaling="weak", wl=500,
+            shape="frag"),
+}
 
 
 def env_int(name, default):
@@ -52,12 +77,13 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """Per-launch DRAM bytes of the POA kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic(cfg_id):
+    """Per-launch DRAM bytes of the POA kernel from the committed ncu --set full capture of this config, if any."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return json.load(f)
+            t = json.load(f)
+        return t.get("config%d" % cfg_id, t if cfg_id == 2 else None)
     except Exception:
         return None
 
@@ -113,24 +139,59 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------
+def make_windows(cfg_id, args, rank, world, sample=None):
+    """The window set of this rank for a step (and, for config 5, the overlaps the windows come from)."""
+    from racon_b200 import shard, windows
+    cfg = CONFIGS[cfg_id]
+    n = args.windows or cfg["windows"]
+    if cfg["shape"] == "ont" and cfg["scaling"] == "weak":
+        if sample is not None:
+            n = min(n, sample)
+        state = 42
+        for _ in range(rank):  # every rank draws ITS OWN stretch of the generator's stream
+            _, state = windows.synth_windows(n, err=0.12, state=state)
+        ws, _ = windows.synth_windows(n, err=0.12, state=state)
+        return ws, {"windows_total": n * world}
+    if cfg["shape"] == "ont":  # one stream for everybody, contiguous cost-balanced ranges (SURVEY.md §8e)
+        if sample is not None:
+            ws, _ = windows.synth_windows(min(n, sample), err=0.12, state=42)
+            return ws, {"windows_total": n}
+        full, _ = windows.synth_windows(n, err=0.12, state=42)
+        lo, hi = shard.shard_bounds_by_cost(windows.window_costs(full), rank, world)
+        return windows.slice_windows(full, lo, hi), {"windows_total": n, "range": [lo, hi]}
+    if cfg["shape"] == "ngs":
+        if sample is not None:
+            n = min(n, sample)
+        ws, _ = windows.synth_ngs_windows(n, state=4242 + 1000003 * rank)
+        return ws, {"windows_total": n * world}
+    raise SystemExit("bench.py: config %d has its own driver" % cfg_id)
+
+
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation (Window::generate_consensus over spoa, compiled unmodified
-    into oracle/_ref) on all host threads.  Each step = a bounded sample of the same workload."""
+    """The reference's own CPU implementation (Window::generate_consensus over spoa, compiled unmodified into
+    oracle/_ref) on all host threads.  Each step = a bounded sample of the same workload."""
     if rank != 0:
         return
     from oracle import bindings as ob
-    from racon_b200 import windows
+    cfg = CONFIGS[args.config]
     cores = host_cores()
     if not ob.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libracon_ref.so not built"}))
         return
-    n_sample = min(args.windows, 200 * cores)
-    ws, _ = windows.synth_windows(n_sample, err=0.12)
+    if cfg["shape"] == "frag":
+        ws = frag_workload(args, 0, sample_reads=min(24, args.frag_reads))["windows"]
+    else:
+        ws, _ = make_windows(args.config, args, 0, 1, sample=(200 if cfg["shape"] == "ont" else 1500) * cores)
+    n_sample = ws.n_windows
     # the reference scales poorly past the physical cores (allocator contention in spoa::Graph): give it the
     # better of "all hardware threads" and "half of them", decided on an untimed probe
     threads = cores
+    from racon_b200 import windows
     if cores >= 4:
-        probe = ws.subset(range(min(n_sample, 16 * cores)))
+        probe = windows.slice_windows(ws, 0, min(n_sample, 16 * cores))
         t_all = ob.ref_consensus(probe, threads=cores)[2]
         t_half = ob.ref_consensus(probe, threads=cores // 2)[2]
         threads = cores if t_all <= t_half else cores // 2
@@ -146,10 +207,10 @@ def run_reference(args, rank, world):
     sample = "%d of the workload's windows per step, %d host threads (of %d hardware threads; best of all/half), " \
              "consensus loop only" % (n_sample, threads, cores)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": "windows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample, "wall_s": wall},
+        "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "baseline_config": args.config, "sample": sample, "wall_s": wall},
         "cpu_baseline": {"value": value, "unit": "windows/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -157,13 +218,112 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# config 5: fragment correction — synthetic reads, overlaps, device pre-alignment, windows
+# ---------------------------------------------------------------------------------------------------------------
+def frag_workload(args, rank, sample_reads=None):
+    """Synthetic -f input: `frag_reads` reads of ~10 kb drawn from a random genome at ~30x (12 % error, forward strand),
+    every pair of reads whose genome intervals share >= 2 kb is an overlap (both directions: dual PAF), overlap
+    coordinates derived from the true genome coordinates like a mapper would report them.  Returns the sequences, the
+    overlap table and — built by the device pre-alignment + breaking points + racon's window assembly (host mirror of
+    polisher.cpp:383-461) — the window set."""
+    import numpy as np
+    from racon_b200 import api
+    from tests import util  # mutate(): the numpy window maker's error model
+    n_reads = sample_reads or args.frag_reads
+    rlen = args.frag_read_len
+    rng = np.random.default_rng(777 + rank)
+    cov = 30
+    glen = max(rlen * 2, n_reads * rlen // cov)
+    genome = bytes(b"ACGT"[i] for i in rng.integers(4, size=glen))
+    starts = np.sort(rng.integers(0, glen - rlen, size=n_reads))
+    reads, spans = [], []
+    for s in starts:
+        r = util.mutate(rng, genome[s:s + rlen], 0.12)
+        reads.append(r)
+        spans.append((int(s), int(s) + rlen))
+    seq_off = np.zeros(n_reads + 1, np.uint64)
+    seq_off[1:] = np.cumsum([len(r) for r in reads])
+    bases = np.frombuffer(b"".join(reads), np.uint8).copy()
+    quals = np.full(bases.size, ord("5"), np.uint8)
+    ov = []
+    for i in range(n_reads):
+        for j in range(i + 1, n_reads):
+            if spans[j][0] >= spans[i][1]:
+                break
+            lo, hi = max(spans[i][0], spans[j][0]), min(spans[i][1], spans[j][1])
+            if hi - lo < 2000:
+                continue
+
+            def coords(k):
+                a = int((lo - spans[k][0]) * len(reads[k]) / rlen)
+                b = int((hi - spans[k][0]) * len(reads[k]) / rlen)
+                return a, min(b, len(reads[k]))
+            qi, qj = coords(i), coords(j)
+            # overlap row: q_id, t_id, strand, q_begin, q_end, q_length, t_begin, t_end, t_length
+            ov.append((i, j, 0, qi[0], qi[1], len(reads[i]), qj[0], qj[1], len(reads[j])))
+            ov.append((j, i, 0, qj[0], qj[1], len(reads[j]), qi[0], qi[1], len(reads[i])))
+    ov = np.asarray(ov, np.uint32).reshape(-1, 9)
+    t0 = time.perf_counter()
+    pol = api.MirrorPolisher(bases.tobytes(), quals.tobytes(), seq_off, np.zeros(n_reads, np.uint8), n_reads, ov,
+                             window_length=500, fragment_correction=True)
+    init_s = time.perf_counter() - t0
+    ex = pol.export()
+    pol.close()
+    from racon_b200 import windows
+    ws = windows.WindowSet(bases=ex["bases"], quals=None, seq_off=ex["seq_off"], seq_has_qual=None,
+                           seq_begin=ex["seq_begin"], seq_end=ex["seq_end"], win_first=ex["win_first"],
+                           win_type=ex["win_type"])
+    pairs = [(bytes(bases[int(seq_off[o[0]]) + int(o[3]):int(seq_off[o[0]]) + int(o[4])]),
+              bytes(bases[int(seq_off[o[1]]) + int(o[6]):int(seq_off[o[1]]) + int(o[7])])) for o in ov]
+    return {"windows": ws, "pairs": pairs, "reads": n_reads, "overlaps": len(ov), "init_s": init_s}
+
+
+def time_aligner(pairs, local, steps, warmup):
+    """rp_aln_* over the overlaps' spans, resident: CUDA events around rp_aln_launch."""
+    import torch
+    from racon_b200 import api
+    b = api.AlnBatch(device=local)
+    st = torch.cuda.current_stream()
+    b.set_stream(st.cuda_stream)
+    taken = 0
+    for q, t in pairs:
+        if not b.add(q, t):
+            break
+        taken += 1
+    cells = float(sum(len(q) * len(t) for q, t in pairs[:taken]))
+    b.upload()
+    for _ in range(max(1, warmup)):
+        b.launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        b.launch()
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    b.download()
+    b.sync()
+    bad = sum(1 for k in range(taken) if b.fetch(k)[2] != 0)
+    b.close()
+    return {"pairs": taken, "pairs_per_s": taken / (ms * 1e-3), "gcups_full_matrix_equivalent": cells / (ms * 1e-3) / 1e9,
+            "ms_per_launch": ms, "soft_failures": bad, "kernel": "rp_aln_kernel",
+            "bound": "integer issue (bit-vector words in registers; HBM sees only sequences and the stored leaf words)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--windows", type=int, default=10000, help="windows per GPU per step (BASELINE config 2)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--windows", type=int, default=0, help="override the config's window count")
+    ap.add_argument("--banded", type=int, default=-1, help="override the config's -b flag (0/1)")
+    ap.add_argument("--frag-reads", type=int, default=400, help="config 5: reads per GPU")
+    ap.add_argument("--frag-read-len", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-batches", type=int, default=2,
                     help="batch objects the end-to-end arm cycles through (racon's -c/--cudapoa-batches)")
@@ -190,14 +350,27 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # each rank generates ITS OWN shard of the stream of synthetic windows (weak scaling: per-GPU work fixed)
-    state = 42
-    for _ in range(rank):
-        state = _skip_state(windows, args.windows, state)
-    ws, _ = windows.synth_windows(args.windows, err=0.12, state=state)
+    cfg = CONFIGS[args.config]
+    banded = cfg["banded"] if args.banded < 0 else bool(args.banded)
+    wl = cfg["wl"]
+    aligner = None
+    meta = {}
+    if cfg["shape"] == "frag":
+        fw = frag_workload(args, rank)
+        ws = fw["windows"]
+        aligner = time_aligner(fw["pairs"], local, args.steps, args.warmup)
+        meta = {"reads_per_gpu": fw["reads"], "overlaps_per_gpu": fw["overlaps"], "windows_total": ws.n_windows * world,
+                "window_build_s": fw["init_s"]}
+    else:
+        ws, meta = make_windows(args.config, args, rank, world)
     n = ws.n_windows
+    n_total = meta.get("windows_total", n * world)
+    mem = int(os.environ.get("RP_BENCH_MEM", 40e9))     # device-memory budget per batch object (several are alive)
 
-    batch = api.PoaBatch(device=local, window_length=500)
+    def new_batch():
+        return api.PoaBatch(device=local, window_length=wl, banded=banded, mem_bytes=mem)
+
+    batch = new_batch()
     stream = torch.cuda.current_stream()
     batch.set_stream(stream.cuda_stream)
     t_pack0 = time.perf_counter()
@@ -217,10 +390,13 @@ def main():
     batch.run()
     batch.sync()
     info = batch.info()
+    band_info = batch.band_info()
     out, lens, pol, st = batch.fetch_all(stride)
-    if (st != 0).any() or not pol.all():
+    if (st != 0).any():
         raise SystemExit("bench.py: %d windows hit a device limit" % int((st != 0).sum()))
     checksum = "%016x" % windows.fnv1a64([out[i, :lens[i]].tobytes() for i in range(min(n, 200))])
+    if cfg["shape"] == "ont" and rank == 0 and n >= 200 and checksum != "50f18d884e3254d2":
+        raise SystemExit("bench.py: consensus checksum %s != the reference's known answer 50f18d884e3254d2" % checksum)
     alg_bytes = 2.0 * (info["dp_cells"] + info["pred_cells"])
     batch.enable_counters(False)
 
@@ -240,7 +416,7 @@ def main():
     # (2) the K timed steps: one launch per step over the resident batch, steps alternating between two batch objects
     # on two streams (both hold the whole batch in HBM), so that the tail of one step — the last windows of a launch
     # leave most SMs idle — is filled by the head of the next, as it is in a real multi-batch run
-    batch2 = api.PoaBatch(device=local, window_length=500)
+    batch2 = new_batch()
     stream2 = torch.cuda.Stream()
     batch2.set_stream(stream2.cuda_stream)
     assert batch2.add_window_set(ws) == n
@@ -270,10 +446,8 @@ def main():
     # stream, is reset, filled from host buffers (copied into pinned staging), run (H2D + kernel + D2H, asynchronous)
     # and read back; while one object's kernel runs, the host fills the next one.
     nb = max(1, args.e2e_batches)
-    # (each on its own stream; torch's current stream stays free for the NCCL gather)
-    objs = [api.PoaBatch(device=local, window_length=500) for _ in range(nb)]
+    objs = [new_batch() for _ in range(nb)]
     bounds = [n * k // nb for k in range(nb + 1)]
-
     last = {}
 
     def finalize(parts):
@@ -284,8 +458,6 @@ def main():
         last["out"], last["lens"] = out, lens
 
     def plugin_steps(n_steps):
-        # the batch objects stay in flight across steps, as CUDAPolisher keeps its batches busy until the window list
-        # is exhausted: object k takes chunk k of every step; before it is refilled its previous results are read back
         pending = [None] * nb
         parts = {}
 
@@ -323,33 +495,43 @@ def main():
     io = objs[0].info()
     io["h2d_bytes"] = sum(b.info()["h2d_bytes"] for b in objs)
     io["d2h_bytes"] = sum(b.info()["d2h_bytes"] for b in objs)
+    for b in objs + [batch]:
+        b.close()
+    torch.cuda.empty_cache()
 
     # ---- max over ranks ---------------------------------------------------------------------------
-    tt = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([total_ms, e2e_ms, float(band_info["band_alignments"]), float(band_info["band_redone_full"])],
+                      dtype=torch.float64, device="cuda")
     if distributed:
+        t2 = tt.clone()
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+        band_tot = (float(t2[2]), float(t2[3]))
+    else:
+        band_tot = (float(tt[2]), float(tt[3]))
     total_ms, e2e_ms = float(tt[0]), float(tt[1])
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         ms_per_step = total_ms / args.steps
-        value = world * n / (ms_per_step * 1e-3)
+        value = n_total / (ms_per_step * 1e-3)
         kern_avg_ms = sum(kern_ms) / len(kern_ms)
         achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
-        traffic = ncu_traffic()
+        traffic = ncu_traffic(args.config)
         line = {
-            "metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": cfg["metric"], "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"],
             "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "windows_per_gpu": n, "window_len": 500, "depth": 32,
-                       "parallelism": "windows sharded across %d GPU(s), no data-path collective" % world,
-                       "l2": "inputs (%.0f MB) + per-step DP scratch (>> 126 MB) exceed L2; no explicit flush"
-                             % (io["h2d_bytes"] / 1e6),
-                       "steps_overlap": "timed steps alternate between two resident batch objects on two streams; "
-                                        "roofline.kernel_ms is an isolated launch",
-                       "worker_warps": io["workers"], "first_pack_ms": pack_ms,
-                       "consensus_fnv_first200": checksum},
-            "e2e": {"value": world * n * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
+            "config": dict({"workload": cfg["workload"], "baseline_config": args.config, "windows_rank0": n,
+                            "window_len": wl, "banded": banded,
+                            "parallelism": "windows sharded across %d GPU(s), no data-path collective" % world,
+                            "l2": "inputs (%.0f MB) + per-step DP scratch (>> 126 MB) exceed L2; no explicit flush"
+                                  % (io["h2d_bytes"] / 1e6),
+                            "steps_overlap": "timed steps alternate between two resident batch objects on two streams; "
+                                             "roofline.kernel_ms is an isolated launch",
+                            "workers_windows_in_flight": io["workers"], "first_pack_ms": pack_ms,
+                            "consensus_fnv_first200": checksum}, **meta),
+            "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": io["h2d_bytes"], "d2h_bytes_per_step": io["d2h_bytes"],
                     "batch_objects": nb,
                     "includes": "every step, per batch object: rp_poa_reset + rp_poa_add_window_set (host buffers -> pinned "
@@ -362,27 +544,28 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                          "kernel": "rp_poa_kernel", "kernel_ms": kern_avg_ms,
-                         "achieved_overlapped": alg_bytes / (ms_per_step * 1e-3) / 1e9,
-                         "frac_overlapped": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "achieved_overlapped": alg_bytes / (ms_per_step * 1e-3) / 1e9 * (n / max(1, n_total / world)),
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "algorithmic_bytes_per_window": alg_bytes / n, "peak_source": peak_src},
+                         "algorithmic_bytes_per_window": alg_bytes / n, "peak_source": peak_src,
+                         "note": "algorithmic bytes count the cells the accepted DP computed: the full rows, or with -b "
+                                 "the band's columns per row"},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
+        if banded:
+            line["band"] = {"width_columns": band_info["band_width"], "alignments_tried_in_band": int(band_tot[0]),
+                            "redone_with_full_matrix_on_device": int(band_tot[1]),
+                            "result_check": "consensus checksum of the first 200 windows == the reference's known "
+                                            "answer (full-matrix spoa)" if cfg["shape"] == "ont" else "see tests"}
+        if aligner:
+            line["aligner"] = aligner
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, cfg, banded, world, ws)
         print(json.dumps(line))
-    for b in objs + [batch]:
-        b.close()
     if distributed:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def _skip_state(windows, n, state):
-    """Advances the generator state past one rank's shard (so every rank draws a different shard)."""
-    _, st = windows.synth_windows(n, err=0.12, state=state)
-    return st
-
-
-def cpu_baseline(args):
+def cpu_baseline(args, cfg, banded, world, ws):
     """oracle/_ref (the unmodified reference) on the box's host cores, bounded sample (~10-30 s of CPU work)."""
     from oracle import bindings as ob
     from racon_b200 import windows
@@ -391,30 +574,39 @@ def cpu_baseline(args):
         kind, fn = "reference", ob.ref_consensus
     else:
         kind, fn = "port", ob.oracle_consensus
-    n_sample = min(args.windows, max(64, 300 * cores))
-    ws, _ = windows.synth_windows(n_sample, err=0.12)
+    per_core = 300 if cfg["shape"] in ("ont", "frag") else 2500
+    n_sample = min(ws.n_windows, max(64, per_core * cores))
+    sample_ws = windows.slice_windows(ws, 0, n_sample)
     threads = cores
     if cores >= 4:  # see run_reference(): best of all hardware threads / half of them
-        probe = ws.subset(range(min(n_sample, 16 * cores)))
+        probe = windows.slice_windows(sample_ws, 0, min(n_sample, 16 * cores))
         threads = cores if fn(probe, threads=cores)[2] <= fn(probe, threads=cores // 2)[2] else cores // 2
-    out = fn(ws, threads=threads)
-    secs = out[2]
+    secs = fn(sample_ws, threads=threads)[2]
     res = {"value": n_sample / secs, "unit": "windows/s", "cores": threads, "kind": kind,
-           "sample": "first %d windows of the workload, %d host threads (of %d hardware threads), consensus loop "
+           "sample": "first %d windows of rank 0's workload, %d host threads (of %d hardware threads), consensus loop "
                      "only (%.1f s)" % (n_sample, threads, cores, secs)}
-    res["gpu_reference"] = gpu_reference(args)
+    if cfg["shape"] == "ont":
+        res["gpu_reference"] = gpu_reference(args, cfg, banded, world)
+    elif cfg["shape"] == "ngs":
+        res["gpu_reference"] = {"note": "the reference's CUDA path marks every kNGS window failed and re-runs it on the CPU "
+                                        "(src/cuda/cudabatch.cpp:229-256): its throughput on this workload is the "
+                                        "cpu_baseline above"}
     return res
 
 
-def gpu_reference(args):
-    """The reference's OWN GPU path (GenomeWorks cudapoa, unmodified, oracle/_ref/libref_cudapoa.so) on the same
-    workload and the same GPU — SURVEY §8(d)'s GPU baseline.  Separate process with a time limit: a failure inside the
-    reference library must not take the bench line down.  Timing only (cudapoa's consensus is not spoa's)."""
-    import subprocess
+def gpu_reference(args, cfg, banded, world):
+    """The reference's OWN GPU path (GenomeWorks cudapoa, unmodified, oracle/_ref/libref_cudapoa.so) on the same workload,
+    the same box and the SAME number of GPUs, driven like CUDAPolisher::polish drives it (two batch objects per GPU, one
+    host thread each) — SURVEY §8(d)'s GPU baseline.  Separate process with a time limit: a failure inside the reference
+    library must not take the bench line down.  Timing only (cudapoa's consensus is not spoa's)."""
     here = os.path.dirname(os.path.abspath(__file__))
+    n = args.windows or cfg["windows"]
+    total = n if cfg["scaling"] == "strong" else n * world
+    cmd = [sys.executable, "-m", "oracle.cudapoa_time", "--windows", str(total), "--devices", str(world), "--batches", "2"]
+    if banded:
+        cmd.append("--banded")
     try:
-        p = subprocess.run([sys.executable, "-m", "oracle.cudapoa_time", "--windows", str(min(args.windows, 10000))],
-                           cwd=here, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=240, text=True)
+        p = subprocess.run(cmd, cwd=here, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=420, text=True)
         lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
         return json.loads(lines[-1]) if lines else {"unavailable": "no output (exit %d)" % p.returncode}
     except Exception as e:  # noqa: BLE001 - reported, never fatal

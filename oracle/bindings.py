@@ -171,3 +171,21 @@ def ref_cudapoa_consensus(ws, match=3, mismatch=-5, gap=-4, banded=False, max_de
         raise RuntimeError("reference cudapoa failed (%d)" % ok)
     return [out[i, :out_len[i]].tobytes() for i in range(n)], int(ok), float(times[0]), float(times[1])
 
+
+
+def ref_cudapoa_multi(ws, match=3, mismatch=-5, gap=-4, banded=False, max_depth=200, n_devices=1, batches_per_device=2):
+    """The reference's own multi-GPU driver shape (CUDAPolisher::polish, cudapolisher.cpp:226-345) over GenomeWorks
+    cudapoa, unmodified: `batches_per_device` batch objects on each of the first n_devices GPUs, one host thread each.
+    Returns (windows reported ok, wall seconds).  Timing only."""
+    lib = C.CDLL(CUDAPOA_SO)
+    lib.ref_cudapoa_multi.restype = C.c_int64
+    lib.ref_cudapoa_multi.argtypes = [C.c_uint32] + [C.c_void_p] * 6 + [C.c_int8, C.c_int8, C.c_int8, C.c_int,
+                                                                       C.c_uint32, C.c_int, C.c_int, C.c_void_p]
+    seq_off = ws.seq_off.astype(np.uint64)
+    times = np.zeros(2, np.float64)
+    ok = lib.ref_cudapoa_multi(ws.n_windows, _ptr(ws.bases), _ptr(ws.quals), _ptr(seq_off), _ptr(ws.seq_has_qual),
+                               _ptr(ws.seq_begin), _ptr(ws.win_first), match, mismatch, gap, 1 if banded else 0,
+                               max_depth, n_devices, batches_per_device, times.ctypes.data)
+    if ok < 0:
+        raise RuntimeError("reference cudapoa (multi) failed (%d)" % ok)
+    return int(ok), float(times[0])

@@ -73,6 +73,16 @@ def load(build_if_missing=True):
     lib.rp_poa_band_info.restype = C.c_int32
     lib.rp_poa_band_info.argtypes = [vp, vp]
     _bind_aln(lib, C, vp, u32)
+    # the C++ host layer and its hooks live in a library of their own (it links against the product, not vice versa)
+    host_path = os.path.join(os.path.dirname(path), "libracon_b200_host.so")
+    if os.path.exists(host_path):
+        host = C.CDLL(host_path)
+        for name in ("rp_mirror_align", "rp_mirror_consensus", "rp_mirror_polisher_open", "rp_mirror_polisher_open_with_bp",
+                     "rp_mirror_polisher_counts", "rp_mirror_polisher_export", "rp_mirror_polisher_polish",
+                     "rp_mirror_polisher_window_consensus", "rp_mirror_polisher_polished", "rp_mirror_polisher_close",
+                     "rp_mirror_polisher_failed", "rp_mirror_format_fasta"):
+            if hasattr(host, name):
+                setattr(lib, name, getattr(host, name))
     if hasattr(lib, "rp_mirror_align"):
         lib.rp_mirror_align.restype = C.c_int
         lib.rp_mirror_align.argtypes = [u32, vp, vp, vp, vp, vp, u32, u32, vp, u32]

@@ -1,7 +1,10 @@
 """Build helpers: every native artefact is built IN-TREE so it travels to the GPU box.
 
-  libracon_b200.so  — the product: C-ABI (include/racon_b200.h) + sm_100a CUDA kernels + C++ host mirror
-  libracon_synth.so — synthetic window generator (bench/test input maker, no CUDA)
+  libracon_b200.so       — the product: C-ABI (include/racon_b200.h) + sm_100a CUDA kernels, nothing else
+  libracon_b200_host.so  — C++ host layer above the C ABI (racon_b200::Window / BatchProcessor / BatchAligner / Polisher,
+                           the reference interface restated) + the rp_mirror_* hooks tests/ and bench.py drive it with;
+                           links against the product, never part of it
+  libracon_synth.so      — synthetic window generator (bench/test input maker, no CUDA)
   libracon_sim.so   — TEST-ONLY host simulation of the device code (tests/ only)
 The checkers (restated CPU model and the compiled reference) have their own recipe outside this package.
 """
@@ -63,16 +66,31 @@ def build_cuda(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libracon_b200.so")
     cu = [os.path.join(CSRC, "rp_api.cu")]
-    deps = _csrc_files((".cu", ".cuh", ".h", ".hpp", ".cpp")) + [os.path.join(ROOT, "include", "racon_b200.h")]
+    deps = [f for f in _csrc_files((".cu", ".cuh", ".h", ".hpp")) if not f.endswith(("sim_main.cu", "host_mirror.hpp"))]
+    deps += [os.path.join(ROOT, "include", "racon_b200.h")]
     if force or _newer(out, deps):
         cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo"] + NVCC_ARCH + [
             "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-            "-o", out] + cu + [os.path.join(CSRC, "host_mirror.cpp")]
+            "-o", out] + cu
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         log = _run(cmd)
         if verbose:
             print(log)
+    build_host(force)
+    return out
+
+
+def build_host(force=False):
+    """The C++ host layer above the C ABI + its test hooks, as a library of its own that links against the product."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libracon_b200_host.so")
+    src = os.path.join(CSRC, "host_mirror.cpp")
+    deps = [src, os.path.join(CSRC, "host_mirror.hpp"), os.path.join(CSRC, "poa_pack.hpp"),
+            os.path.join(ROOT, "include", "racon_b200.h"), os.path.join(LIBDIR, "libracon_b200.so")]
+    if force or _newer(out, deps):
+        _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+              "-o", out, src, "-L", LIBDIR, "-lracon_b200", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

@@ -106,6 +106,7 @@ const std::vector<bool>& BatchProcessor::generateConsensus() {
         exit(1);
     }
     window_consensus_status_.clear();
+    failed_.clear();
     for (uint32_t i = 0; i < windows_.size(); ++i) {
         const char* c = nullptr;
         uint32_t l = 0;
@@ -120,6 +121,7 @@ const std::vector<bool>& BatchProcessor::generateConsensus() {
             windows_[i]->consensus_ = std::string(windows_[i]->sequences_.front().first,
                                                   windows_[i]->sequences_.front().second);
             window_consensus_status_.push_back(false);
+            failed_.push_back(i);
             continue;
         }
         windows_[i]->consensus_.assign(c, l);
@@ -302,6 +304,7 @@ void Polisher::find_overlap_breaking_points(std::vector<Overlap>& overlaps) {
                 /* the reference re-aligns such overlaps with its CPU edlib (cudapolisher.cpp:213); this path has no CPU
                  * aligner, so the overlap contributes no layers and the caller is told */
                 fprintf(stderr, "[racon_b200::Polisher] warning: overlap %zu exceeded device limit %u\n", k, st);
+                failed_overlaps_.push_back(k);
                 continue;
             }
             rp_aln_fetch_breaking_points(aln, static_cast<uint32_t>(k - first), &pts, &n);
@@ -381,6 +384,7 @@ void Polisher::polish(std::vector<PolishedSequence>& dst, bool drop_unpolished_s
         }
         const std::vector<bool>& flags = batch->generateConsensus();
         for (size_t k = 0; k < flags.size(); ++k) polished[first + k] = flags[k];
+        for (uint32_t k : batch->failedWindows()) failed_windows_.push_back(first + k);
         batch->reset();
     }
 
@@ -465,6 +469,13 @@ extern "C" void* rp_mirror_polisher_open_with_bp(uint32_t n_seq, const char* bas
                                    fragment_correction != 0, window_length, quality_threshold, true, 3, -5, -4, 0));
     h->polisher->build_windows(ovl);
     return h;
+}
+
+/* failed[0] = overlaps, failed[1] = windows the device could not finish (Polisher::failed_overlaps/failed_windows) */
+extern "C" void rp_mirror_polisher_failed(void* hv, uint64_t* failed) {
+    PolHandle* h = static_cast<PolHandle*>(hv);
+    failed[0] = h->polisher->failed_overlaps().size();
+    failed[1] = h->polisher->failed_windows().size();
 }
 
 extern "C" void rp_mirror_polisher_counts(void* hv, uint64_t* counts) {

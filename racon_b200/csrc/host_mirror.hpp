@@ -77,6 +77,11 @@ public:
     const std::vector<bool>& generateConsensus();
     void reset();
     uint32_t getBatchID() const { return bid_; }
+    /* indices (within the batch) of the windows of the last generateConsensus() that hit a device limit (soft RP_WIN_*
+     * status): their flag is false and their consensus is the backbone — not what racon would produce; the reference's
+     * caller re-runs such windows on the CPU (cudapolisher.cpp:354-370), a caller without a CPU path must treat them as
+     * an error */
+    const std::vector<uint32_t>& failedWindows() const { return failed_; }
 
     friend std::unique_ptr<BatchProcessor> createBatch(uint32_t, uint32_t, size_t, int8_t, int8_t, int8_t, bool,
                                                        uint32_t, bool);
@@ -93,6 +98,7 @@ private:
     bool trim_ = true;
     std::vector<std::shared_ptr<Window>> windows_;
     std::vector<bool> window_consensus_status_;
+    std::vector<uint32_t> failed_;
 };
 
 /* Mirror of racon::CUDABatchAligner (src/cuda/cudaaligner.hpp:21-92).  The reference's addOverlap takes an
@@ -171,6 +177,13 @@ public:
     void build_windows(const std::vector<Overlap>& overlaps);
     void polish(std::vector<PolishedSequence>& dst, bool drop_unpolished_sequences);
     const std::vector<std::shared_ptr<Window>>& windows() const { return windows_; }
+    /* Items the device could not finish (soft RP_ALN_* / RP_WIN_* status).  The reference hands such items to its CPU
+     * code (cudapolisher.cpp:213 edlib, :354-370 spoa); this library has no CPU path, so a failed overlap contributes
+     * no layers and a failed window keeps its backbone — the result then DIFFERS from racon's, which is why the indices
+     * are reported here instead of a stderr line: a caller with a CPU implementation (the integration shim's host is
+     * the reference itself) must process them, any other caller should treat a non-empty list as an error. */
+    const std::vector<size_t>& failed_overlaps() const { return failed_overlaps_; }
+    const std::vector<size_t>& failed_windows() const { return failed_windows_; }
 
 private:
     Polisher(const Polisher&) = delete;
@@ -191,6 +204,7 @@ private:
     std::vector<std::string> reverse_complement_, reverse_quality_;
     std::vector<uint32_t> targets_coverages_;
     std::vector<std::shared_ptr<Window>> windows_;
+    std::vector<size_t> failed_overlaps_, failed_windows_;
 };
 
 }  // namespace racon_b200

@@ -1,6 +1,7 @@
 /*
  * rp_api.cu — the C ABI (include/racon_b200.h) over the sm_100a kernels.  Product library
- * libracon_b200.so = this file + host_mirror.cpp.  There is no CPU implementation behind these calls.
+ * libracon_b200.so = this file alone (the C++ host layer above it, host_mirror.cpp, is a library of its own).
+ * There is no CPU implementation behind these calls.
  *
  * POA batch object = racon::CUDABatchProcessor + cudapoa::Batch (src/cuda/cudabatch.cpp:23-278):
  *   add (copy into pinned staging) -> upload (H2D) -> launch (one persistent kernel) -> download (D2H).
@@ -426,8 +427,16 @@ rp_status rp_poa_add_window_set(rp_poa* p, uint32_t first, uint32_t count, const
     std::vector<const char*> sp(nseq), qp(nseq);
     std::vector<uint32_t> ln(nseq);
     const bool any_q = quals && seq_has_qual;
+    /* host threads for the byte-heavy packing steps: the machine's threads are shared by every rank of the node
+     * (LOCAL_WORLD_SIZE, set by torchrun) and by every batch object a caller drives concurrently — more packers than
+     * hardware threads only slow each other down (round 1: 8 ranks x 32 packers on 128 threads) */
     unsigned hw = std::thread::hardware_concurrency();
-    const unsigned nthreads = std::max(1u, std::min(hw ? hw : 1u, std::min(32u, count / 64 + 1)));
+    unsigned share = 1;
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) share = std::max(1, atoi(lw));
+    unsigned cap = 32;
+    if (const char* pt = getenv("RP_PACK_THREADS")) cap = std::max(1, atoi(pt));
+    const unsigned fair = std::max(1u, (hw ? hw : 1u) / share / 2);
+    const unsigned nthreads = std::max(1u, std::min(std::min(fair, cap), count / 64 + 1));
     std::vector<rp::PackedBatch::Prep> preps(count);
     const uint32_t max_len = p->batch.max_seq_len;
     auto prep_range = [&](uint32_t a, uint32_t b) {

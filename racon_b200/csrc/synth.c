@@ -123,6 +123,115 @@ fail:
     return (uint64_t)-1;
 }
 
+/*
+ * Illumina-mode windows (BASELINE.json config 4; SURVEY.md §8(d) config map): window length `w` (200), `depth` (60)
+ * layers that are pieces of `read_len`-base (150) reads cut at the window edges — so every layer is partial-span and
+ * goes through the Subgraph path of Window::generate_consensus (/root/reference/src/window.cpp:89-108) —, substitution
+ * errors at rate `sub` (0.005) in the reads, Phred 30-40 qualities on every layer, window type kNGS (no trimming,
+ * window.cpp:125).  The backbone is the truth with `bb_err` (0.01) errors, a third each substitutions / insertions /
+ * deletions, which is what the reads have to polish away; layer coordinates are mapped through that edit script onto
+ * the backbone, inclusive, as Polisher::initialize derives them from the breaking points (polisher.cpp:440-457).
+ * Pieces shorter than 0.02 * w are dropped like polisher.cpp:415 drops them.  Same splitmix64 stream as above.
+ * Outputs as rp_synth_windows plus `quals` (same offsets; backbone quality bytes are '!').  seq arrays need room for
+ * n_windows * (depth + 1) + 1 entries; fewer sequences may be produced (win_first tells).  Returns bases written.
+ */
+uint64_t rp_synth_ngs_windows(uint64_t* state_io, uint32_t n_windows, uint32_t w, uint32_t depth, uint32_t read_len,
+                              double sub, double bb_err, char* bases, char* quals, uint64_t bases_cap,
+                              uint64_t* seq_off, uint32_t* seq_begin, uint32_t* seq_end, uint32_t* win_first) {
+    rp_rng r;
+    r.state = *state_io;
+    char* truth = (char*)malloc(w);
+    char* bb = (char*)malloc(4 * w + 64);
+    uint32_t* map = (uint32_t*)malloc(sizeof(uint32_t) * (w + 1)); /* truth index -> backbone index of the base that
+                                                                      represents it (or of the next kept base) */
+    const double p = bb_err / 3.0;
+    const uint32_t min_piece = (uint32_t)(0.02 * w) + 1;
+    uint64_t nb = 0, ns = 0;
+    seq_off[0] = 0;
+    for (uint32_t wi = 0; wi < n_windows; ++wi) {
+        win_first[wi] = (uint32_t)ns;
+        for (uint32_t k = 0; k < w; ++k) truth[k] = kBases[rng_next(&r) & 3];
+        /* backbone = edited truth, remembering where every truth base went */
+        uint32_t bl = 0;
+        for (uint32_t i = 0; i < w; ++i) {
+            for (;;) {
+                double u = rng_u01(&r);
+                if (u < p) { /* deleted from the backbone */
+                    map[i] = bl;
+                    break;
+                } else if (u < 2 * p) {
+                    bb[bl++] = kBases[rng_next(&r) & 3];
+                    continue;
+                } else if (u < 3 * p) {
+                    char c;
+                    do {
+                        c = kBases[rng_next(&r) & 3];
+                    } while (c == truth[i]);
+                    map[i] = bl;
+                    bb[bl++] = c;
+                    break;
+                } else {
+                    map[i] = bl;
+                    bb[bl++] = truth[i];
+                    break;
+                }
+            }
+        }
+        if (bl < 2) {
+            bb[0] = truth[0];
+            bb[1] = truth[1 % w];
+            bl = 2;
+            for (uint32_t i = 0; i < w; ++i) map[i] = i < 2 ? i : 1;
+        }
+        if (nb + bl > bases_cap) goto fail;
+        memcpy(bases + nb, bb, bl);
+        memset(quals + nb, '!', bl);
+        nb += bl;
+        seq_begin[ns] = 0;
+        seq_end[ns] = 0;
+        seq_off[++ns] = nb;
+        for (uint32_t d = 0; d < depth; ++d) {
+            /* a read_len-base read placed uniformly among the positions where it overlaps the window */
+            const int64_t start = (int64_t)(rng_next(&r) % (uint64_t)(w + read_len - 1)) - (int64_t)(read_len - 1);
+            int64_t a = start < 0 ? 0 : start;
+            int64_t b = start + read_len - 1 >= (int64_t)w ? (int64_t)w - 1 : start + read_len - 1;
+            if (b - a + 1 < (int64_t)min_piece) continue;
+            uint32_t begin = map[a], end = map[b];
+            if (end >= bl) end = bl - 1;
+            if (begin >= end) continue;
+            const uint32_t len = (uint32_t)(b - a + 1);
+            if (nb + len > bases_cap) goto fail;
+            for (uint32_t k = 0; k < len; ++k) {
+                char c = truth[a + k];
+                if (rng_u01(&r) < sub) {
+                    char m;
+                    do {
+                        m = kBases[rng_next(&r) & 3];
+                    } while (m == c);
+                    c = m;
+                }
+                bases[nb + k] = c;
+                quals[nb + k] = (char)(33 + 30 + (rng_next(&r) % 11));
+            }
+            nb += len;
+            seq_begin[ns] = begin;
+            seq_end[ns] = end;
+            seq_off[++ns] = nb;
+        }
+    }
+    win_first[n_windows] = (uint32_t)ns;
+    *state_io = r.state;
+    free(truth);
+    free(bb);
+    free(map);
+    return nb;
+fail:
+    free(truth);
+    free(bb);
+    free(map);
+    return (uint64_t)-1;
+}
+
 /* FNV-1a-64 over a byte range, continuing from `h` (start: 1469598103934665603). */
 uint64_t rp_fnv1a64(uint64_t h, const unsigned char* p, uint64_t n) {
     for (uint64_t i = 0; i < n; ++i) {

@@ -11,6 +11,18 @@ def shard_bounds(n_windows, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_bounds_by_cost(costs, rank, world):
+    """Contiguous, COST-balanced window range [lo, hi) of `rank`: boundaries at the equal quantiles
+    of the cumulative per-window cost estimate (windows.window_costs); output order stays window order."""
+    c = np.cumsum(np.asarray(costs, dtype=np.float64))
+    n = len(c)
+    if n == 0 or c[-1] <= 0:
+        return shard_bounds(n, rank, world)
+    cuts = [0] + [int(np.searchsorted(c, c[-1] * k / world, side="left")) + 1 for k in range(1, world)] + [n]
+    cuts = np.minimum(np.maximum.accumulate(cuts), n)
+    return int(cuts[rank]), int(cuts[rank + 1])
+
+
 def pack_consensus(cons):
     """list of bytes -> (flat uint8 array, uint32 lengths)"""
     lens = np.asarray([len(c) for c in cons], dtype=np.uint32)

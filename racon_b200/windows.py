@@ -96,6 +96,10 @@ def _synth_lib():
         lib.rp_synth_windows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
                                          C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p]
+        lib.rp_synth_ngs_windows.restype = C.c_uint64
+        lib.rp_synth_ngs_windows.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
+                                             C.c_double, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
         lib.rp_fnv1a64.restype = C.c_uint64
         lib.rp_fnv1a64.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64]
         _synth = lib
@@ -120,6 +124,60 @@ def synth_windows(n_windows, truth_len=500, depth=32, err=0.12, state=42):
     ws = WindowSet(bases=bases[:nb].copy(), quals=None, seq_off=seq_off, seq_has_qual=None, seq_begin=beg,
                    seq_end=end, win_first=first, win_type=np.ones(n_windows, dtype=np.uint8))
     return ws, st.value
+
+
+def synth_ngs_windows(n_windows, w=200, depth=60, read_len=150, sub=0.005, bb_err=0.01, state=4242):
+    """BASELINE config 4 shape (Illumina mode): w-base windows, `depth` partial-span pieces of read_len-base reads with
+    qualities, kNGS.  Returns (WindowSet, new_state).  Generator: racon_b200/csrc/synth.c rp_synth_ngs_windows."""
+    lib = _synth_lib()
+    n_seq = n_windows * (depth + 1)
+    cap = int(n_windows * (2 * w + 64 + depth * read_len))
+    bases = np.empty(cap, dtype=np.uint8)
+    quals = np.empty(cap, dtype=np.uint8)
+    seq_off = np.empty(n_seq + 1, dtype=np.uint64)
+    beg = np.empty(n_seq, dtype=np.uint32)
+    end = np.empty(n_seq, dtype=np.uint32)
+    first = np.empty(n_windows + 1, dtype=np.uint32)
+    st = C.c_uint64(state)
+    nb = lib.rp_synth_ngs_windows(C.byref(st), n_windows, w, depth, read_len, float(sub), float(bb_err),
+                                  bases.ctypes.data, quals.ctypes.data, cap, seq_off.ctypes.data, beg.ctypes.data,
+                                  end.ctypes.data, first.ctypes.data)
+    if nb == 2 ** 64 - 1:
+        raise RuntimeError("synthetic NGS generator: capacity too small")
+    ns = int(first[n_windows])
+    hasq = np.ones(ns, dtype=np.uint8)
+    hasq[first[:-1]] = 0                  # backbones carry the dummy '!' quality (polisher.cpp:174,396-399)
+    ws = WindowSet(bases=bases[:nb].copy(), quals=quals[:nb].copy(), seq_off=seq_off[:ns + 1].copy(), seq_has_qual=hasq,
+                   seq_begin=beg[:ns].copy(), seq_end=end[:ns].copy(), win_first=first,
+                   win_type=np.zeros(n_windows, dtype=np.uint8))
+    return ws, st.value
+
+
+def window_costs(ws):
+    """SURVEY.md §8(e) cost estimate per window: sum over layers s of L_s * (len_backbone + 0.1 * sum_{k<s} L_k)."""
+    lens = np.diff(ws.seq_off.astype(np.int64)).astype(np.float64)
+    first = ws.win_first.astype(np.int64)
+    nw = ws.n_windows
+    win_of = np.repeat(np.arange(nw), np.diff(first))
+    blen = lens[first[:-1]]
+    csum = np.cumsum(lens)
+    before = csum - lens - (csum[first[:-1]] - lens[first[:-1]])[win_of]    # bases of the window before this sequence
+    prior_layers = before - blen[win_of]                                     # layers only (excludes the backbone)
+    per_seq = lens * (blen[win_of] + 0.1 * np.maximum(prior_layers, 0.0))
+    per_seq[first[:-1]] = 0.0
+    return np.bincount(win_of, weights=per_seq, minlength=nw)
+
+
+def slice_windows(ws, lo, hi):
+    """Contiguous windows [lo, hi) of a WindowSet as a new WindowSet (vectorised; subset() is for small picks)."""
+    s0, s1 = int(ws.win_first[lo]), int(ws.win_first[hi])
+    b0, b1 = int(ws.seq_off[s0]), int(ws.seq_off[s1])
+    return WindowSet(bases=ws.bases[b0:b1].copy(), quals=None if ws.quals is None else ws.quals[b0:b1].copy(),
+                     seq_off=(ws.seq_off[s0:s1 + 1] - ws.seq_off[s0]).astype(np.uint64),
+                     seq_has_qual=None if ws.seq_has_qual is None else ws.seq_has_qual[s0:s1].copy(),
+                     seq_begin=ws.seq_begin[s0:s1].copy(), seq_end=ws.seq_end[s0:s1].copy(),
+                     win_first=(ws.win_first[lo:hi + 1] - ws.win_first[lo]).astype(np.uint32),
+                     win_type=ws.win_type[lo:hi].copy())
 
 
 def fnv1a64(chunks):

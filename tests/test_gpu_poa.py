@@ -241,3 +241,71 @@ def test_gpu_windows_beyond_spoa_int16_bound():
     bad = util.make_set(23, 4, wlen=600, depth=5, err=0.1)
     cons, pol, st = api.consensus(bad, match=3, mismatch=-5, gap=-64, window_length=600)
     assert (st == 4).all() and not pol.any()
+
+
+def test_gpu_memory_budget_back_pressure():
+    """createCUDABatch's avail_mem contract (cudabatch.cpp:23-72, cudapolisher.cpp:232-238): an object created with a small
+    budget keeps its device allocations inside it, reports RP_BATCH_FULL when the next window would not fit (add-until-full
+    -> run -> reset -> continue, cudabatch.cpp:126-132 / cudapolisher.cpp:254-276) and still produces the same consensus."""
+    import torch
+    n = 2000
+    ws, _ = windows.synth_windows(n, err=0.12)
+    free0 = torch.cuda.mem_get_info()[0]
+    budget = 256 << 20
+    b = api.PoaBatch(mem_bytes=budget, window_length=500)
+    stride = 1200
+    cons, batches, first = [], 0, 0
+    peak_used = 0
+    while first < n:
+        b.reset()
+        took = b.add_window_set(ws, first, n - first)
+        assert took > 0
+        if first + took < n:   # the batch is full: one more window must be refused, not crash
+            assert b.add_window(ws.window(first + took)) == api.RP_BATCH_FULL
+        b.run()
+        b.sync()
+        out, lens, pol, st = b.fetch_all(stride)
+        assert (st == 0).all()
+        cons += [out[i, :lens[i]].tobytes() for i in range(took)]
+        peak_used = max(peak_used, free0 - torch.cuda.mem_get_info()[0])
+        first += took
+        batches += 1
+    b.close()
+    assert batches >= 3, "a 256 MB object swallowed %d windows in %d batches: the budget is not enforced" % (n, batches)
+    assert peak_used <= budget * 1.25 + (64 << 20), "device memory in use %d MB for a %d MB budget" % (peak_used >> 20, budget >> 20)
+    ref, _, _ = api.consensus(ws)
+    assert cons == ref
+    assert "%016x" % windows.fnv1a64(cons[:200]) == "50f18d884e3254d2"
+
+
+def test_gpu_four_batch_objects_per_gpu_like_racon_c4():
+    """racon -c 4: four batch objects on one GPU, each with 0.9 * free / 4 bytes (cudapolisher.cpp:226-240), alive at the
+    same time, driven from four host threads."""
+    import threading
+    import torch
+    ws, _ = windows.synth_windows(1200, err=0.12)
+    free = torch.cuda.mem_get_info()[0]
+    objs = [api.PoaBatch(mem_bytes=int(0.9 * free / 4), window_length=500) for _ in range(4)]
+    res = [None] * 4
+
+    def work(k):
+        b = objs[k]
+        lo, hi = 300 * k, 300 * (k + 1)
+        assert b.add_window_set(ws, lo, hi - lo) == hi - lo
+        b.run()
+        b.sync()
+        out, lens, pol, st = b.fetch_all(1200)
+        res[k] = ([out[i, :lens[i]].tobytes() for i in range(hi - lo)], st)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    cons = sum((r[0] for r in res), [])
+    assert all((r[1] == 0).all() for r in res)
+    for b in objs:
+        b.close()
+    assert "%016x" % windows.fnv1a64(cons[:200]) == "50f18d884e3254d2"
+    ref, _, _ = api.consensus(ws)
+    assert cons == ref

@@ -182,3 +182,38 @@ def test_gpu_real_larger_windows():
     bad = [w for w in range(ws.n_windows) if cons[w] != ref[w]]
     assert not bad, "windows differ: %s" % bad[:8]
     assert b"".join(cons) == polished
+
+
+# ---- racon -b on the real windows: same outputs, with the band audit (every accepted band result recomputed with the
+# full matrix on the device) reporting zero differing alignments -----------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes", [8, 16])
+def test_gpu_banded_real_windows_equal_the_reference(lanes, monkeypatch):
+    from racon_b200 import api
+    monkeypatch.setenv("RP_POA_GROUP", str(lanes))
+    monkeypatch.setenv("RP_BAND_AUDIT", "1")
+    ws, ref, polished, name = load()
+    stats = {}
+    cons, pol, st = api.consensus(ws, 3, -5, -4, banded=True, band_stats=stats)
+    assert (st == 0).all()
+    assert cons == ref and fasta_md5(name, cons) == MD5
+    assert stats["band_alignments"] > 1000 and stats["band_audit_mismatches"] == 0, stats
+    print("lambda contig, %d-column band: %s" % (16 * lanes, stats))
+    stats = {}
+    cons, pol, st = api.consensus(ws, 5, -4, -8, banded=True, band_stats=stats)
+    assert (st == 0).all() and cons == load_second_scores() and stats["band_audit_mismatches"] == 0
+    ws, ref = load_frag()
+    stats = {}
+    cons, pol, st = api.consensus(ws, 1, -1, -1, banded=True, band_stats=stats)
+    assert (st == 0).all() and cons == ref and stats["band_audit_mismatches"] == 0, stats
+    print("lambda -f windows, %d-column band: %s" % (16 * lanes, stats))
+
+
+@pytest.mark.gpu
+def test_gpu_banded_real_larger_windows():
+    from racon_b200 import api
+    ws, ref, polished = load_w1000()
+    stats = {}
+    cons, pol, st = api.consensus(ws, 5, -4, -8, window_length=1000, banded=True, band_stats=stats)
+    assert (st == 0).all(), st
+    assert cons == ref and b"".join(cons) == polished

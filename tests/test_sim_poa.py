@@ -238,3 +238,14 @@ def test_sim_matrix_scratch_limit_is_reported():
     ws = _mk("fullspan_small", seed=4)
     _, pol, st, _, _ = simlib.sim_consensus(ws, hcap=20000)
     assert (st == 9).all() and not pol.any()
+
+
+def test_sim_band_audit_finds_no_differing_alignment():
+    """debug flag 2 recomputes every ACCEPTED band result with the full matrix inside the device code and counts the
+    alignments that differ (stats[6]): none, also on the 30 %-error family whose graphs have > 8 in-edges per node."""
+    ws = util.make_set(101, 32, wlen=300, depth=40, err=0.3).subset([0, 12])
+    stats = _check(ws, lanes=8, smem=3584, banded=1, debug_flags=2)
+    assert stats[4] > 0 and stats[6] == 0
+    ws = util.make_set(12, 2, wlen=500, depth=20, err=0.12, partial_frac=0.3, with_qual=True)
+    stats = _check(ws, lanes=8, smem=3584, banded=1, debug_flags=2)
+    assert stats[4] > 0 and stats[6] == 0
