@@ -182,6 +182,9 @@ RP_DEV uint32_t rec_pred(const Rec& r, uint32_t k) {  // k < 7
 struct alignas(16) U4 {
     uint32_t x, y, z, w;
 };
+struct alignas(8) U2 {
+    uint32_t x, y;
+};
 
 /* A lane's 16 columns = two 16-byte granules 2*lane, 2*lane+1 of the row (chunk or band) it belongs to */
 RP_DEV Row8 load_row_smem(const int16_t* row, int lane) {
@@ -220,9 +223,93 @@ RP_DEV void store_row_gmem(int16_t* row, int lane, const Row8& v) {
 /* One lane group's view of its scratch slot + shared memory (G lanes = one window; rp_warp.cuh "lane groups").
  * All scalar members are group-uniform.  The collectives the code below calls unqualified (syncwarp, ballot, shfl,
  * ...) are the member versions declared here: they span the G lanes of this group only. */
-template <int G>
+template <int G, int KB = 16>
 struct PoaWarp {
-    static constexpr uint32_t kCC = 16u * G;   // columns of a register-resident row chunk (or of the band)
+    static constexpr uint32_t kCC = 16u * G;   // full matrix: columns of a register-resident row chunk (16 per lane)
+    /* banded rows: KB columns per lane (16, 8 or 4) => a band of G*KB columns = NB blocks of 16 columns, each block
+     * spread over LPB neighbouring lanes, R packed int16x2 registers per lane */
+    static constexpr uint32_t kBW = static_cast<uint32_t>(G) * KB;
+    static constexpr uint32_t NB = kBW / 16u;
+    static constexpr uint32_t LPB = 16u / KB;
+    static constexpr int R = KB / 2;
+    static_assert(KB == 16 || KB == 8 || KB == 4, "columns per lane of a banded row");
+    static_assert(NB >= 2 && (NB & (NB - 1)) == 0, "blocks per band must be a power of two");
+
+    /* element index, inside a band row, of logical column c (low 4 bits: place inside its 16-column block): lane q of
+     * the block holds columns q*KB .. q*KB+KB-1 as registers r = k mod R, half = k div R (k = column inside the lane) */
+    static RP_DEV uint32_t perm_band(uint32_t c) {
+        if (KB == 16) return perm(c);
+        const uint32_t ib = c & 15u, q = ib / KB, k = ib % KB;
+        return (c & ~15u) | (q * KB + ((k % R) << 1) + (k / R));
+    }
+    static RP_DEV uint32_t unperm_band(uint32_t el) {   // inverse of perm_band inside one block (el = 0..15)
+        const uint32_t q = el / KB, w = el % KB;
+        return q * KB + (w >> 1) + (w & 1u) * R;
+    }
+    struct RowB {
+        uint32_t r[R];
+    };
+    /* a lane's R registers of a band row in shared memory / HBM (lane-contiguous; 16-column lanes use the swizzled
+     * two-granule layout of the full rows) */
+    static RP_DEV RowB load_band_smem(const int16_t* row, int lane) {
+        RowB o;
+        if constexpr (R == 8) {
+            const Row8 t = load_row_smem(row, lane);
+#pragma unroll
+            for (int r = 0; r < R; ++r) o.r[r] = t.r[r];
+        } else if constexpr (R == 4) {
+            const U4 t = reinterpret_cast<const U4*>(row)[lane];
+            o.r[0] = t.x; o.r[1] = t.y; o.r[2] = t.z; o.r[3] = t.w;
+        } else {
+            const U2 t = reinterpret_cast<const U2*>(row)[lane];
+            o.r[0] = t.x; o.r[1] = t.y;
+        }
+        return o;
+    }
+    static RP_DEV void store_band_smem(int16_t* row, int lane, const RowB& v) {
+        if constexpr (R == 8) {
+            Row8 t;
+#pragma unroll
+            for (int r = 0; r < R; ++r) t.r[r] = v.r[r];
+            store_row_smem(row, lane, t);
+        } else if constexpr (R == 4) {
+            reinterpret_cast<U4*>(row)[lane] = U4{v.r[0], v.r[1], v.r[2], v.r[3]};
+        } else {
+            reinterpret_cast<U2*>(row)[lane] = U2{v.r[0], v.r[1]};
+        }
+    }
+    static RP_DEV RowB load_band_gmem(const int16_t* row, int lane) {
+        RowB o;
+        if constexpr (R == 8) {
+            const Row8 t = load_row_gmem(row, lane);
+#pragma unroll
+            for (int r = 0; r < R; ++r) o.r[r] = t.r[r];
+        } else if constexpr (R == 4) {
+            const U4 t = reinterpret_cast<const U4*>(row)[lane];
+            o.r[0] = t.x; o.r[1] = t.y; o.r[2] = t.z; o.r[3] = t.w;
+        } else {
+            const U2 t = reinterpret_cast<const U2*>(row)[lane];
+            o.r[0] = t.x; o.r[1] = t.y;
+        }
+        return o;
+    }
+    static RP_DEV void store_band_gmem(int16_t* row, int lane, const RowB& v) {
+        if constexpr (R == 8) {
+            Row8 t;
+#pragma unroll
+            for (int r = 0; r < R; ++r) t.r[r] = v.r[r];
+            store_row_gmem(row, lane, t);
+        } else if constexpr (R == 4) {
+            reinterpret_cast<U4*>(row)[lane] = U4{v.r[0], v.r[1], v.r[2], v.r[3]};
+        } else {
+            reinterpret_cast<U2*>(row)[lane] = U2{v.r[0], v.r[1]};
+        }
+    }
+    /* where column c of a band row sits in a shared-memory ring row */
+    static RP_DEV uint32_t band_elem_smem(uint32_t c) {
+        const uint32_t e = (((c >> 4) & (NB - 1)) << 4) | (perm_band(c) & 15u);
+        return KB == 16 ? swz_e(e) : e;
+    }
     static RP_DEV void syncwarp() { gsync<G>(); }
     static RP_DEV uint32_t ballot(bool p) { return gballot<G>(p); }
     template <typename T> static RP_DEV T shfl(T v, int src) { return gshfl<G, T>(v, src); }
@@ -464,7 +551,7 @@ struct PoaWarp {
         const uint16_t* rk = sub ? dp_rank : rank_of;
         uint32_t pred_rows = 0;
         const uint32_t nblk = (len + 16) >> 4;            // blocks holding columns 0..len
-        const int32_t smax = static_cast<int32_t>(nblk) - G;
+        const int32_t smax = static_cast<int32_t>(nblk) - static_cast<int32_t>(NB);
         int32_t brun = 0;
         /* The graph lives in HBM, so every level of the chain row -> node -> in-edges -> ranks costs a full
          * memory latency.  Rows are handled kU per lane at a time with all loads of one level issued together. */
@@ -493,7 +580,7 @@ struct PoaWarp {
                     uint32_t x = bp[u] > b0 ? bp[u] - b0 : 0u;
                     if (x >= span) x = span - 1;
                     const int32_t cc = static_cast<int32_t>((x * (len + 1)) / span);
-                    int32_t t = (cc + 8) / 16 - G / 2;
+                    int32_t t = (cc + 8) / 16 - static_cast<int32_t>(NB) / 2;
                     t = t > smax ? smax : t;
                     t = t < 0 ? 0 : t;
                     if (r[u] > nrows) t = 0;
@@ -755,20 +842,20 @@ struct PoaWarp {
      * as minus infinity (kBandFloor, also the floor of every stored cell, so excluded regions cannot wrap around
      * int16): banded values are <= the full matrix's and equal to them on every cell of an optimal path that lies
      * inside the band.  traceback<true> decides whether the result can be trusted. */
-    RP_DEV void build_profile_block(const uint8_t* seq, uint32_t len, uint32_t cb) {
+    RP_DEV void build_profile_block(const uint8_t* seq, uint32_t len, uint32_t col0) {
         const int32_t m = P->match, x = P->mismatch;
-        uint8_t ch[16];
+        uint8_t ch[KB];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const uint32_t col = cb * 16u + c;
+        for (int c = 0; c < KB; ++c) {
+            const uint32_t col = col0 + c;
             ch[c] = (col >= 1 && col <= len) ? seq[col - 1] : 0;   // 0 never is a window character
         }
         for (uint32_t k = 0; k < ncodes; ++k) {
             const uint8_t c = static_cast<uint8_t>(alpha >> (8 * k));
-            Row8 v;
+            RowB v;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) v.r[r] = pack16(ch[r] == c ? m : x, ch[8 + r] == c ? m : x);
-            store_row_smem(prof + k * kCC, lane, v);
+            for (int r = 0; r < R; ++r) v.r[r] = pack16(ch[r] == c ? m : x, ch[R + r] == c ? m : x);
+            store_band_smem(prof + k * kBW, lane, v);
         }
     }
 
@@ -776,23 +863,24 @@ struct PoaWarp {
                         int32_t* best_score, uint32_t* n_best) {
         const int32_t g = P->gap;
         const uint32_t g2 = pack16(g, g);
-        const int32_t negsafe = -32768 - 16 * g;
+        const int32_t negsafe = -32768 - KB * g;
         const uint32_t floor2 = pack16(kBandFloor, kBandFloor);
-        uint32_t gb[8], gc[8];
+        uint32_t gb[R], gc[R];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < R; ++r) {
             gb[r] = pack16(0, (r + 1) * g);
-            gc[r] = pack16((r + 1) * g, (r + 9) * g);
+            gc[r] = pack16((r + 1) * g, (r + 1 + R) * g);
         }
         const uint32_t lanem = static_cast<uint32_t>(lane);
-        const uint32_t lane_left = (lanem + G - 1) & (G - 1);   // the lane that holds the block to the left
+        const uint32_t lane_left = (lanem + G - 1) & (G - 1);   // the lane that holds the columns to the left
+        const uint32_t sub_lane = lanem & (LPB - 1);            // which KB-column part of its block the lane holds
         const uint32_t sink_blk = len >> 4;
-        const uint32_t sink_e = swz(((sink_blk & (G - 1)) << 4) | (len & 15u));
+        const uint32_t sink_e = band_elem_smem(len);
         int32_t best = kNeg32;
         uint32_t bi = 0, nb = 0;
         /* rows with the same band start form a segment; predecessors from before the segment need a validity test */
         uint32_t s_cur = 0xffffffffu, seg_i0 = 1, s_prev = 0, prev_i0 = 1;
-        uint32_t cb = 0, pos = 0;          // this lane's block and its position inside the band
+        uint32_t cb = 0, bo = 0;           // this lane's block and its place in band order (0 = leftmost lane)
         uint32_t pcb = 0xffffffffu;        // block whose profile this lane's profile slot holds
         uint32_t rec_a_lo = 0, rec_a_hi = 0, rec_b_lo = 0, rec_b_hi = 0, bsv = 0;
         uint32_t myslot = 0;
@@ -815,45 +903,46 @@ struct PoaWarp {
                 prev_i0 = seg_i0;
                 s_cur = s_i;
                 seg_i0 = i;
-                pos = (lanem - s_cur) & (G - 1);
+                const uint32_t pos = ((lanem / LPB) - s_cur) & (NB - 1);   // block position inside the band
                 cb = s_cur + pos;
+                bo = pos * LPB + sub_lane;
                 if (cb != pcb) {  // only the lanes whose block changed
-                    build_profile_block(seq, len, cb);
+                    build_profile_block(seq, len, cb * 16u + sub_lane * KB);
                     pcb = cb;
                 }
             }
             const uint32_t cidx = lo & 0xff;
             const uint32_t np = (lo >> 8) & 0x7f;
             const bool sink = (lo >> 15) & 1;
-            const Row8 pf = load_row_smem(prof + cidx * kCC, lane);
-            Row8 pm;
-            auto load_pred = [&](uint32_t p, Row8& pr) {
+            const RowB pf = load_band_smem(prof + cidx * kBW, lane);
+            RowB pm;
+            auto load_pred = [&](uint32_t p, RowB& pr) {
                 if (p == 0) {  // virtual root row: H[0][j] = j * g
-                    const int32_t base = static_cast<int32_t>(cb * 16u) * g;
+                    const int32_t base = static_cast<int32_t>(cb * 16u + sub_lane * KB) * g;
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) pr.r[r] = pack16(base + r * g, base + (8 + r) * g);
+                    for (int r = 0; r < R; ++r) pr.r[r] = pack16(base + r * g, base + (R + r) * g);
                     return;
                 }
                 const uint32_t dist = i - p;
                 if (dist < ring_rows) {  // group-uniform
                     const uint32_t slot = myslot >= dist ? myslot - dist : myslot + ring_rows - dist;
-                    pr = load_row_smem(ring + slot * kCC, lane);
+                    pr = load_band_smem(ring + slot * kBW, lane);
                 } else {
-                    pr = load_row_gmem(H + static_cast<uint64_t>(p) * kCC, lane);
+                    pr = load_band_gmem(H + static_cast<uint64_t>(p) * kBW, lane);
                 }
                 if (p < seg_i0) {  // from an earlier segment: its band may not hold this lane's block
                     const uint32_t sp = p >= prev_i0 ? s_prev : static_cast<uint32_t>(bs[p]);
-                    if (cb - sp >= G) {
+                    if (cb - sp >= NB) {
 #pragma unroll
-                        for (int r = 0; r < 8; ++r) pr.r[r] = floor2;
+                        for (int r = 0; r < R; ++r) pr.r[r] = floor2;
                     }
                 }
             };
             auto more = [&](uint32_t p) {
-                Row8 pr;
+                RowB pr;
                 load_pred(p, pr);
 #pragma unroll
-                for (int r = 0; r < 8; ++r) pm.r[r] = vmax_s16x2(pm.r[r], pr.r[r]);
+                for (int r = 0; r < R; ++r) pm.r[r] = vmax_s16x2(pm.r[r], pr.r[r]);
             };
             load_pred(np ? (lo >> 16) : 0u, pm);
             if (np > 1) {
@@ -871,42 +960,42 @@ struct PoaWarp {
                     }
                 }
             }
-            uint32_t acc[8];
+            uint32_t acc[R];
             {
-                uint32_t left = shfl(pm.r[7], lane_left);  // hi half = last column of the block to the left
-                left = pos == 0 ? floor2 : left;           // first block of the band: nothing to its left
-                const uint32_t d0 = byte_perm(left, pm.r[7], 0x5432);
+                uint32_t left = shfl(pm.r[R - 1], lane_left);  // hi half = last column of the lane to the left
+                left = bo == 0 ? floor2 : left;                // leftmost lane of the band: nothing to its left
+                const uint32_t d0 = byte_perm(left, pm.r[R - 1], 0x5432);
                 acc[0] = viaddmax_s16x2(pm.r[0], g2, viaddmax_s16x2(d0, pf.r[0], floor2));
 #pragma unroll
-                for (int r = 1; r < 8; ++r)
+                for (int r = 1; r < R; ++r)
                     acc[r] = viaddmax_s16x2(pm.r[r], g2, viaddmax_s16x2(pm.r[r - 1], pf.r[r], floor2));
             }
 #pragma unroll
-            for (int r = 1; r < 8; ++r) acc[r] = viaddmax_s16x2(acc[r - 1], g2, acc[r]);
-            const uint32_t bridge = byte_perm(acc[7], 0x80008000u, 0x1076);  // lo = INT16_MIN, hi = acc[7].lo
+            for (int r = 1; r < R; ++r) acc[r] = viaddmax_s16x2(acc[r - 1], g2, acc[r]);
+            const uint32_t bridge = byte_perm(acc[R - 1], 0x80008000u, 0x1076);  // lo = INT16_MIN, hi = acc[R-1].lo
 #pragma unroll
-            for (int r = 0; r < 8; ++r) acc[r] = viaddmax_s16x2(bridge, gb[r], acc[r]);
-            /* max-plus scan of the lane totals in band order (the band starts at lane s_cur mod G) */
-            int32_t t = hi16(acc[7]);
+            for (int r = 0; r < R; ++r) acc[r] = viaddmax_s16x2(bridge, gb[r], acc[r]);
+            /* max-plus scan of the lane totals in band order (the band starts at lane s_cur * LPB mod G) */
+            int32_t t = hi16(acc[R - 1]);
 #pragma unroll
             for (int dd = 1; dd < G; dd <<= 1) {
                 const int32_t o = shfl(t, (lanem - dd) & (G - 1));
-                t = viaddmax_s32(pos >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * 16 * g, t);
+                t = viaddmax_s32(bo >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * KB * g, t);
             }
             int32_t carry = shfl(t, lane_left);
-            carry = pos == 0 ? kNeg32 : carry;
+            carry = bo == 0 ? kNeg32 : carry;
             carry = carry < negsafe ? negsafe : carry;
             const uint32_t c2 = pack16(carry, carry);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) acc[r] = viaddmax_s16x2(c2, gc[r], acc[r]);
-            Row8 out;
+            for (int r = 0; r < R; ++r) acc[r] = viaddmax_s16x2(c2, gc[r], acc[r]);
+            RowB out;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) out.r[r] = acc[r];
-            int16_t* myrow_s = ring + myslot * kCC;
-            store_row_smem(myrow_s, lane, out);
-            store_row_gmem(H + static_cast<uint64_t>(i) * kCC, lane, out);
+            for (int r = 0; r < R; ++r) out.r[r] = acc[r];
+            int16_t* myrow_s = ring + myslot * kBW;
+            store_band_smem(myrow_s, lane, out);
+            store_band_gmem(H + static_cast<uint64_t>(i) * kBW, lane, out);
             syncwarp();
-            if (sink && sink_blk - s_cur < G) {  // group-uniform
+            if (sink && sink_blk - s_cur < NB) {  // group-uniform
                 const int32_t sc = myrow_s[sink_e];
                 if (sc > best) {
                     best = sc;
@@ -1139,8 +1228,8 @@ struct PoaWarp {
         if (!BAND) return H[static_cast<uint64_t>(r) * lpa + perm(c)];
         if (r == 0) return static_cast<int32_t>(c) * g;
         const uint32_t cbk = c >> 4;
-        if (cbk - bs[r] >= G) return kBandFloor;
-        return H[static_cast<uint64_t>(r) * kCC + ((cbk & (G - 1)) << 4) + (perm(c) & 15u)];
+        if (cbk - bs[r] >= NB) return kBandFloor;
+        return H[static_cast<uint64_t>(r) * kBW + ((cbk & (NB - 1)) << 4) + (perm_band(c) & 15u)];
     }
 
     template <bool BAND>
@@ -1182,9 +1271,9 @@ struct PoaWarp {
                 if (p != 0) {
                     const uint32_t sp = bs[p];
                     const int32_t dlp = static_cast<int32_t>(j) - 1 - static_cast<int32_t>(16u * sp);
-                    const int32_t drp = static_cast<int32_t>(16u * (sp + G)) - 1 - static_cast<int32_t>(j);
+                    const int32_t drp = static_cast<int32_t>(16u * (sp + NB)) - 1 - static_cast<int32_t>(j);
                     unsure |= (sp > 0 && dlp < static_cast<int32_t>(margin)) ||
-                              (sp + G < nblk && drp < static_cast<int32_t>(margin));
+                              (sp + NB < nblk && drp < static_cast<int32_t>(margin));
                 }
             }
         }
@@ -1226,32 +1315,36 @@ struct PoaWarp {
                 const uint32_t cbj = j >> 4;
                 const uint32_t cba = cbj ? cbj - 1 : 0;
                 t_col0 = cba << 4;
-                for (uint32_t q = lane; q < t_rows; q += G) {
+                /* four lanes per tile row, one 16-byte granule each: consecutive lanes write consecutive 16-byte
+                 * granules of the tile (no shared-memory bank conflict) and read one 64-byte piece of an H row */
+                for (uint32_t e = lane; e < 4 * t_rows; e += G) {
+                    const uint32_t q = e >> 2, gq = e & 3u;
                     const uint32_t rk = t_top - q;
-                    U4* dst = reinterpret_cast<U4*>(tile + q * kTileCols);
+                    U4 v;
                     if (BAND) {
                         const uint32_t sr = bs[rk];
-                        if (rk == 0) {
-                            for (uint32_t c = 0; c < kTileCols; ++c)
-                                tile[q * kTileCols + perm(t_col0 + c) - t_col0] =
-                                    static_cast<int16_t>(static_cast<int32_t>(t_col0 + c) * g);
+                        const uint32_t blk = cba + (gq >> 1);
+                        if (rk == 0) {  // virtual root row: H[0][c] = c * g, in the row's register order
+                            int16_t t8[8];
+#pragma unroll
+                            for (uint32_t k = 0; k < 8; ++k) {
+                                const uint32_t el = (gq & 1u) * 8 + k;                  // element inside the block
+                                const uint32_t col = blk * 16 + unperm_band(el);
+                                t8[k] = static_cast<int16_t>(static_cast<int32_t>(col) * g);
+                            }
+                            v = U4{pack16(t8[0], t8[1]), pack16(t8[2], t8[3]), pack16(t8[4], t8[5]), pack16(t8[6], t8[7])};
+                        } else if (blk - sr >= NB) {
+                            v = f4;
                         } else {
-                            const int16_t* rowb = H + static_cast<uint64_t>(rk) * kCC;
-                            const U4* sa = reinterpret_cast<const U4*>(rowb + ((cba & (G - 1)) << 4));
-                            const U4* sb = reinterpret_cast<const U4*>(rowb + (((cba + 1) & (G - 1)) << 4));
-                            U4 a = sa[0], b = sa[1], c = sb[0], d = sb[1];
-                            if (cba - sr >= G) a = b = f4;
-                            if (cba + 1 - sr >= G) c = d = f4;
-                            dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+                            v = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * kBW + ((blk & (NB - 1)) << 4))[gq & 1u];
                         }
-                        tbs[q] = static_cast<uint8_t>(sr);
+                        if (gq == 0) tbs[q] = static_cast<uint8_t>(sr);
                     } else {
-                        const U4* src = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0);
-                        U4 a = src[0], b = src[1], c = src[2], d = src[3];
-                        dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+                        v = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0)[gq];
                     }
-                    trec[q] = rec[rk];
+                    reinterpret_cast<U4*>(tile)[e] = v;
                 }
+                for (uint32_t q = lane; q < t_rows; q += G) trec[q] = rec[t_top - q];
                 have_tile = true;
                 syncwarp();
             }
@@ -1260,13 +1353,13 @@ struct PoaWarp {
             const uint32_t lo = static_cast<uint32_t>(rc.a);
             const uint32_t cidx = lo & 0xff, np = (lo >> 8) & 0x7f;
             const uint32_t npe = np ? np : 1;
-            const uint32_t ej = perm(j) - t_col0;                      // element of column j inside a tile row
-            const uint32_t ejm = j > 0 ? perm(j - 1) - t_col0 : 0;     // column j-1
+            const uint32_t ej = (BAND ? perm_band(j) : perm(j)) - t_col0;   // element of column j inside a tile row
+            const uint32_t ejm = j > 0 ? (BAND ? perm_band(j - 1) : perm(j - 1)) - t_col0 : 0;     // column j-1
             const int32_t hij = tile[q * kTileCols + ej];
             if (BAND) {
                 const uint32_t si = tbs[q];
-                const uint32_t dl = j - 16u * si, dr = 16u * (si + G) - 1u - j;
-                if ((si > 0 && dl < margin) || (si + G < nblk && dr < margin) || hij < worst) {  // group-uniform
+                const uint32_t dl = j - 16u * si, dr = 16u * (si + NB) - 1u - j;
+                if ((si > 0 && dl < margin) || (si + NB < nblk && dr < margin) || hij < worst) {  // group-uniform
                     bad = true;
                     break;
                 }
@@ -1300,9 +1393,9 @@ struct PoaWarp {
                          * cut closer than the margin to these columns (or does not hold them at all) could hide a tie
                          * the full matrix would have resolved the other way */
                         const int32_t dlp = static_cast<int32_t>(j) - 1 - static_cast<int32_t>(16u * sp);
-                        const int32_t drp = static_cast<int32_t>(16u * (sp + G)) - 1 - static_cast<int32_t>(j);
+                        const int32_t drp = static_cast<int32_t>(16u * (sp + NB)) - 1 - static_cast<int32_t>(j);
                         unsure = (sp > 0 && dlp < static_cast<int32_t>(margin)) ||
-                                 (sp + G < nblk && drp < static_cast<int32_t>(margin));
+                                 (sp + NB < nblk && drp < static_cast<int32_t>(margin));
                     }
                 }
                 if (BAND && ballot(unsure)) {  // group-uniform
@@ -1313,7 +1406,8 @@ struct PoaWarp {
                 const uint32_t mv = ballot(okv);
                 const uint32_t sel = md ? md : mv;
                 if (sel) {
-                    found_p = shfl(p, ffs_(sel) - 1);
+                    const uint32_t kw = static_cast<uint32_t>(ffs_(sel) - 1);   // winning lane = its predecessor's index
+                    found_p = kw < 7 ? (np ? rec_pred(rc, kw) : 0u) : shfl(p, static_cast<int>(kw));
                     move = md ? 1 : 2;
                 }
             } else {
@@ -1819,10 +1913,13 @@ RP_DEV bool fits_int16(int32_t m, int32_t g, int64_t len, int64_t nodes) {
 }
 
 /* Processes one window end to end. `slot`: this group's HBM scratch, `smem`: this group's shared memory. */
-template <int G>
+template <int G, int KB = 16>
 RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* smem) {
-    constexpr uint32_t kCC = PoaWarp<G>::kCC;
-    PoaWarp<G> W;
+    using PW = PoaWarp<G, KB>;
+    constexpr uint32_t kCC = PW::kCC;
+    constexpr uint32_t kBW = PW::kBW;
+    constexpr uint32_t NB = PW::NB;
+    PW W;
     W.bind(&P, slot, smem, P.smem_per_group);
     W.status = kWinOk;
     const uint32_t s0 = P.win_first[w], s1 = P.win_first[w + 1];
@@ -1883,7 +1980,7 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         const uint32_t lpa = (len + 1 + kCC - 1) / kCC * kCC;
         /* shared memory (chunk-local): profile chunk | ring of the last R DP rows; the traceback re-uses it */
         const uint32_t prof_bytes = W.ncodes * kCC * 2;
-        const uint32_t tb_bytes = 8 * PoaWarp<G>::kTileRowBytes + 32 + len;  // at least 8 tile rows + the read
+        const uint32_t tb_bytes = 8 * PW::kTileRowBytes + 32 + len;  // at least 8 tile rows + the read
         if (prof_bytes + 2 * kCC * 2 > P.smem_per_group || tb_bytes > P.smem_per_group) {
             W.fail(kWinSeqTooLong);
             break;
@@ -1896,15 +1993,21 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
          * than the band, band starts fit a byte, the band rows fit the matrix scratch, and real scores are
          * separated from anything derived from an excluded cell (worst > kBandFloor + match * len). */
         const uint32_t nblk = (len + 16) >> 4;
-        const bool band = P.banded && nblk > static_cast<uint32_t>(G) && nblk - G <= 255u && fits &&
+        const bool band = P.banded && nblk > NB && nblk - NB <= 255u && fits &&
                           worst > static_cast<int64_t>(kBandFloor) + static_cast<int64_t>(P.match > 0 ? P.match : 0) * (len + 8) &&
-                          static_cast<uint64_t>(nrows + 1) * kCC <= P.lim.hcap;
+                          static_cast<uint64_t>(nrows + 1) * kBW <= P.lim.hcap;
         uint32_t pred_rows = W.build_program(nrows, sub, band, len, b0, span);
         uint32_t best_row, n_best;
         int32_t best;
         bool done = false;
         if (band) {
-            W.dp_band(seq, nrows, len, ring_rows, &best_row, &best, &n_best);
+            /* the band's profile and ring rows are narrower than a full chunk's: more ring rows fit */
+            const uint32_t bprof = W.ncodes * kBW * 2;
+            uint32_t bring = (P.smem_per_group - bprof) / (kBW * 2);
+            if (bring > 32) bring = 32;
+            W.ring = reinterpret_cast<int16_t*>(smem + bprof);
+            W.dp_band(seq, nrows, len, bring, &best_row, &best, &n_best);
+            W.ring = reinterpret_cast<int16_t*>(smem + prof_bytes);
             done = best_row != 0;
             if (done && n_best > 1) {
                 best_row = W.template resolve_sink_tie<true>(nrows, len, lpa, best, sub);
@@ -1960,7 +2063,7 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
         if (P.stats) pred_rows = W.warp_incl_sum(pred_rows);
         if (P.stats) pred_rows = W.shfl(pred_rows, G - 1);
         if (P.stats && lane == 0) {
-            const unsigned long long cols = (band && done) ? kCC : len + 1;   // columns the accepted DP computed per row
+            const unsigned long long cols = (band && done) ? kBW : len + 1;   // columns the accepted DP computed per row
 #if !defined(RP_HOST_SIM)
             atomicAdd(reinterpret_cast<unsigned long long*>(P.stats + 3), static_cast<unsigned long long>(pred_rows) * cols);
             atomicAdd(reinterpret_cast<unsigned long long*>(P.stats), 1ull);

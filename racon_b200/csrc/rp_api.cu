@@ -74,7 +74,7 @@ constexpr int kWarpsPerBlock = 4;
  * windows from an atomic queue — 32/G windows in flight per warp, advancing together wherever their control
  * flow agrees.  Compiled for several group widths and occupancy points (blocks per SM -> register cap);
  * RP_POA_GROUP / RP_BLOCKS_PER_SM select one (defaults in rp_poa_create). */
-template <int G, int kBlocksPerSm>
+template <int G, int KB, int kBlocksPerSm>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kernel(rp::PoaParams P) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const uint32_t grp = threadIdx.x / G;
@@ -86,25 +86,37 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kern
         if (rp::glane<G>() == 0) q = atomicAdd(P.queue_head, 1u);
         q = rp::gshfl<G>(q, 0);
         if (q >= P.n_windows) break;
-        rp::poa_window<G>(P, P.queue[q], slot, smem);
+        rp::poa_window<G, KB>(P, P.queue[q], slot, smem);
     }
 }
 
 typedef void (*PoaKernel)(rp::PoaParams);
-template <int G>
+/* lanes per window x columns per lane of a banded row x blocks per SM (register cap) */
+template <int G, int KB>
 PoaKernel pick_kernel_g(int blocks_per_sm) {
     switch (blocks_per_sm) {
-        case 2: return rp_poa_kernel<G, 2>;
-        case 3: return rp_poa_kernel<G, 3>;
-        case 6: return rp_poa_kernel<G, 6>;
-        default: return rp_poa_kernel<G, 4>;
+        case 2: return rp_poa_kernel<G, KB, 2>;
+        case 3: return rp_poa_kernel<G, KB, 3>;
+        case 6: return rp_poa_kernel<G, KB, 6>;
+        default: return rp_poa_kernel<G, KB, 4>;
     }
 }
-PoaKernel pick_kernel(int group, int blocks_per_sm) {
+template <int KB>
+PoaKernel pick_kernel_narrow(int blocks_per_sm) {   // 32 lanes, narrow banded rows: few registers per row
+    switch (blocks_per_sm) {
+        case 4: return rp_poa_kernel<32, KB, 4>;
+        case 5: return rp_poa_kernel<32, KB, 5>;
+        case 8: return rp_poa_kernel<32, KB, 8>;
+        default: return rp_poa_kernel<32, KB, 6>;
+    }
+}
+PoaKernel pick_kernel(int group, int band_k, int blocks_per_sm) {
+    if (group == 32 && band_k == 4) return pick_kernel_narrow<4>(blocks_per_sm);
+    if (group == 32 && band_k == 8) return pick_kernel_narrow<8>(blocks_per_sm);
     switch (group) {
-        case 8: return pick_kernel_g<8>(blocks_per_sm);
-        case 16: return pick_kernel_g<16>(blocks_per_sm);
-        default: return pick_kernel_g<32>(blocks_per_sm);
+        case 8: return pick_kernel_g<8, 16>(blocks_per_sm);
+        case 16: return pick_kernel_g<16, 16>(blocks_per_sm);
+        default: return pick_kernel_g<32, 16>(blocks_per_sm);
     }
 }
 
@@ -177,6 +189,7 @@ struct rp_poa {
     PoaKernel kernel = nullptr;
     int blocks_per_sm = 4;
     int group = 32;                // lanes per window
+    int band_k = 16;               // columns per lane of a banded row
     uint32_t groups_per_block = 4;
     bool uploaded = false, launched = false, downloaded = false, synced = false;
     bool counters = false;
@@ -299,19 +312,27 @@ static rp_status configure(rp_poa* p, uint32_t wl) {
     /* tests only: recompute every accepted band result with the full matrix and count the differences */
     if (const char* e_a = getenv("RP_BAND_AUDIT")) p->P.debug_flags = atoi(e_a) ? 2u : 0u;
 
-    /* launch shape: persistent blocks of 4 warps = 128/G lane groups, kBlocksPerSm blocks per SM */
-    int group = banded ? 8 : 32;
+    /* launch shape: persistent blocks of 4 warps = 128/G lane groups, kBlocksPerSm blocks per SM.  Defaults measured on
+     * B200 (profiles/README.md, round 2): full matrix: 32 lanes per window, 16 columns per lane, 4 blocks/SM; banded
+     * (-b): 32 lanes x 4 columns = a 128-column band — two packed registers per row instead of eight. */
+    int group = 32;
     if (const char* e_g = getenv("RP_POA_GROUP")) group = atoi(e_g);
-    if (group != 8 && group != 16 && group != 32) group = banded ? 8 : 32;
-    /* measured on B200 (profiles/README.md, round 2): full matrix: 32 lanes per window, 4 blocks/SM; banded: 8 lanes per
-     * window (128-column band), 3 blocks/SM */
-    int bps = (banded && group == 8) ? 3 : 4;
+    if (group != 8 && group != 16 && group != 32) group = 32;
+    int band_k = (banded && group == 32) ? 4 : 16;
+    if (const char* e_k = getenv("RP_POA_BAND_K")) band_k = atoi(e_k);
+    if (group != 32 || (band_k != 4 && band_k != 8)) band_k = 16;
+    int bps = band_k == 16 ? 4 : 6;
     if (const char* e_bps = getenv("RP_BLOCKS_PER_SM")) bps = atoi(e_bps);
-    if (bps != 2 && bps != 3 && bps != 6) bps = 4;
+    if (band_k == 16) {
+        if (bps != 2 && bps != 3 && bps != 6) bps = 4;
+    } else if (bps != 4 && bps != 5 && bps != 8) {
+        bps = 6;
+    }
     p->group = group;
+    p->band_k = band_k;
     p->groups_per_block = kWarpsPerBlock * 32 / group;
     p->blocks_per_sm = bps;
-    p->kernel = pick_kernel(group, bps);
+    p->kernel = pick_kernel(group, band_k, bps);
     uint32_t smem_per_sm = static_cast<uint32_t>(prop.sharedMemPerMultiprocessor);
     uint32_t per_block = smem_per_sm / bps - 1024;                              // 1 KB reserved per block
     if (per_block > prop.sharedMemPerBlockOptin) per_block = static_cast<uint32_t>(prop.sharedMemPerBlockOptin);
@@ -334,7 +355,8 @@ static rp_status configure(rp_poa* p, uint32_t wl) {
      * by the escalation pass); only then fewer workers */
     const uint64_t hcap_full = static_cast<uint64_t>(lim.nmax + 1) * lim.lp;
     const uint64_t hcap_min = std::min<uint64_t>(
-        hcap_full, static_cast<uint64_t>(4 * wl + 64) * (((wl + wl / 4 + wl / 32 + 1) + 127) / 128 * 128));
+        hcap_full, static_cast<uint64_t>(4 * wl + 64) *
+                       (((wl + wl / 4 + wl / 32 + 1) + 16 * group - 1) / (16 * group) * (16 * group)));
     lim.hcap = 0;
     const uint64_t fixed_bytes = rp::make_layout(lim).bytes;
     uint64_t hcap = hcap_full;
@@ -761,7 +783,7 @@ rp_status rp_poa_band_info(rp_poa* p, uint64_t info[8]) {
     info[0] = p->banded ? 1 : 0;
     info[1] = p->h_band[0];
     info[2] = p->h_band[1];
-    info[3] = static_cast<uint64_t>(p->group) * 16;
+    info[3] = static_cast<uint64_t>(p->group) * p->band_k;
     info[4] = p->h_band[2];
     return RP_OK;
 }

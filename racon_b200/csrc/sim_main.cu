@@ -40,10 +40,10 @@ void aln_entry(void* arg) {
     rp::aln_pair(*j->P, j->p, j->slot);
 }
 
-template <int G>
+template <int G, int KB>
 void group_entry(void* arg) {
     Job* j = static_cast<Job*>(arg);
-    rp::poa_window<G>(*j->P, j->w, j->slot, j->smem);
+    rp::poa_window<G, KB>(*j->P, j->w, j->slot, j->smem);
 }
 
 }  // namespace
@@ -157,7 +157,8 @@ int rp_sim_pack_only(uint32_t n_windows, const char* bases, const char* quals, c
 }
 
 /* Flat window set in, consensus out.  limits: {nmax, lmax, ki, ka, smem_per_group, tile_rows, debug_flags,
- * lanes per group (8/16/32), banded, band margin, matrix scratch cells (0 = nmax x padded lmax)}.  With banded,
+ * lanes per group (8/16/32), banded, band margin, matrix scratch cells (0 = nmax x padded lmax), columns per lane
+ * of a banded row (16/8/4; 8 and 4 only with 32 lanes)}.  With banded,
  * stats[4] = alignments tried in the band, stats[5] = redone with the full matrix.  Returns 0 or <0. */
 int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
                const uint8_t* seq_has_qual, const uint32_t* seq_begin, const uint32_t* seq_end,
@@ -233,12 +234,17 @@ int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const u
 
     for (uint32_t q = 0; q < pb.n_gpu(); ++q) {
         Job job{&P, pb.queue.data[q], slot_al, smem_al};
+        const uint32_t kb = limits[11] ? limits[11] : 16;   // columns per lane of a banded row
         if (lanes == 8)
-            rp::sim::run_warp(group_entry<8>, &job, 256 * 1024, 8);
+            rp::sim::run_warp(group_entry<8, 16>, &job, 256 * 1024, 8);
         else if (lanes == 16)
-            rp::sim::run_warp(group_entry<16>, &job, 256 * 1024, 16);
+            rp::sim::run_warp(group_entry<16, 16>, &job, 256 * 1024, 16);
+        else if (kb == 4)
+            rp::sim::run_warp(group_entry<32, 4>, &job, 256 * 1024, 32);
+        else if (kb == 8)
+            rp::sim::run_warp(group_entry<32, 8>, &job, 256 * 1024, 32);
         else
-            rp::sim::run_warp(group_entry<32>, &job, 256 * 1024, 32);
+            rp::sim::run_warp(group_entry<32, 16>, &job, 256 * 1024, 32);
     }
 
     for (uint32_t w = 0; w < n_windows; ++w) {

@@ -34,7 +34,7 @@ def _ptr(a):
 
 
 def sim_consensus(ws, m=3, x=-5, g=-4, trim=True, nmax=4096, lmax=1535, ki=16, ka=8, smem=14336, tile_rows=0, debug_flags=0,
-                  lanes=32, banded=0, band_margin=16, hcap=0):
+                  lanes=32, banded=0, band_margin=16, hcap=0, band_cols_per_lane=16):
     n = ws.n_windows
     lens = np.diff(ws.seq_off.astype(np.int64))
     stride = int(max(64, 2 * lens.max() + 64))
@@ -44,7 +44,8 @@ def sim_consensus(ws, m=3, x=-5, g=-4, trim=True, nmax=4096, lmax=1535, ki=16, k
     pol = np.zeros(n, dtype=np.uint8)
     st = np.zeros(n, dtype=np.uint32)
     stats = np.zeros(8, dtype=np.uint64)
-    limits = np.asarray([nmax, lmax, ki, ka, smem, tile_rows, debug_flags, lanes, banded, band_margin, hcap], dtype=np.uint32)
+    limits = np.asarray([nmax, lmax, ki, ka, smem, tile_rows, debug_flags, lanes, banded, band_margin, hcap,
+                         band_cols_per_lane], dtype=np.uint32)
     r = lib().rp_sim_poa(n, _ptr(ws.bases), _ptr(ws.quals), _ptr(ws.seq_off), _ptr(ws.seq_has_qual),
                          _ptr(ws.seq_begin), _ptr(ws.seq_end), _ptr(ws.win_first), _ptr(ws.win_type), m, x, g,
                          1 if trim else 0, limits.ctypes.data, out.ctypes.data, stride, out_len.ctypes.data,

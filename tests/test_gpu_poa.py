@@ -251,7 +251,7 @@ def test_gpu_memory_budget_back_pressure():
     n = 2000
     ws, _ = windows.synth_windows(n, err=0.12)
     free0 = torch.cuda.mem_get_info()[0]
-    budget = 256 << 20
+    budget = 192 << 20
     b = api.PoaBatch(mem_bytes=budget, window_length=500)
     stride = 1200
     cons, batches, first = [], 0, 0
@@ -271,7 +271,7 @@ def test_gpu_memory_budget_back_pressure():
         first += took
         batches += 1
     b.close()
-    assert batches >= 3, "a 256 MB object swallowed %d windows in %d batches: the budget is not enforced" % (n, batches)
+    assert batches >= 3, "a 192 MB object swallowed %d windows in %d batches: the budget is not enforced" % (n, batches)
     assert peak_used <= budget * 1.25 + (64 << 20), "device memory in use %d MB for a %d MB budget" % (peak_used >> 20, budget >> 20)
     ref, _, _ = api.consensus(ws)
     assert cons == ref

@@ -249,3 +249,28 @@ def test_sim_band_audit_finds_no_differing_alignment():
     ws = util.make_set(12, 2, wlen=500, depth=20, err=0.12, partial_frac=0.3, with_qual=True)
     stats = _check(ws, lanes=8, smem=3584, banded=1, debug_flags=2)
     assert stats[4] > 0 and stats[6] == 0
+
+
+@pytest.mark.parametrize("kb", [4, 8])
+@pytest.mark.parametrize("name", sorted(BAND_CASES))
+def test_sim_narrow_banded_rows_equal_oracle(name, kb):
+    """racon -b default layout: 32 lanes x 4 (or 8) columns per lane — a 128- (256-) column band held in two (four) packed
+    registers per lane; band audit on (every accepted band result recomputed with the full matrix: no difference)."""
+    kw = dict(BAND_CASES[name])
+    ws = util.make_set(7, kw.pop("n"), **kw)
+    stats = _check(ws, lanes=32, smem=9216, banded=1, nmax=8192, lmax=2047, band_cols_per_lane=kb, debug_flags=2)
+    assert stats[6] == 0
+    if 32 * kb < kw["wlen"] // 2:
+        assert stats[4] > 0, "no alignment went through the band"
+
+
+def test_sim_narrow_band_refusal_and_other_scores():
+    ws = util.make_set(9, 2, wlen=400, depth=10, err=0.12, partial_frac=0.3)
+    stats = _check(ws, lanes=32, smem=9216, banded=1, band_margin=56, band_cols_per_lane=4)
+    assert stats[4] > 0 and stats[5] == stats[4]
+    ws = util.make_set(8, 2, wlen=400, depth=12, err=0.15, partial_frac=0.3, with_qual=True)
+    for scores in ((5, -4, -8), (1, -1, -1)):
+        _check(ws, scores=scores, lanes=32, smem=9216, banded=1, band_cols_per_lane=4, debug_flags=2)
+    ws = util.make_set(101, 32, wlen=300, depth=40, err=0.3).subset([0, 12])
+    stats = _check(ws, lanes=32, smem=9216, banded=1, band_cols_per_lane=4, debug_flags=2)
+    assert stats[4] > 0 and stats[6] == 0

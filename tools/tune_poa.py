@@ -1,6 +1,6 @@
 """Kernel-only throughput of rp_poa_kernel over its launch-shape knobs (lanes per window, blocks per SM, banded),
 inputs resident in HBM, CUDA-event timed.  A tuning aid; bench.py is the judged measurement.
-  python tools/tune_poa.py [--windows 10000] [--configs "b,g,bps;..."]"""
+  python tools/tune_poa.py [--windows 10000] [--configs "banded,lanes,blocks_per_sm[,band columns per lane];..."]"""
 import argparse
 import json
 import os
@@ -26,9 +26,12 @@ def main():
     stride = int(2 * np.diff(ws.seq_off.astype(np.int64)).max() + 64)
     ref = None
     for cfg in args.configs.split(";"):
-        banded, g, bps = (int(x) for x in cfg.split(","))
+        f = [int(x) for x in cfg.split(",")]
+        banded, g, bps = f[:3]
+        k = f[3] if len(f) > 3 else 16
         os.environ["RP_POA_GROUP"] = str(g)
         os.environ["RP_BLOCKS_PER_SM"] = str(bps)
+        os.environ["RP_POA_BAND_K"] = str(k)
         try:
             b = api.PoaBatch(device=0, window_length=500, banded=bool(banded), mem_bytes=int(60e9))
             st = torch.cuda.current_stream()
@@ -53,7 +56,7 @@ def main():
             torch.cuda.synchronize()
             ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.reps)]
             info = b.info()
-            res = {"banded": banded, "lanes": g, "blocks_per_sm": bps, "ms": [round(x, 2) for x in ms],
+            res = {"banded": banded, "lanes": g, "blocks_per_sm": bps, "band_cols_per_lane": k, "ms": [round(x, 2) for x in ms],
                    "windows_per_s": round(ws.n_windows / (min(ms) * 1e-3)), "workers": info["workers"],
                    "scratch_MB_per_worker": round(info["scratch_bytes_per_worker"] / 1e6, 2),
                    "bad_status": int((status != 0).sum()), "fnv200": ck, "same_as_first": full == ref,
