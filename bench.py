@@ -453,8 +453,7 @@ def main():
     def finalize(parts):
         out, lens, pol, st = (np.concatenate([p[i] for p in parts]) for i in range(4))
         if distributed:  # the one exchange step of the path: final consensus gather over NCCL
-            flat = np.concatenate([out[i, :lens[i]] for i in range(len(lens))])
-            last["gathered"] = shard.gather_packed(flat, lens, device="cuda")
+            last["gathered"] = shard.gather_rows(out, lens, device="cuda", dst=0)
         last["out"], last["lens"] = out, lens
 
     def plugin_steps(n_steps):

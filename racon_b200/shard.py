@@ -68,3 +68,43 @@ def gather_consensus(cons, device=None, group=None):
             out.append(bb[off:off + int(ll[k])].tobytes())
             off += int(ll[k])
     return out
+
+
+def gather_rows(out, lens, device=None, group=None, dst=0):
+    """The final consensus gather as ONE data collective: every rank contributes its fetch_all() result (`out`: [n, stride]
+    uint8 rows, `lens`: uint32 [n]) as a fixed-size block [n_max, 4 + len_max] (length prefix + padded row), gathered with
+    all_gather_into_tensor on `device` (NCCL over NVLink on the GPU box; a 2-int all_reduce fixes n_max / len_max first).
+    Only rank `dst` copies the gathered block back to the host and returns [(rows_r, lens_r)] in rank (= window) order;
+    the other ranks return None."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = device if device is not None else "cpu"
+    n = int(len(lens))
+    lmax = int(lens.max()) if n else 0
+    dims = torch.tensor([n, lmax], dtype=torch.int64, device=dev)
+    dist.all_reduce(dims, op=dist.ReduceOp.MAX, group=group)
+    n_max, l_max = int(dims[0]), max(4, (int(dims[1]) + 3) // 4 * 4)
+    block = np.zeros((n_max + 1, 4 + l_max), dtype=np.uint8)      # row 0: this rank's window count
+    block[0, :4] = np.asarray([n], dtype="<u4").view(np.uint8)
+    block[1:n + 1, :4] = np.asarray(lens, dtype="<u4").view(np.uint8).reshape(n, 4)
+    w = min(l_max, out.shape[1]) if n else 0
+    block[1:n + 1, 4:4 + w] = out[:n, :w]
+    mine = torch.from_numpy(block).to(dev)
+    gathered = torch.empty((world,) + block.shape, dtype=torch.uint8, device=dev)
+    try:
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    except Exception:  # a backend without the flat variant
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        gathered = torch.stack(parts)
+    if rank != dst:
+        return None
+    g = gathered.cpu().numpy()
+    res = []
+    for r in range(world):
+        nr = int(g[r, 0, :4].copy().view("<u4")[0])
+        ll = g[r, 1:nr + 1, :4].copy().view("<u4").reshape(-1)
+        res.append((g[r, 1:nr + 1, 4:], ll.astype(np.uint32)))
+    return res

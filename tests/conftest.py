@@ -10,3 +10,24 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _device_count():
+    try:
+        from racon_b200 import api
+        return api.load(build_if_missing=False).rp_device_count()
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped, not failed, on a machine without a CUDA device (plain `pytest` on the CPU container).
+    The product itself still fails loudly there: tests/test_abi.py::test_no_device_means_hard_error_not_fallback."""
+    if not any("gpu" in item.keywords for item in items):
+        return
+    if _device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device: GPU parity tests run on the B200 box (pytest -m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

@@ -29,6 +29,19 @@ def _worker(rank, world, port, n_windows, ret):
     cons, pol, st, _, _ = simlib.sim_consensus(ws.subset(range(lo, hi)))
     assert (st == 0).all()
     full = shard.gather_consensus(cons)
+    # the array form the bench uses: one data collective, result on rank 0 only
+    stride = 200
+    out = np.zeros((len(cons), stride), np.uint8)
+    lens = np.zeros(len(cons), np.uint32)
+    for k, c in enumerate(cons):
+        out[k, :len(c)] = np.frombuffer(c, np.uint8)
+        lens[k] = len(c)
+    rows = shard.gather_rows(out, lens, dst=0)
+    if rank == 0:
+        flat = [rr[k, :ll[k]].tobytes() for rr, ll in rows for k in range(len(ll))]
+        assert flat == full
+    else:
+        assert rows is None
     ret[rank] = full
     dist.barrier()
     dist.destroy_process_group()
@@ -63,3 +76,42 @@ def test_two_rank_gloo_shard_and_gather():
     ws = util.make_set(123, n, wlen=60, depth=5, err=0.12, partial_frac=0.3)
     ora, _, _ = ob.oracle_consensus(ws, threads=2)
     assert list(ret[0]) == ora and list(ret[1]) == ora
+
+
+def test_cost_balanced_ranges():
+    """contiguous ranges balanced by the estimated cost sum_s L_s * (len_b + 0.1 * sum_{k<s} L_k)."""
+    from racon_b200 import shard, windows
+    from tests import util
+    ws = util.make_set(5, 40, wlen=120, depth=8, err=0.1, partial_frac=0.4)
+    cost = windows.window_costs(ws)
+    # the vectorised cost equals the formula evaluated window by window
+    for w in (0, 7, 39):
+        win = ws.window(w)
+        lb = len(win[0][0])
+        acc, want = 0.0, 0.0
+        for (b, _, _, _) in win[1:]:
+            want += len(b) * (lb + 0.1 * acc)
+            acc += len(b)
+        assert abs(cost[w] - want) < 1e-6 * max(1.0, want)
+    heavy = np.concatenate([cost[:20] * 10, cost[20:]])     # the first half ten times more expensive
+    for world in (1, 2, 3, 8):
+        b = [shard.shard_bounds_by_cost(heavy, r, world) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == len(heavy) and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        loads = [heavy[lo:hi].sum() for lo, hi in b]
+        assert max(loads) <= heavy.sum() / world + heavy.max() + 1e-9
+    sl = windows.slice_windows(ws, 10, 25)
+    assert sl.n_windows == 15 and sl.window(0) == ws.window(10) and sl.window(14) == ws.window(24)
+
+
+def test_ngs_generator_shape():
+    """BASELINE config 4 windows: all layers partial-span with qualities, kNGS, begin < end < backbone length."""
+    from racon_b200 import windows
+    ws, _ = windows.synth_ngs_windows(50)
+    assert (ws.win_type == 0).all() and ws.quals is not None
+    for w in (0, 17, 49):
+        win = ws.window(w)
+        bl = len(win[0][0])
+        assert 190 <= bl <= 210 and win[0][1] is None and len(win) > 40
+        for (b, q, s, e) in win[1:]:
+            assert q is not None and len(q) == len(b) and 4 <= len(b) <= 150 and s < e < bl
+            assert min(q) >= 33 + 30 and max(q) <= 33 + 40
