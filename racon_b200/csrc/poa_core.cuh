@@ -1228,8 +1228,9 @@ struct PoaWarp {
         if (!BAND) return H[static_cast<uint64_t>(r) * lpa + perm(c)];
         if (r == 0) return static_cast<int32_t>(c) * g;
         const uint32_t cbk = c >> 4;
-        if (cbk - bs[r] >= NB) return kBandFloor;
-        return H[static_cast<uint64_t>(r) * kBW + ((cbk & (NB - 1)) << 4) + (perm_band(c) & 15u)];
+        const uint32_t sr = bs[r];   // independent of the cell's address: the two loads overlap
+        const int32_t v = H[static_cast<uint64_t>(r) * kBW + ((cbk & (NB - 1)) << 4) + (perm_band(c) & 15u)];
+        return cbk - sr >= NB ? kBandFloor : v;
     }
 
     template <bool BAND>
@@ -1317,7 +1318,8 @@ struct PoaWarp {
                 t_col0 = cba << 4;
                 /* four lanes per tile row, one 16-byte granule each: consecutive lanes write consecutive 16-byte
                  * granules of the tile (no shared-memory bank conflict) and read one 64-byte piece of an H row */
-                for (uint32_t e = lane; e < 4 * t_rows; e += G) {
+                const uint32_t n_gran = 4 * t_rows;
+                auto fetch = [&](uint32_t e) -> U4 {
                     const uint32_t q = e >> 2, gq = e & 3u;
                     const uint32_t rk = t_top - q;
                     U4 v;
@@ -1333,16 +1335,26 @@ struct PoaWarp {
                                 t8[k] = static_cast<int16_t>(static_cast<int32_t>(col) * g);
                             }
                             v = U4{pack16(t8[0], t8[1]), pack16(t8[2], t8[3]), pack16(t8[4], t8[5]), pack16(t8[6], t8[7])};
-                        } else if (blk - sr >= NB) {
-                            v = f4;
                         } else {
+                            /* the granule's address does not depend on the row's band start: both loads go out together */
                             v = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * kBW + ((blk & (NB - 1)) << 4))[gq & 1u];
+                            if (blk - sr >= NB) v = f4;
                         }
                         if (gq == 0) tbs[q] = static_cast<uint8_t>(sr);
                     } else {
                         v = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0)[gq];
                     }
-                    reinterpret_cast<U4*>(tile)[e] = v;
+                    return v;
+                };
+                /* four granules per lane in flight (one HBM round trip per batch, not per granule) */
+                for (uint32_t e0 = lane; e0 < n_gran; e0 += 4 * G) {
+                    U4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (e0 + u * G < n_gran) v[u] = fetch(e0 + u * G);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (e0 + u * G < n_gran) reinterpret_cast<U4*>(tile)[e0 + u * G] = v[u];
                 }
                 for (uint32_t q = lane; q < t_rows; q += G) trec[q] = rec[t_top - q];
                 have_tile = true;

@@ -105,9 +105,9 @@ template <int KB>
 PoaKernel pick_kernel_narrow(int blocks_per_sm) {   // 32 lanes, narrow banded rows: few registers per row
     switch (blocks_per_sm) {
         case 4: return rp_poa_kernel<32, KB, 4>;
-        case 5: return rp_poa_kernel<32, KB, 5>;
+        case 6: return rp_poa_kernel<32, KB, 6>;
         case 8: return rp_poa_kernel<32, KB, 8>;
-        default: return rp_poa_kernel<32, KB, 6>;
+        default: return rp_poa_kernel<32, KB, 5>;
     }
 }
 PoaKernel pick_kernel(int group, int band_k, int blocks_per_sm) {
@@ -321,12 +321,12 @@ static rp_status configure(rp_poa* p, uint32_t wl) {
     int band_k = (banded && group == 32) ? 4 : 16;
     if (const char* e_k = getenv("RP_POA_BAND_K")) band_k = atoi(e_k);
     if (group != 32 || (band_k != 4 && band_k != 8)) band_k = 16;
-    int bps = band_k == 16 ? 4 : 6;
+    int bps = band_k == 16 ? 4 : 5;
     if (const char* e_bps = getenv("RP_BLOCKS_PER_SM")) bps = atoi(e_bps);
     if (band_k == 16) {
         if (bps != 2 && bps != 3 && bps != 6) bps = 4;
-    } else if (bps != 4 && bps != 5 && bps != 8) {
-        bps = 6;
+    } else if (bps != 4 && bps != 6 && bps != 8) {
+        bps = 5;
     }
     p->group = group;
     p->band_k = band_k;

@@ -9,6 +9,24 @@ import sys
 import tempfile
 
 rep, lib = sys.argv[1], sys.argv[2]
+
+def pick_function(rep, funcs_dis, ninst):
+    """The captured kernel's SASS among the library's template instantiations: by its template arguments (raw page
+    'Kernel Name' = rp_poa_kernel<G, KB, BPS>), else the function whose length is closest."""
+    try:
+        raw = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE,
+                                             text=True).stdout.splitlines()))
+        name = raw[2][raw[0].index("Kernel Name")]
+        m = re.search(r"(\w+)<([\d, ]+)>", name)
+        if m:
+            pat = m.group(1) + "I" + "".join("Li%sE" % a.strip() for a in m.group(2).split(",")) + "E"
+            for k, v in funcs_dis.items():
+                if pat in k:
+                    return v
+    except Exception:
+        pass
+    return min(funcs_dis.values(), key=lambda v: abs(len(v) - ninst))
+
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin") and "host_mirror" not in f][0]
@@ -32,7 +50,7 @@ ia, ii, isamp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.in
 data = rows[2:]
 base = int(data[0][ia], 16)
 ninst = sum(1 for r in data if r[ia].startswith("0x"))
-lines = min(funcs_dis.values(), key=lambda v: abs(len(v) - ninst))
+lines = pick_function(rep, funcs_dis, ninst)
 byoff = {int(r[ia], 16) - base: (int(r[ii] or 0), int(r[isamp] or 0), r[1]) for r in data if r[ia].startswith("0x")}
 # function ranges in poa_core.cuh
 srcpath = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "racon_b200", "csrc", "poa_core.cuh")

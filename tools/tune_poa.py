@@ -15,11 +15,12 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--configs", default="0,32,4;0,16,4;0,8,4;1,16,4;1,8,4;1,8,3;1,8,2;0,8,3;0,16,3;1,16,3")
     ap.add_argument("--two-streams", action="store_true", help="also time launches alternating between two objects")
+    ap.add_argument("--wlen", type=int, default=500, help="window length of the synthetic windows")
     ap.add_argument("--replicate", type=int, default=1, help="every window this many times in a row (lock-step experiment)")
     args = ap.parse_args()
     import torch
     from racon_b200 import api, windows
-    ws, _ = windows.synth_windows(args.windows // args.replicate, err=0.12)
+    ws, _ = windows.synth_windows(args.windows // args.replicate, truth_len=args.wlen, err=0.12)
     import numpy as np
     if args.replicate > 1:
         ws = ws.subset(np.repeat(np.arange(ws.n_windows), args.replicate))
@@ -33,7 +34,7 @@ def main():
         os.environ["RP_BLOCKS_PER_SM"] = str(bps)
         os.environ["RP_POA_BAND_K"] = str(k)
         try:
-            b = api.PoaBatch(device=0, window_length=500, banded=bool(banded), mem_bytes=int(60e9))
+            b = api.PoaBatch(device=0, window_length=args.wlen, banded=bool(banded), mem_bytes=int(60e9))
             st = torch.cuda.current_stream()
             b.set_stream(st.cuda_stream)
             assert b.add_window_set(ws) == ws.n_windows
@@ -50,11 +51,11 @@ def main():
             torch.cuda.synchronize()
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.reps + 1)]
             ev[0].record(st)
-            for k in range(args.reps):
+            for kk in range(args.reps):
                 b.launch()
-                ev[k + 1].record(st)
+                ev[kk + 1].record(st)
             torch.cuda.synchronize()
-            ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.reps)]
+            ms = [ev[kk].elapsed_time(ev[kk + 1]) for kk in range(args.reps)]
             info = b.info()
             res = {"banded": banded, "lanes": g, "blocks_per_sm": bps, "band_cols_per_lane": k, "ms": [round(x, 2) for x in ms],
                    "windows_per_s": round(ws.n_windows / (min(ms) * 1e-3)), "workers": info["workers"],
@@ -62,7 +63,7 @@ def main():
                    "bad_status": int((status != 0).sum()), "fnv200": ck, "same_as_first": full == ref,
                    "band": bi}
             if args.two_streams:
-                b2 = api.PoaBatch(device=0, window_length=500, banded=bool(banded), mem_bytes=int(60e9))
+                b2 = api.PoaBatch(device=0, window_length=args.wlen, banded=bool(banded), mem_bytes=int(60e9))
                 s2 = torch.cuda.Stream()
                 b2.set_stream(s2.cuda_stream)
                 assert b2.add_window_set(ws) == ws.n_windows
@@ -73,8 +74,8 @@ def main():
                 e0.record(st)
                 s2.wait_event(e0)
                 K = 6
-                for k in range(K):
-                    (b if k % 2 == 0 else b2).launch()
+                for kk in range(K):
+                    (b if kk % 2 == 0 else b2).launch()
                 eb.record(s2)
                 st.wait_event(eb)
                 e1.record(st)
