@@ -80,7 +80,7 @@ def load(build_if_missing=True):
         for name in ("rp_mirror_align", "rp_mirror_consensus", "rp_mirror_polisher_open", "rp_mirror_polisher_open_with_bp",
                      "rp_mirror_polisher_counts", "rp_mirror_polisher_export", "rp_mirror_polisher_polish",
                      "rp_mirror_polisher_window_consensus", "rp_mirror_polisher_polished", "rp_mirror_polisher_close",
-                     "rp_mirror_polisher_failed", "rp_mirror_format_fasta"):
+                     "rp_mirror_polisher_failed", "rp_mirror_format_fasta", "rp_mirror_polisher_stream_fasta"):
             if hasattr(host, name):
                 setattr(lib, name, getattr(host, name))
     if hasattr(lib, "rp_mirror_align"):
@@ -455,6 +455,23 @@ class MirrorPolisher:
             k = self.lib.rp_mirror_polisher_polished(self.h, i, C.byref(tid), tags, len(tags), data, len(data))
             out.append((tid.value, tags.value.decode(), data.raw[:k]))
         return cons, out
+
+    def stream_fasta(self, path, names, drop_unpolished=False, mem_bytes=0, banded=False):
+        """Polisher::polish_streaming into a FASTA file: two batch objects in flight, every polished sequence written the
+        moment its last window is collected (polisher.cpp:504-537 + main.cpp:159-161).  names: target names by id."""
+        f = self.lib.rp_mirror_polisher_stream_fasta
+        f.restype = C.c_uint32
+        f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_uint64, C.c_int]
+        blob = b"".join(n.encode() + b"\0" for n in names) + b"\0"
+        return f(self.h, 1 if drop_unpolished else 0, path.encode(), blob, mem_bytes, 1 if banded else 0)
+
+    def failed(self):
+        """(overlaps, windows) the device could not finish (see host_mirror.hpp: Polisher::failed_overlaps/windows)."""
+        a = (C.c_uint64 * 2)()
+        self.lib.rp_mirror_polisher_failed.restype = None
+        self.lib.rp_mirror_polisher_failed.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.rp_mirror_polisher_failed(self.h, a)
+        return int(a[0]), int(a[1])
 
     def close(self):
         if self.h:

@@ -98,11 +98,22 @@ bool BatchProcessor::addWindow(std::shared_ptr<Window> window) {
 bool BatchProcessor::hasWindows() const { return rp_poa_size(poa_) > 0; }
 
 const std::vector<bool>& BatchProcessor::generateConsensus() {
-    rp_status s = rp_poa_run(poa_);
-    if (s == RP_OK) s = rp_poa_sync(poa_);
+    launch();
+    return collect();
+}
+
+void BatchProcessor::launch() {
+    const rp_status s = rp_poa_run(poa_);
     if (s != RP_OK) {
-        fprintf(stderr, "[racon_b200::BatchProcessor::generateConsensus] error: %s (%s)\n", rp_strerror(s),
-                rp_last_error());
+        fprintf(stderr, "[racon_b200::BatchProcessor::launch] error: %s (%s)\n", rp_strerror(s), rp_last_error());
+        exit(1);
+    }
+}
+
+const std::vector<bool>& BatchProcessor::collect() {
+    const rp_status s = rp_poa_sync(poa_);
+    if (s != RP_OK) {
+        fprintf(stderr, "[racon_b200::BatchProcessor::collect] error: %s (%s)\n", rp_strerror(s), rp_last_error());
         exit(1);
     }
     window_consensus_status_.clear();
@@ -409,6 +420,64 @@ void Polisher::polish(std::vector<PolishedSequence>& dst, bool drop_unpolished_s
     }
 }
 
+void Polisher::polish_streaming(const std::function<void(const PolishedSequence&)>& sink,
+                                bool drop_unpolished_sequences, size_t memory, bool banded) {
+    constexpr int kObjects = 2;
+    struct InFlight {
+        std::unique_ptr<BatchProcessor> batch;
+        size_t first = 0, count = 0;
+        bool busy = false;
+    };
+    InFlight obj[kObjects];
+    for (auto& o : obj) o.batch = createBatch(0, device_, memory, gap_, mismatch_, match_, banded, window_length_, trim_);
+    std::string polished_data;
+    uint32_t num_polished_windows = 0;
+    auto stitch = [&](size_t w, bool polished) {  // polisher.cpp:504-530, one window at a time, in window order
+        num_polished_windows += polished ? 1 : 0;
+        polished_data += windows_[w]->consensus();
+        if (w == windows_.size() - 1 || windows_[w + 1]->rank() == 0) {
+            const double polished_ratio = num_polished_windows / static_cast<double>(windows_[w]->rank() + 1);
+            if (!drop_unpolished_sequences || polished_ratio > 0) {
+                std::string tags = fragment_correction_ ? "r" : "";
+                tags += " LN:i:" + std::to_string(polished_data.size());
+                tags += " RC:i:" + std::to_string(targets_coverages_[windows_[w]->id()]);
+                tags += " XC:f:" + std::to_string(polished_ratio);
+                sink(PolishedSequence{windows_[w]->id(), tags, polished_data});
+            }
+            num_polished_windows = 0;
+            polished_data.clear();
+        }
+        windows_[w].reset();  // polisher.cpp:531: the window is not needed any more
+    };
+    size_t next = 0;
+    int fill = 0, drain = 0;  // objects are filled and drained in the same round-robin order => window order
+    while (next < windows_.size() || obj[drain].busy) {
+        InFlight& f = obj[fill];
+        if (!f.busy && next < windows_.size()) {
+            f.batch->reset();
+            f.first = next;
+            while (next < windows_.size() && f.batch->addWindow(windows_[next])) ++next;
+            f.count = next - f.first;
+            if (f.count == 0) {
+                fprintf(stderr, "[racon_b200::Polisher::polish_streaming] error: window does not fit an empty batch\n");
+                exit(1);
+            }
+            f.batch->launch();  // asynchronous: the host goes on filling the other object / stitching
+            f.busy = true;
+            fill = (fill + 1) % kObjects;
+            if (!obj[fill].busy && next < windows_.size()) continue;  // keep both in flight before draining
+        }
+        InFlight& d = obj[drain];
+        if (d.busy) {
+            const std::vector<bool>& flags = d.batch->collect();
+            for (uint32_t k : d.batch->failedWindows()) failed_windows_.push_back(d.first + k);
+            for (size_t k = 0; k < d.count; ++k) stitch(d.first + k, flags[k]);
+            d.busy = false;
+            drain = (drain + 1) % kObjects;
+        }
+    }
+}
+
 }  // namespace racon_b200
 
 /* Test hooks with the shape of oracle/ref_polisher_harness.cpp (open -> counts -> export -> polish -> polished), so
@@ -545,6 +614,27 @@ extern "C" uint64_t rp_mirror_polisher_polished(void* hv, uint32_t i, uint64_t* 
     if (s.data.size() > data_cap) return ~0ull;
     std::memcpy(data, s.data.data(), s.data.size());
     return s.data.size();
+}
+
+/* Streaming polish straight into a FASTA file (names: NUL-separated target names, one per target id); returns the
+ * number of records written.  mem_bytes: budget per batch object (small budgets force many batches). */
+extern "C" uint32_t rp_mirror_polisher_stream_fasta(void* hv, int drop_unpolished, const char* path, const char* names,
+                                                     uint64_t mem_bytes, int banded) {
+    PolHandle* h = static_cast<PolHandle*>(hv);
+    std::vector<std::string> name_of;
+    for (const char* p = names; p && *p; p += std::strlen(p) + 1) name_of.emplace_back(p);
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return 0;
+    uint32_t n = 0;
+    h->polisher->polish_streaming(
+        [&](const racon_b200::PolishedSequence& s) {
+            const std::string rec = racon_b200::format_fasta(s.id < name_of.size() ? name_of[s.id] : "?", s);
+            std::fwrite(rec.data(), 1, rec.size(), f);
+            ++n;
+        },
+        drop_unpolished != 0, static_cast<size_t>(mem_bytes), banded != 0);
+    std::fclose(f);
+    return n;
 }
 
 extern "C" void rp_mirror_polisher_close(void* hv) { delete static_cast<PolHandle*>(hv); }

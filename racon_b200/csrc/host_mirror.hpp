@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <functional>
 #include <memory>
 #include <string>
 #include <utility>
@@ -75,6 +76,10 @@ public:
     bool hasWindows() const;
     /* writes window->consensus_ for every accepted window; flag = what Window::generate_consensus returns */
     const std::vector<bool>& generateConsensus();
+    /* the two halves of generateConsensus (generatePOA / getConsensus of the reference, cudabatch.cpp:193-270):
+     * launch() queues H2D + kernel + D2H on the object's stream and returns, collect() waits and reads back */
+    void launch();
+    const std::vector<bool>& collect();
     void reset();
     uint32_t getBatchID() const { return bid_; }
     /* indices (within the batch) of the windows of the last generateConsensus() that hit a device limit (soft RP_WIN_*
@@ -176,6 +181,12 @@ public:
     /* the window-building half of initialize() alone, for overlaps whose breaking points are already known */
     void build_windows(const std::vector<Overlap>& overlaps);
     void polish(std::vector<PolishedSequence>& dst, bool drop_unpolished_sequences);
+    /* Streaming form (polisher.cpp:504-537 + main.cpp:159-161 as a consumer overlapped with the compute): two batch
+     * objects stay in flight; while one runs on the GPU the other's finished windows are stitched in window order, and
+     * `sink` gets every polished sequence the moment its last window is collected (e.g. a FASTA writer).  `memory` =
+     * device budget per batch object (0 = library default), `banded` = racon -b. */
+    void polish_streaming(const std::function<void(const PolishedSequence&)>& sink, bool drop_unpolished_sequences,
+                          size_t memory = 0, bool banded = false);
     const std::vector<std::shared_ptr<Window>>& windows() const { return windows_; }
     /* Items the device could not finish (soft RP_ALN_* / RP_WIN_* status).  The reference hands such items to its CPU
      * code (cudapolisher.cpp:213 edlib, :354-370 spoa); this library has no CPU path, so a failed overlap contributes

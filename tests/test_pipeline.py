@@ -75,3 +75,46 @@ def test_pipeline_lambda_fragment_correction_matches_reference():
     assert hashlib.md5(b"".join(p[2] for p in polished)).hexdigest() == lam.z["polished_md5"].tobytes().decode()
     tags = lam.z["polished_tags"].tobytes().decode().split("\n")
     assert ["r" + t for t in tags] == [p[1] for p in polished] or tags == [p[1][1:] for p in polished]
+
+
+def test_pipeline_streaming_stitch_writes_the_golden_fasta(tmp_path):
+    """the stitch + FASTA writer as a streaming consumer — two batch objects in flight (a 96 MB budget each
+    forces several batches over the 96 windows), every sequence written the moment its last window is collected; the file
+    is byte-identical to racon's stdout on the sample (md5 b0e2a278...), with and without -b."""
+    from racon_b200 import api
+    lam = LambdaOverlaps()
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lambda_windows.npz"))
+    name = ref["polished_name"].tobytes().decode().split(" ")[0]
+    for banded in (False, True):
+        pol = api.MirrorPolisher(lam.bases, lam.quals, lam.seq_off, lam.seq_has_qual, n_targets=1, overlaps=lam.ov,
+                                 window_length=lam.window_length, quality_threshold=lam.quality_threshold, trim=True,
+                                 match=3, mismatch=-5, gap=-4, window_type_tgs=bool(ref["win_type"][0]))
+        out = str(tmp_path / ("polished_%d.fasta" % banded))
+        n = pol.stream_fasta(out, [name], drop_unpolished=True, mem_bytes=96 << 20, banded=banded)
+        assert pol.failed() == (0, 0)
+        pol.close()
+        assert n == 1
+        assert hashlib.md5(open(out, "rb").read()).hexdigest() == "b0e2a2788440a4982e544e2e9b3bf378"
+
+
+def test_pipeline_streaming_stitch_many_batches_fragment_correction(tmp_path):
+    """Same consumer on the -f flow with a 40 MB budget per batch object: the 3461 windows need a dozen batches, which
+    alternate between the two objects; the 236 corrected reads come out in target order with the reference's bytes."""
+    from racon_b200 import api
+    lam = LambdaOverlaps("lambda_frag_overlaps.npz")
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lambda_frag_windows.npz"))
+    m, x, g = (int(v) for v in lam.z["scores"])
+    n_seq = len(lam.seq_off) - 1
+    pol = api.MirrorPolisher(lam.bases, lam.quals, lam.seq_off, lam.seq_has_qual, n_targets=n_seq, overlaps=lam.ov,
+                             window_length=lam.window_length, quality_threshold=lam.quality_threshold, trim=True,
+                             match=m, mismatch=x, gap=g, window_type_tgs=bool(ref["win_type"][0]),
+                             fragment_correction=True)
+    out = str(tmp_path / "corrected.fasta")
+    n = pol.stream_fasta(out, ["read%d" % i for i in range(n_seq)], drop_unpolished=False, mem_bytes=40 << 20)
+    assert pol.failed() == (0, 0)
+    pol.close()
+    assert n == 236
+    lines = open(out, "rb").read().split(b"\n")
+    data = b"".join(lines[1::2])
+    assert len(data) == 1658216
+    assert hashlib.md5(data).hexdigest() == lam.z["polished_md5"].tobytes().decode()
