@@ -43,6 +43,10 @@ CUDABatchAligner::~CUDABatchAligner() {
 }
 
 bool CUDABatchAligner::addOverlap(Overlap* overlap, std::vector<std::unique_ptr<Sequence>>& sequences) {
+    /* an overlap that came with its alignment (SAM input) keeps it, as on the CPU path (Overlap::find_breaking_points,
+     * overlap.cpp:179-203 aligns only when cigar_ is empty); the reference's CUDA shim re-aligns it, which is one of the
+     * reasons its results differ from the CPU build's */
+    if (!overlap->cigar_.empty()) return true;
     /* same spans as Overlap::find_breaking_points (overlap.cpp:193-197) and the reference shim (cudaaligner.cpp:53-57) */
     const char* q = !overlap->strand_ ? &(sequences[overlap->q_id_]->data()[overlap->q_begin_])
                                       : &(sequences[overlap->q_id_]->reverse_complement()[overlap->q_length_ - overlap->q_end_]);

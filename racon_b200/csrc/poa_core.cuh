@@ -1318,8 +1318,7 @@ struct PoaWarp {
                 t_col0 = cba << 4;
                 /* four lanes per tile row, one 16-byte granule each: consecutive lanes write consecutive 16-byte
                  * granules of the tile (no shared-memory bank conflict) and read one 64-byte piece of an H row */
-                const uint32_t n_gran = 4 * t_rows;
-                auto fetch = [&](uint32_t e) -> U4 {
+                for (uint32_t e = lane; e < 4 * t_rows; e += G) {
                     const uint32_t q = e >> 2, gq = e & 3u;
                     const uint32_t rk = t_top - q;
                     U4 v;
@@ -1344,17 +1343,7 @@ struct PoaWarp {
                     } else {
                         v = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0)[gq];
                     }
-                    return v;
-                };
-                /* four granules per lane in flight (one HBM round trip per batch, not per granule) */
-                for (uint32_t e0 = lane; e0 < n_gran; e0 += 4 * G) {
-                    U4 v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (e0 + u * G < n_gran) v[u] = fetch(e0 + u * G);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (e0 + u * G < n_gran) reinterpret_cast<U4*>(tile)[e0 + u * G] = v[u];
+                    reinterpret_cast<U4*>(tile)[e] = v;
                 }
                 for (uint32_t q = lane; q < t_rows; q += G) trec[q] = rec[t_top - q];
                 have_tile = true;

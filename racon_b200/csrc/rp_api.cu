@@ -196,7 +196,9 @@ struct rp_poa {
     uint64_t launches = 0, last_h2d = 0, last_d2h = 0;
     int banded = 0;
     uint32_t configured_wl = 0;    // window length the scratch is sized for (0 = not yet: sized at the first upload)
-    uint64_t h_band[4] = {0, 0, 0, 0};   // alignments tried in the band / redone with the full matrix (last launch)
+    uint64_t h_band[4] = {0, 0, 0, 0};
+    uint64_t band_total[3] = {0, 0, 0};   // sums of h_band over the object's life (RP_BAND_AUDIT report)
+    bool band_counted = true;   // alignments tried in the band / redone with the full matrix (last launch)
     /* escalation pass for windows that exceeded a device limit (never a CPU re-run) */
     DevBuf d_scratch_big, d_queue_big;
     rp::PoaLimits lim_big;
@@ -314,11 +316,12 @@ static rp_status configure(rp_poa* p, uint32_t wl) {
 
     /* launch shape: persistent blocks of 4 warps = 128/G lane groups, kBlocksPerSm blocks per SM.  Defaults measured on
      * B200 (profiles/README.md, round 2): full matrix: 32 lanes per window, 16 columns per lane, 4 blocks/SM; banded
-     * (-b): 32 lanes x 4 columns = a 128-column band — two packed registers per row instead of eight. */
+     * (-b): 32 lanes x 8 columns = a 256-column band (the width of cudapoa's static band) — four packed registers per
+     * row instead of eight.  RP_POA_BAND_K=4 selects a 128-column band (faster on clean data, refuses more often). */
     int group = 32;
     if (const char* e_g = getenv("RP_POA_GROUP")) group = atoi(e_g);
     if (group != 8 && group != 16 && group != 32) group = 32;
-    int band_k = (banded && group == 32) ? 4 : 16;
+    int band_k = (banded && group == 32) ? 8 : 16;
     if (const char* e_k = getenv("RP_POA_BAND_K")) band_k = atoi(e_k);
     if (group != 32 || (band_k != 4 && band_k != 8)) band_k = 16;
     int bps = band_k == 16 ? 4 : 5;
@@ -397,6 +400,11 @@ void rp_poa_destroy(rp_poa* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->banded && getenv("RP_BAND_AUDIT"))   // test mode: what the band did over this object's life
+        fprintf(stderr, "[racon_b200] band %u columns: %llu alignments tried, %llu redone with the full matrix, %llu accepted "
+                        "band alignments differ from the full-matrix alignment (audit)\n",
+                static_cast<unsigned>(p->group * p->band_k), static_cast<unsigned long long>(p->band_total[0]),
+                static_cast<unsigned long long>(p->band_total[1]), static_cast<unsigned long long>(p->band_total[2]));
     DevBuf* bufs[] = {&p->d_bases, &p->d_weights, &p->d_seq_flags, &p->d_win_flags, &p->d_seq_off, &p->d_seq_begin,
                       &p->d_seq_end, &p->d_win_first, &p->d_out_off, &p->d_out_cap, &p->d_queue, &p->d_win_alpha,
                       &p->d_cons, &p->d_cov, &p->d_len, &p->d_status, &p->d_head, &p->d_stats, &p->d_scratch,
@@ -612,8 +620,11 @@ rp_status rp_poa_download(rp_poa* p) {
     if (p->counters)
         RP_CUDA(cudaMemcpyAsync(p->h_stats, p->d_stats.p, 64, cudaMemcpyDeviceToHost, p->stream));
     if (p->banded && n > 0)
+    {
         RP_CUDA(cudaMemcpyAsync(p->h_band, static_cast<uint8_t*>(p->d_stats.p) + 128, 32, cudaMemcpyDeviceToHost,
                                 p->stream));
+        p->band_counted = false;
+    }
     p->last_d2h = d2h;
     p->downloaded = true;
     p->synced = false;
@@ -687,6 +698,10 @@ rp_status rp_poa_sync(rp_poa* p) {
         rp_status s = escalate(p);
         if (s != RP_OK) return s;
         p->synced = true;
+        if (p->banded && !p->band_counted) {
+            for (int k = 0; k < 3; ++k) p->band_total[k] += p->h_band[k];
+            p->band_counted = true;
+        }
     }
     return RP_OK;
 }

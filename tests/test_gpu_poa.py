@@ -73,7 +73,7 @@ def test_gpu_every_group_width(lanes, banded, monkeypatch):
     _compare(_mk("partial", seed=33), banded=banded, band_stats=stats)
     _compare(_mk("fullspan", seed=34), banded=banded, band_stats=stats)
     if banded:
-        assert stats["band_alignments"] > 0 and stats["band_width"] == (128 if lanes == 32 else 16 * lanes)
+        assert stats["band_alignments"] > 0 and stats["band_width"] == (256 if lanes == 32 else 16 * lanes)
 
 
 def test_gpu_band_refusals_are_redone_with_the_full_matrix(monkeypatch):
@@ -95,7 +95,7 @@ def test_gpu_band_refusals_are_redone_with_the_full_matrix(monkeypatch):
             win.append((r, None, 0, len(bb) - 1))
         wins.append(win)
     ws = windows.from_lists(wins)
-    monkeypatch.setenv("RP_POA_GROUP", "8")
+    monkeypatch.setenv("RP_POA_BAND_K", "4")     # 128-column band
     stats = {}
     _compare(ws, banded=True, band_stats=stats)
     assert 0 < stats["band_redone_full"] < stats["band_alignments"]
