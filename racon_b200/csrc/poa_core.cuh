@@ -30,6 +30,9 @@
  */
 #pragma once
 #include "rp_warp.cuh"
+#if defined(RP_HOST_SIM)
+#include <vector>
+#endif
 
 namespace rp {
 
@@ -185,6 +188,13 @@ struct alignas(16) U4 {
 struct alignas(8) U2 {
     uint32_t x, y;
 };
+#if defined(RP_HOST_SIM)
+/* simulation only (debug_flags bit 3): copies for the band audit's diagnosis of a differing alignment */
+struct AuditStep { uint32_t i, j, move, p; int32_t h; };
+static std::vector<AuditStep> g_audit_path[2];
+static std::vector<int16_t> g_audit_h;
+static std::vector<uint8_t> g_audit_bs;
+#endif
 
 /* A lane's 16 columns = two 16-byte granules 2*lane, 2*lane+1 of the row (chunk or band) it belongs to */
 RP_DEV Row8 load_row_smem(const int16_t* row, int lane) {
@@ -1214,8 +1224,10 @@ struct PoaWarp {
      *
      * BAND: the matrix is the banded one (dp_band).  The result is accepted — the function returns true — only if
      * every cell of the path (i) keeps `band_margin` columns away from every band edge that really cuts the matrix
-     * (an edge at column 0 or at the last column cuts nothing) and (ii) holds a value a real alignment can have
-     * (>= worst: anything derived from an excluded cell is below that, see poa_window).  Otherwise false is
+     * (an edge at column 0 or at the last column cuts nothing; the cells of the predecessor rows the walk compares with
+     * must keep the same distance inside THEIR bands), (ii) holds a value a real alignment can have (>= worst: anything
+     * derived from an excluded cell is below that, see poa_window), and (iii) the path is not a long stretch of
+     * mismatches and gaps (the true path then probably lies outside the band: kBandJunkLimit).  Otherwise false is
      * returned and the caller repeats the alignment with the full matrix.  Why an accepted result equals the
      * full-matrix result: banded values never exceed the full ones and are equal wherever an optimal path lies
      * inside the band, so every equality test of the walk has the same outcome as in the full matrix as long as
@@ -1282,6 +1294,7 @@ struct PoaWarp {
     }
 
     static constexpr uint32_t kTileCols = 32;
+    static constexpr uint32_t kBandJunkLimit = 48;   // see traceback<true>, check (iii)
     static constexpr uint32_t kTileRowBytes = kTileCols * 2 + 16 + 1;   // H cells | record | band start
 
     template <bool BAND>
@@ -1302,8 +1315,12 @@ struct PoaWarp {
         const U4 f4 = U4{pack16(kBandFloor, kBandFloor), pack16(kBandFloor, kBandFloor), pack16(kBandFloor, kBandFloor),
                          pack16(kBandFloor, kBandFloor)};
         uint32_t i = best_row, j = len;
+#if defined(RP_HOST_SIM)
+        if (lane == 0) g_audit_path[BAND ? 1 : 0].clear();
+#endif
         uint32_t t_top = 0, t_rows = 0, t_col0 = 0;  // tile covers ranks (t_top - t_rows, t_top], cols [t_col0, t_col0+32)
         bool have_tile = false, bad = false;
+        uint32_t quality = 0;
         while (i != 0) {
             bool need = !have_tile || i + t_rows <= t_top || (j > 0 && j - 1 < t_col0);
             /* when a group that runs in lock step with this one refills, refill too: the groups of a warp then
@@ -1419,6 +1436,21 @@ struct PoaWarp {
                 move = traceback_step_wide<BAND>(H, bs, rec, pred_ovf, ki, lane, g, i, j, npe, hij, mc, lpa, &found_p);
             }
             if (!move) move = 3;
+            if (BAND) {
+                /* (iii) the path must look like a real alignment: a long stretch that is mostly mismatches and gaps
+                 * means the read's true path probably runs somewhere else — outside the band, where this matrix cannot
+                 * see it.  Leaky counter: +2 per mismatch / gap step, -1 per match; a good alignment keeps it near
+                 * zero (12 % errors: -0.6 per step), aligned junk drives it up by about +0.5 per step. */
+                const bool is_match = move == 1 && mc == m && m != x;
+                quality = is_match ? (quality ? quality - 1 : 0u) : quality + 2u;
+                if (quality > kBandJunkLimit) {
+                    bad = true;
+                    break;
+                }
+            }
+#if defined(RP_HOST_SIM)
+            if ((P->debug_flags & 8u) && lane == 0) g_audit_path[BAND ? 1 : 0].push_back({i, j, static_cast<uint32_t>(move), found_p, hij});
+#endif
             if (move == 1) {
                 if (lane == 0) aln[j - 1] = static_cast<uint16_t>(i);   // rank for now, node below
                 i = found_p;
@@ -2032,6 +2064,13 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
             for (uint32_t c = lane; c < len; c += G) W.cur[c] = W.aln[c];
             W.syncwarp();
             done = false;
+#if defined(RP_HOST_SIM)
+            if ((P.debug_flags & 8u) && lane == 0) {
+                g_audit_h.assign(W.H, W.H + static_cast<size_t>(nrows + 1) * kBW);
+                g_audit_bs.assign(W.bs, W.bs + nrows + 1);
+            }
+            W.syncwarp();
+#endif
         }
         if (!done) {
             if (static_cast<uint64_t>(nrows + 1) * lpa > P.lim.hcap) {
@@ -2056,6 +2095,57 @@ RP_DEV void poa_window(const PoaParams& P, uint32_t w, uint8_t* slot, uint8_t* s
                     atomicAdd(P.band_stats + 2, 1ull);
 #else
                     P.band_stats[2] += 1;
+                    if (P.debug_flags & 8u) {
+                        auto hbv = [&](uint32_t r, uint32_t c) -> int32_t {
+                            if (r == 0) return static_cast<int32_t>(c) * P.gap;
+                            const uint32_t cbk = c >> 4;
+                            if (cbk - g_audit_bs[r] >= NB) return -99999;
+                            return g_audit_h[static_cast<size_t>(r) * kBW + ((cbk & (NB - 1)) << 4) + (PW::perm_band(c) & 15u)];
+                        };
+                        const auto& pb = g_audit_path[1];
+                        const auto& pf = g_audit_path[0];
+                        fprintf(stderr, "[band audit] window %u layer %u: len %u rows %u sub %d, full best %d; band path %zu steps, full path %zu steps\n",
+                                w, s - s0, len, nrows, sub ? 1 : 0, best, pb.size(), pf.size());
+                        size_t k = 0;
+                        while (k < pb.size() && k < pf.size() && pb[k].i == pf[k].i && pb[k].j == pf[k].j && pb[k].move == pf[k].move && pb[k].p == pf[k].p) ++k;
+                        if (k < pb.size() && k < pf.size()) {
+                            fprintf(stderr, "    DIVERGE at step %zu: cell (rank %u, col %u) h band %d full %d; band move %u -> %u, full move %u -> %u; band cols [%u,%u)\n",
+                                    k, pb[k].i, pb[k].j, pb[k].h, pf[k].h, pb[k].move, pb[k].p, pf[k].move, pf[k].p,
+                                    16u * g_audit_bs[pb[k].i], 16u * (g_audit_bs[pb[k].i] + NB));
+                            const uint32_t i0 = pf[k].i, j0 = pf[k].j;
+                            const Rec rc = W.rec[i0];
+                            const uint32_t np = (static_cast<uint32_t>(rc.a) >> 8) & 0x7f;
+                            for (uint32_t q = 0; q < np; ++q) {
+                                const uint32_t pp = q < 7 ? rec_pred(rc, q) : W.pred_ovf[i0 * W.ki + q];
+                                fprintf(stderr, "      pred %u rank %u band cols [%u,%u): band (j-1) %d (j) %d | full (j-1) %d (j) %d\n", q, pp,
+                                        16u * g_audit_bs[pp], 16u * (g_audit_bs[pp] + NB), hbv(pp, j0 ? j0 - 1 : 0), hbv(pp, j0),
+                                        static_cast<int>(W.H[static_cast<uint64_t>(pp) * lpa + perm(j0 ? j0 - 1 : 0)]),
+                                        static_cast<int>(W.H[static_cast<uint64_t>(pp) * lpa + perm(j0)]));
+                            }
+                        }
+                        /* where along the FULL path is the band value lower (or the cell outside the band)? */
+                        int shown = 0, n_out = 0, far = 0;
+                        uint32_t first_out_j = 0, last_out_j = 0;
+                        for (const auto& st : pf) {
+                            const int32_t lo_c = 16 * g_audit_bs[st.i], hi_c = 16 * (g_audit_bs[st.i] + NB);
+                            const int32_t jj = st.j;
+                            if (jj < lo_c || jj >= hi_c) {
+                                ++n_out;
+                                const int d = jj < lo_c ? lo_c - jj : jj - hi_c + 1;
+                                if (d > far) far = d;
+                                if (!last_out_j) last_out_j = st.j;
+                                first_out_j = st.j;
+                            }
+                        }
+                        fprintf(stderr, "    full path: %d cells outside the band (columns %u..%u), farthest %d columns beyond the edge\n",
+                                n_out, first_out_j, last_out_j, far);
+                        for (const auto& st : pf) {
+                            const int32_t hb = hbv(st.i, st.j);
+                            if (hb != st.h && shown++ < 4)
+                                fprintf(stderr, "    full-path cell (rank %u, col %u): full %d band %d, band cols [%u,%u)\n", st.i, st.j, st.h, hb,
+                                        16u * g_audit_bs[st.i], 16u * (g_audit_bs[st.i] + NB));
+                        }
+                    }
 #endif
                 }
             }

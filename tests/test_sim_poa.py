@@ -274,3 +274,21 @@ def test_sim_narrow_band_refusal_and_other_scores():
     ws = util.make_set(101, 32, wlen=300, depth=40, err=0.3).subset([0, 12])
     stats = _check(ws, lanes=32, smem=9216, banded=1, band_cols_per_lane=4, debug_flags=2)
     assert stats[4] > 0 and stats[6] == 0
+
+
+def test_sim_band_real_windows_whose_true_path_leaves_the_band():
+    """Two windows of the lambda -f run (unit scores) found on the B200 by tools/find_band_divergence.py: a layer's true
+    alignment runs 70-130 columns away from the band's centre line while an in-band path of almost the same score keeps
+    every margin — the band result used to be accepted and the consensus differed from the reference's.  The acceptance
+    check's alignment-quality rule (kBandJunkLimit) now refuses those band results; the on-device full-matrix redo makes the
+    windows exact again."""
+    import os
+    from racon_b200 import windows
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lambda_frag_band_cases.npz"))
+    ws = windows.WindowSet(bases=z["bases"], quals=z["quals"] if z["quals"].size else None, seq_off=z["seq_off"],
+                           seq_has_qual=z["seq_has_qual"] if z["seq_has_qual"].size else None, seq_begin=z["seq_begin"],
+                           seq_end=z["seq_end"], win_first=z["win_first"], win_type=z["win_type"])
+    scores = tuple(int(v) for v in z["scores"])
+    for kb in (8, 4):
+        stats = _check(ws, scores=scores, lanes=32, smem=9216, banded=1, band_cols_per_lane=kb, debug_flags=2)
+        assert stats[5] > 0 and stats[6] == 0, stats
