@@ -352,6 +352,10 @@ def main():
 
     cfg = CONFIGS[args.config]
     banded = cfg["banded"] if args.banded < 0 else bool(args.banded)
+    if banded:
+        # the configuration is DEFINED as the banded run: ask for the band layout explicitly (a banded object would
+        # otherwise pick the full matrix for 500-base windows, where that is the faster kernel — see `band` below)
+        os.environ.setdefault("RP_POA_BAND_K", "8")
     wl = cfg["wl"]
     aligner = None
     meta = {}
@@ -440,6 +444,26 @@ def main():
     total_ms = ev0.elapsed_time(ev1)
     gpu_launches = batch.info()["launches"] + batch2.info()["launches"] - launches0
     batch2.close()
+    full_ms = None
+    if banded:   # what -b does by default at this window length: the full-matrix kernel (same results)
+        saved = os.environ.pop("RP_POA_BAND_K", None)
+        bf = api.PoaBatch(device=local, window_length=wl, banded=True, mem_bytes=mem)
+        bf.set_stream(stream.cuda_stream)
+        assert bf.add_window_set(ws) == n
+        bf.upload()
+        bf.launch()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        bf.launch()
+        bf.launch()
+        f1.record(stream)
+        barrier()
+        full_ms = f0.elapsed_time(f1) / 2
+        default_uses_band = bf.band_info()["band_layout_in_use"] if False else None
+        bf.close()
+        if saved is not None:
+            os.environ["RP_POA_BAND_K"] = saved
 
     # ---- end-to-end arm: C-ABI call with host buffers (H2D + kernel + D2H + fetch) ------------------
     # what racon's CUDAPolisher does with `-c K` batch objects (cudapolisher.cpp:254-276): each object, on its own
@@ -499,8 +523,8 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- max over ranks ---------------------------------------------------------------------------
-    tt = torch.tensor([total_ms, e2e_ms, float(band_info["band_alignments"]), float(band_info["band_redone_full"])],
-                      dtype=torch.float64, device="cuda")
+    tt = torch.tensor([total_ms, e2e_ms, float(band_info["band_alignments"]), float(band_info["band_redone_full"]),
+                       float(full_ms or 0.0)], dtype=torch.float64, device="cuda")
     if distributed:
         t2 = tt.clone()
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -508,7 +532,7 @@ def main():
         band_tot = (float(t2[2]), float(t2[3]))
     else:
         band_tot = (float(tt[2]), float(tt[3]))
-    total_ms, e2e_ms = float(tt[0]), float(tt[1])
+    total_ms, e2e_ms, full_ms = float(tt[0]), float(tt[1]), float(tt[4])
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -553,7 +577,11 @@ def main():
             line["band"] = {"width_columns": band_info["band_width"], "alignments_tried_in_band": int(band_tot[0]),
                             "redone_with_full_matrix_on_device": int(band_tot[1]),
                             "result_check": "consensus checksum of the first 200 windows == the reference's known "
-                                            "answer (full-matrix spoa)" if cfg["shape"] == "ont" else "see tests"}
+                                            "answer (full-matrix spoa)" if cfg["shape"] == "ont" else "see tests",
+                            "layout": "asked for explicitly (RP_POA_BAND_K=8); by default a banded object uses the band "
+                                      "for windows of >= 768 bases and the full matrix below that",
+                            "value_with_default_policy_isolated": n_total / (full_ms * 1e-3) if full_ms else None,
+                            "value_band_isolated": n_total / (kern_avg_ms * 1e-3)}
         if aligner:
             line["aligner"] = aligner
         if not args.no_cpu_baseline:

@@ -220,7 +220,7 @@ class PoaBatch:
         a = (C.c_uint64 * 8)()
         _check(self.lib, self.lib.rp_poa_band_info(self.h, a), "rp_poa_band_info")
         return {"banded": bool(a[0]), "band_alignments": int(a[1]), "band_redone_full": int(a[2]),
-                "band_width": int(a[3]), "band_audit_mismatches": int(a[4])}
+                "band_width": int(a[3]), "band_audit_mismatches": int(a[4]), "band_layout_in_use": bool(a[5])}
 
     def fetch_all(self, stride):
         n = self.size()
@@ -502,7 +502,7 @@ def consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=500, de
             out, lens, p, s = batch.fetch_all(stride)
             if band_stats is not None:
                 for k, v in batch.band_info().items():
-                    band_stats[k] = v if k in ("banded", "band_width") else band_stats.get(k, 0) + v
+                    band_stats[k] = v if k in ("banded", "band_width", "band_layout_in_use") else band_stats.get(k, 0) + v
                 band_stats["batches"] = band_stats.get("batches", 0) + 1
             for i in range(took):
                 cons.append(out[i, :lens[i]].tobytes())

@@ -69,6 +69,7 @@ struct DevBuf {
 };
 
 constexpr int kWarpsPerBlock = 4;
+constexpr uint32_t kBandPaysFromWindowLength = 768;   // rows of two or more 512-column chunks
 
 /* Persistent kernel: every GROUP of G lanes (G = 8, 16, 32; rp_warp.cuh) is an independent worker that pulls
  * windows from an atomic queue — 32/G windows in flight per warp, advancing together wherever their control
@@ -261,7 +262,7 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
     p->P.match = match;
     p->P.mismatch = mismatch;
     p->P.gap = gap;
-    p->P.banded = banded ? 1 : 0;
+    p->P.banded = banded ? 1 : 0;   // the request; configure() decides whether the band layout is used (window length)
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (mem_bytes == 0 || mem_bytes > free_b) mem_bytes = static_cast<size_t>(free_b * 0.8);
@@ -324,6 +325,13 @@ static rp_status configure(rp_poa* p, uint32_t wl) {
     int band_k = (banded && group == 32) ? 8 : 16;
     if (const char* e_k = getenv("RP_POA_BAND_K")) band_k = atoi(e_k);
     if (group != 32 || (band_k != 4 && band_k != 8)) band_k = 16;
+    /* -b is a request for speed with unchanged results.  Measured (profiles/README.md, round 2): for rows that fit one
+     * 512-column chunk the full matrix is the faster kernel (a DP row's cost is mostly width-independent), the band
+     * pays from two chunks per row on (w = 1000: 1.35x).  So a banded object uses the band when its windows are long
+     * enough, or when the band layout is asked for explicitly (RP_POA_BAND_K / RP_POA_GROUP: tests, bench config 3). */
+    const bool band_forced = getenv("RP_POA_BAND_K") != nullptr || getenv("RP_POA_GROUP") != nullptr;
+    p->P.banded = (banded && (band_forced || wl >= kBandPaysFromWindowLength)) ? 1 : 0;
+    if (!p->P.banded) band_k = 16;
     int bps = band_k == 16 ? 4 : 5;
     if (const char* e_bps = getenv("RP_BLOCKS_PER_SM")) bps = atoi(e_bps);
     if (band_k == 16) {
@@ -796,6 +804,7 @@ rp_status rp_poa_band_info(rp_poa* p, uint64_t info[8]) {
     if (s != RP_OK) return s;
     std::memset(info, 0, 8 * sizeof(uint64_t));
     info[0] = p->banded ? 1 : 0;
+    info[5] = p->P.banded ? 1 : 0;   // the band layout is in use for this object's window length
     info[1] = p->h_band[0];
     info[2] = p->h_band[1];
     info[3] = static_cast<uint64_t>(p->group) * p->band_k;

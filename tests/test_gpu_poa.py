@@ -35,6 +35,16 @@ def _mk(name, seed):
     return ws
 
 
+@pytest.fixture(autouse=True)
+def _force_the_band_layout(request, monkeypatch):
+    """A banded object only uses the band layout for windows of >= 768 bases (where it is the faster kernel).  The
+    `banded` parametrisations below exist to test the band itself, so they ask for it explicitly (256 columns)."""
+    if "banded" in getattr(request.node, "callspec", type("x", (), {"params": {}})).params and \
+            request.node.callspec.params["banded"] and "RP_POA_BAND_K" not in os.environ:
+        monkeypatch.setenv("RP_POA_BAND_K", "8")
+    yield
+
+
 def _compare(ws, scores=(3, -5, -4), trim=True, window_length=500, banded=False, band_stats=None):
     m, x, g = scores
     cons, pol, st, covs = api.consensus(ws, m, x, g, trim=trim, window_length=window_length, want_coverage=True,
@@ -309,3 +319,18 @@ def test_gpu_four_batch_objects_per_gpu_like_racon_c4():
     assert "%016x" % windows.fnv1a64(cons[:200]) == "50f18d884e3254d2"
     ref, _, _ = api.consensus(ws)
     assert cons == ref
+
+
+def test_gpu_banded_policy_by_window_length():
+    """racon -b is a request for speed with unchanged results: for 500-base windows the full matrix is the faster kernel,
+    so a banded object does not use the band layout there (and says so); for 1000-base windows it does.  Same consensus
+    either way."""
+    assert "RP_POA_BAND_K" not in os.environ and "RP_POA_GROUP" not in os.environ
+    ws = _mk("fullspan", seed=41)
+    stats = {}
+    _compare(ws, banded=True, band_stats=stats)
+    assert stats["banded"] and not stats["band_layout_in_use"] and stats["band_alignments"] == 0
+    big = util.make_set(42, 6, wlen=1000, depth=12, err=0.1, partial_frac=0.2)
+    stats = {}
+    _compare(big, window_length=1000, banded=True, band_stats=stats)
+    assert stats["band_layout_in_use"] and stats["band_alignments"] > 0 and stats["band_width"] == 256
