@@ -189,6 +189,12 @@ struct alignas(8) U2 {
     uint32_t x, y;
 };
 #if defined(RP_HOST_SIM)
+static unsigned long g_sim_scan_rows = 0, g_sim_scan_full = 0;   // simulation only: how often the full carry scan runs
+#define RP_SIM_COUNT(x) do { if (lane == 0) ++(x); } while (0)
+#else
+#define RP_SIM_COUNT(x) do { } while (0)
+#endif
+#if defined(RP_HOST_SIM)
 /* simulation only (debug_flags bit 3): copies for the band audit's diagnosis of a differing alignment */
 struct AuditStep { uint32_t i, j, move, p; int32_t h; };
 static std::vector<AuditStep> g_audit_path[2];
@@ -716,6 +722,9 @@ struct PoaWarp {
                 ring[swz(c)] = static_cast<int16_t>(static_cast<int32_t>(ch * kCC + c) * g);
             syncwarp();
             const bool multi = ch > 0;
+            /* columns beyond the read's last one are computed but never read by anything that matters (dependencies run
+             * left to right and the walk starts at column len): lanes that only hold such columns do not vote */
+            const bool scan_lane = ch * kCC + lanem * 16u <= len;
             uint32_t rec_a_lo = 0, rec_a_hi = 0, rec_b_lo = 0, rec_b_hi = 0;
             int16_t* hrow = H + static_cast<uint64_t>(ch) * kCC;  // row i of this chunk = hrow + i*lpa
             uint32_t myslot = 0;  // i % ring_rows, kept incrementally (any ring size, no division)
@@ -799,14 +808,25 @@ struct PoaWarp {
                 int32_t chunk_carry = kNeg32;
                 if (multi) chunk_carry = cc_prev[i];
                 int32_t t = hi16(acc[7]);
-                t = viaddmax_s32(lanem == 0 ? chunk_carry : kNeg32, 16 * g, t);
-#pragma unroll
-                for (int dd = 1; dd < G; dd <<= 1) {
-                    int32_t o = shfl_up(t, dd);
-                    t = viaddmax_s32(lanem >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * 16 * g, t);
-                }
+                /* Short cut: if no lane's total is raised by what its left neighbour hands over (neighbour's total +
+                 * 16 gaps), no carry travels further than one lane and the carry into a lane is simply the neighbour's
+                 * total — one shuffle and a vote instead of the five dependent scan steps.  (Right of the alignment
+                 * path the gap-extended values tie with the diagonal ones already in the row, so this is the common
+                 * case; the scan stays for the rows where a long gap run really wins.) */
                 int32_t carry = shfl_up(t, 1);
                 carry = lanem == 0 ? chunk_carry : carry;
+                if (ballot(scan_lane && carry + 16 * g > t)) {  // group-uniform
+                    t = viaddmax_s32(lanem == 0 ? chunk_carry : kNeg32, 16 * g, t);
+#pragma unroll
+                    for (int dd = 1; dd < G; dd <<= 1) {
+                        int32_t o = shfl_up(t, dd);
+                        t = viaddmax_s32(lanem >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * 16 * g, t);
+                    }
+                    carry = shfl_up(t, 1);
+                    carry = lanem == 0 ? chunk_carry : carry;
+                    RP_SIM_COUNT(g_sim_scan_full);
+                }
+                RP_SIM_COUNT(g_sim_scan_rows);
                 carry = carry < negsafe ? negsafe : carry;
                 const uint32_t c2 = pack16(carry, carry);
 #pragma unroll
@@ -987,13 +1007,17 @@ struct PoaWarp {
             for (int r = 0; r < R; ++r) acc[r] = viaddmax_s16x2(bridge, gb[r], acc[r]);
             /* max-plus scan of the lane totals in band order (the band starts at lane s_cur * LPB mod G) */
             int32_t t = hi16(acc[R - 1]);
-#pragma unroll
-            for (int dd = 1; dd < G; dd <<= 1) {
-                const int32_t o = shfl(t, (lanem - dd) & (G - 1));
-                t = viaddmax_s32(bo >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * KB * g, t);
-            }
-            int32_t carry = shfl(t, lane_left);
+            int32_t carry = shfl(t, lane_left);   // same short cut as in dp(): usually no carry travels beyond one lane
             carry = bo == 0 ? kNeg32 : carry;
+            if (ballot(cb * 16u + sub_lane * KB <= len && carry + KB * g > t)) {  // group-uniform; see dp()
+#pragma unroll
+                for (int dd = 1; dd < G; dd <<= 1) {
+                    const int32_t o = shfl(t, (lanem - dd) & (G - 1));
+                    t = viaddmax_s32(bo >= static_cast<uint32_t>(dd) ? o : kNeg32, dd * KB * g, t);
+                }
+                carry = shfl(t, lane_left);
+                carry = bo == 0 ? kNeg32 : carry;
+            }
             carry = carry < negsafe ? negsafe : carry;
             const uint32_t c2 = pack16(carry, carry);
 #pragma unroll

@@ -132,6 +132,11 @@ int rp_sim_aln_bp(uint32_t n_pairs, const uint8_t* bases, const uint32_t* q_off,
 }
 
 unsigned long rp_sim_leaf_pairs() { return rp::g_sim_leaf_pairs; }
+/* DP rows processed / rows that needed the full in-row carry scan (the rest took the one-shuffle short cut) */
+void rp_sim_scan_counts(unsigned long* out) {
+    out[0] = rp::g_sim_scan_rows;
+    out[1] = rp::g_sim_scan_full;
+}
 
 /* packing only (host-side cost of rp_poa_add_window): returns number of GPU windows packed */
 int rp_sim_pack_only(uint32_t n_windows, const char* bases, const char* quals, const uint64_t* seq_off,
