@@ -352,10 +352,6 @@ def main():
 
     cfg = CONFIGS[args.config]
     banded = cfg["banded"] if args.banded < 0 else bool(args.banded)
-    if banded:
-        # the configuration is DEFINED as the banded run: ask for the band layout explicitly (a banded object would
-        # otherwise pick the full matrix for 500-base windows, where that is the faster kernel — see `band` below)
-        os.environ.setdefault("RP_POA_BAND_K", "8")
     wl = cfg["wl"]
     aligner = None
     meta = {}
@@ -444,12 +440,21 @@ def main():
     total_ms = ev0.elapsed_time(ev1)
     gpu_launches = batch.info()["launches"] + batch2.info()["launches"] - launches0
     batch2.close()
-    full_ms = None
-    if banded:   # what -b does by default at this window length: the full-matrix kernel (same results)
-        saved = os.environ.pop("RP_POA_BAND_K", None)
+    forced = None
+    if banded:
+        # A banded object (racon -b) picks the kernel by window length: the band layout from 768 bases on, the full matrix
+        # below — same results, the faster of the two.  Everything above measured THAT.  The band layout
+        # itself, asked for explicitly on the same windows: isolated launches + how many band results the device refused.
+        saved = os.environ.get("RP_POA_BAND_K")
+        os.environ["RP_POA_BAND_K"] = "8"
         bf = api.PoaBatch(device=local, window_length=wl, banded=True, mem_bytes=mem)
         bf.set_stream(stream.cuda_stream)
         assert bf.add_window_set(ws) == n
+        bf.run()
+        bf.sync()
+        fo, fl, _, fst = bf.fetch_all(stride)
+        f_ck = "%016x" % windows.fnv1a64([fo[i, :fl[i]].tobytes() for i in range(min(n, 200))])
+        fbi = bf.band_info()
         bf.upload()
         bf.launch()
         barrier()
@@ -459,10 +464,12 @@ def main():
         bf.launch()
         f1.record(stream)
         barrier()
-        full_ms = f0.elapsed_time(f1) / 2
-        default_uses_band = bf.band_info()["band_layout_in_use"] if False else None
+        forced = {"ms": f0.elapsed_time(f1) / 2, "tried": fbi["band_alignments"], "redone": fbi["band_redone_full"],
+                  "width": fbi["band_width"], "same_consensus": f_ck == checksum and not (fst != 0).any()}
         bf.close()
-        if saved is not None:
+        if saved is None:
+            os.environ.pop("RP_POA_BAND_K", None)
+        else:
             os.environ["RP_POA_BAND_K"] = saved
 
     # ---- end-to-end arm: C-ABI call with host buffers (H2D + kernel + D2H + fetch) ------------------
@@ -523,8 +530,8 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- max over ranks ---------------------------------------------------------------------------
-    tt = torch.tensor([total_ms, e2e_ms, float(band_info["band_alignments"]), float(band_info["band_redone_full"]),
-                       float(full_ms or 0.0)], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([total_ms, e2e_ms, float(forced["tried"] if forced else 0), float(forced["redone"] if forced else 0),
+                       float(forced["ms"] if forced else 0.0)], dtype=torch.float64, device="cuda")
     if distributed:
         t2 = tt.clone()
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -532,7 +539,7 @@ def main():
         band_tot = (float(t2[2]), float(t2[3]))
     else:
         band_tot = (float(tt[2]), float(tt[3]))
-    total_ms, e2e_ms, full_ms = float(tt[0]), float(tt[1]), float(tt[4])
+    total_ms, e2e_ms, forced_ms = float(tt[0]), float(tt[1]), float(tt[4])
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -574,14 +581,17 @@ def main():
                                  "the band's columns per row"},
         }
         if banded:
-            line["band"] = {"width_columns": band_info["band_width"], "alignments_tried_in_band": int(band_tot[0]),
-                            "redone_with_full_matrix_on_device": int(band_tot[1]),
-                            "result_check": "consensus checksum of the first 200 windows == the reference's known "
-                                            "answer (full-matrix spoa)" if cfg["shape"] == "ont" else "see tests",
-                            "layout": "asked for explicitly (RP_POA_BAND_K=8); by default a banded object uses the band "
-                                      "for windows of >= 768 bases and the full matrix below that",
-                            "value_with_default_policy_isolated": n_total / (full_ms * 1e-3) if full_ms else None,
-                            "value_band_isolated": n_total / (kern_avg_ms * 1e-3)}
+            line["band"] = {
+                "policy": "a banded object uses the band layout for windows of >= 768 bases and the full-matrix kernel below "
+                          "(same results; the faster kernel either way): value / e2e / roofline above are what -b runs for "
+                          "this window length",
+                "layout_in_use_here": bool(band_info["band_layout_in_use"]),
+                "band_layout_forced": {
+                    "width_columns": forced["width"], "alignments_tried_in_band": int(band_tot[0]),
+                    "redone_with_full_matrix_on_device": int(band_tot[1]),
+                    "same_consensus_as_default": bool(forced["same_consensus"]),
+                    "kernel_ms_isolated": forced_ms, "value_isolated": n_total / (forced_ms * 1e-3),
+                    "value_default_isolated": n / (kern_avg_ms * 1e-3) * (n_total / n)}}
         if aligner:
             line["aligner"] = aligner
         if not args.no_cpu_baseline:
