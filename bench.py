@@ -643,7 +643,7 @@ def gpu_reference(args, cfg, banded, world):
     if banded:
         cmd.append("--banded")
     try:
-        p = subprocess.run(cmd, cwd=here, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=420, text=True)
+        p = subprocess.run(cmd, cwd=here, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=240, text=True)
         lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
         return json.loads(lines[-1]) if lines else {"unavailable": "no output (exit %d)" % p.returncode}
     except Exception as e:  # noqa: BLE001 - reported, never fatal

@@ -217,3 +217,26 @@ def test_gpu_banded_real_larger_windows():
     cons, pol, st = api.consensus(ws, 5, -4, -8, window_length=1000, banded=True, band_stats=stats)
     assert (st == 0).all(), st
     assert cons == ref and b"".join(cons) == polished
+
+
+@pytest.mark.parametrize("kb", [8, 4])
+def test_sim_banded_on_real_windows(kb):
+    """The banded device code (32 lanes x 8 / 4 columns) in the CPU simulation on real lambda windows — the deepest and two
+    with partial-span layers — with the band audit on: same consensus as the unmodified reference, no accepted band
+    alignment differs from the full-matrix one."""
+    from tests import simlib
+    ws, ref, _, _ = load()
+    depth = np.diff(ws.win_first.astype(np.int64))
+    pick = [int(np.argmax(depth))]
+    for w in range(ws.n_windows):
+        s0, s1 = int(ws.win_first[w]), int(ws.win_first[w + 1])
+        blen = int(ws.seq_off[s0 + 1] - ws.seq_off[s0])
+        if any(int(ws.seq_begin[s]) > 10 or int(ws.seq_end[s]) < blen - 10 for s in range(s0 + 1, s1)) and w not in pick:
+            pick.append(w)
+        if len(pick) == 3:
+            break
+    sub = ws.subset(pick)
+    cons, pol, st, _, stats = simlib.sim_consensus(sub, 3, -5, -4, lanes=32, smem=9216, banded=1, band_cols_per_lane=kb,
+                                                   debug_flags=2)
+    assert (st == 0).all() and cons == [ref[w] for w in pick]
+    assert stats[4] > 0 and stats[6] == 0, stats
