@@ -598,7 +598,15 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args, cfg, banded, world, ws)
         print(json.dumps(line))
     if distributed:
-        dist.barrier()
+        # The other ranks wait for rank 0's baselines on the HOST (rendezvous store), not in an NCCL barrier: a pending
+        # NCCL collective is a spinning kernel on every GPU, and the reference's GPU path is being timed on those GPUs.
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("bench_baselines_done", "1")
+            time.sleep(1.0)   # let the waiters read the key before the process that may host the store goes away
+        else:
+            store.wait(["bench_baselines_done"], datetime.timedelta(minutes=20))
         dist.destroy_process_group()
 
 
