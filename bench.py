@@ -313,6 +313,37 @@ def time_aligner(pairs, local, steps, warmup):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_near_gpu(props):
+    """Multi-rank runs: keep this rank's host threads (and with them its pinned staging buffers, first touched after this
+    call) on the CPUs of the socket its GPU hangs off (sysfs local_cpulist of the PCI device), as `numactl` would on a
+    production node; without it, 8 ranks' packers and H2D/D2H staging wander across both sockets.  Returns a short
+    description for the JSON line; any failure leaves the affinity untouched."""
+    if os.environ.get("RP_BENCH_NO_BIND"):
+        return "off (RP_BENCH_NO_BIND)"
+    try:
+        dev = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % dev) as f:
+            near = parse_cpulist(f.read())
+        have = os.sched_getaffinity(0)
+        use = near & have
+        if not use or use == have:
+            return "none needed (%d cpus, all local to %s)" % (len(have), dev)
+        os.sched_setaffinity(0, use)
+        return "%d of %d cpus, local to %s" % (len(use), len(have), dev)
+    except Exception as e:  # noqa: BLE001 — sysfs layout differs between boxes; the run is valid without the binding
+        return "unavailable (%s)" % type(e).__name__
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,6 +377,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the POA hot path has no CPU fallback")
     torch.cuda.set_device(local)
     distributed = world > 1
+    host_binding = bind_near_gpu(torch.cuda.get_device_properties(local)) if distributed else "single rank: not bound"
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -481,10 +513,18 @@ def main():
     bounds = [n * k // nb for k in range(nb + 1)]
     last = {}
 
+    # the one exchange step of the path: the final consensus gather over NCCL, once per step, asynchronous:
+    # a step's gather is queued when its last object is read back and finished before the next one is queued (and before
+    # the timed region ends), so no rank waits for another rank in the middle of its step
+    gather = shard.RowGather(n, stride, device="cuda", dst=0) if distributed else None
+
     def finalize(parts):
         out, lens, pol, st = (np.concatenate([p[i] for p in parts]) for i in range(4))
-        if distributed:  # the one exchange step of the path: final consensus gather over NCCL
-            last["gathered"] = shard.gather_rows(out, lens, device="cuda", dst=0)
+        if gather is not None:
+            got = gather.finish()
+            if got is not None:
+                last["gathered"] = got
+            gather.start(out, lens)
         last["out"], last["lens"] = out, lens
 
     def plugin_steps(n_steps):
@@ -512,6 +552,10 @@ def main():
         for k in range(nb):
             if pending[k] is not None:
                 collect(k)
+        if gather is not None:
+            got = gather.finish()
+            if got is not None:
+                last["gathered"] = got
 
     plugin_steps(2)
     barrier()
@@ -560,6 +604,7 @@ def main():
                             "steps_overlap": "timed steps alternate between two resident batch objects on two streams; "
                                              "roofline.kernel_ms is an isolated launch",
                             "workers_windows_in_flight": io["workers"], "first_pack_ms": pack_ms,
+                            "host_cpu_binding": host_binding,
                             "consensus_fnv_first200": checksum}, **meta),
             "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": io["h2d_bytes"], "d2h_bytes_per_step": io["d2h_bytes"],
@@ -568,7 +613,8 @@ def main():
                                 "staging) + rp_poa_run (H2D, kernel, D2H) + rp_poa_sync + rp_poa_fetch_all; the objects stay "
                                 "in flight across steps (as CUDAPolisher keeps its batches busy), timed from the first add "
                                 "to the last fetch"
-                                + ("; + NCCL all_gather of consensus bytes" if distributed else "")},
+                                + ("; + one NCCL all_gather of the step's consensus per step, queued asynchronously and "
+                                   "finished inside the timed region" if distributed else "")},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

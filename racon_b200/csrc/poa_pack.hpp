@@ -12,6 +12,9 @@
 #pragma once
 #include <stdint.h>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -166,11 +169,8 @@ struct PackedBatch {
         /* alphabet: the distinct characters of the window (any order: only equality matters on the device) */
         uint8_t seen[256];
         std::memset(seen, 0, sizeof(seen));
-        for (uint32_t i = 0; i < pr.order.size(); ++i) {
-            const uint8_t* sq = reinterpret_cast<const uint8_t*>(seq[pr.order[i]]);
-            const uint32_t n = len[pr.order[i]];
-            for (uint32_t j = 0; j < n; ++j) seen[sq[j]] = 1;
-        }
+        for (uint32_t i = 0; i < pr.order.size(); ++i)
+            scan_alphabet(reinterpret_cast<const uint8_t*>(seq[pr.order[i]]), len[pr.order[i]], seen);
         if (seen[0]) {
             pr.status = kPackInvalid;
             return;
@@ -184,6 +184,29 @@ struct PackedBatch {
             }
             pr.alpha |= static_cast<uint64_t>(c) << (8 * ncodes++);
         }
+    }
+
+    /* seen[c] = 1 for every byte value c of sq[0..n).  Sequences are almost always over the four bases: 16 bytes at a
+     * time are compared with A, C, G and T, and only a block holding anything else is walked byte by byte. */
+    static void scan_alphabet(const uint8_t* sq, uint32_t n, uint8_t* seen) {
+        uint32_t j = 0;
+#if defined(__SSE2__)
+        const __m128i ca = _mm_set1_epi8('A'), cc = _mm_set1_epi8('C'), cg = _mm_set1_epi8('G'), ct = _mm_set1_epi8('T');
+        int any_a = 0, any_c = 0, any_g = 0, any_t = 0;
+        for (; j + 16 <= n; j += 16) {
+            const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sq + j));
+            const int ma = _mm_movemask_epi8(_mm_cmpeq_epi8(v, ca)), mc = _mm_movemask_epi8(_mm_cmpeq_epi8(v, cc));
+            const int mg = _mm_movemask_epi8(_mm_cmpeq_epi8(v, cg)), mt = _mm_movemask_epi8(_mm_cmpeq_epi8(v, ct));
+            any_a |= ma; any_c |= mc; any_g |= mg; any_t |= mt;
+            if ((ma | mc | mg | mt) != 0xffff)
+                for (uint32_t t = 0; t < 16; ++t) seen[sq[j + t]] = 1;
+        }
+        if (any_a) seen[static_cast<uint8_t>('A')] = 1;
+        if (any_c) seen[static_cast<uint8_t>('C')] = 1;
+        if (any_g) seen[static_cast<uint8_t>('G')] = 1;
+        if (any_t) seen[static_cast<uint8_t>('T')] = 1;
+#endif
+        for (; j < n; ++j) seen[sq[j]] = 1;
     }
 
     /* serial; returns kPackOk / kPackFull / kPackNoMem (or pr.status when the window is malformed) */

@@ -108,3 +108,78 @@ def gather_rows(out, lens, device=None, group=None, dst=0):
         ll = g[r, 1:nr + 1, :4].copy().view("<u4").reshape(-1)
         res.append((g[r, 1:nr + 1, 4:], ll.astype(np.uint32)))
     return res
+
+
+class RowGather:
+    """The per-step consensus gather of a multi-rank run, asynchronous: start() queues ONE all_gather_into_tensor of this
+    rank's fixed-size block [n_max + 1, 4 + l_max] (row 0: window count; then length prefix + padded consensus per window)
+    and returns at once; finish() waits for it and, on rank `dst`, copies the gathered blocks to the host and returns
+    [(rows_r, lens_r)] in rank (= window) order (views of a reused pinned buffer: valid until the next finish()).  The block shape is fixed when the object is made (n_max = the largest
+    per-rank window count, agreed with one all-reduce here; l_max = the caller's row stride), so a step needs no shape
+    exchange and no rank waits for another one inside its step: the next step's packing and kernels overlap the gather."""
+
+    def __init__(self, n_local, l_max, device=None, group=None, dst=0):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.dst = torch, dist, group, dst
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dev = device if device is not None else "cpu"
+        t = torch.tensor([int(n_local)], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        self.n_max = int(t[0])
+        self.l_max = max(4, (int(l_max) + 3) // 4 * 4)
+        self.pending = None
+        self.host = None
+
+    def start(self, out, lens):
+        torch, dist = self.torch, self.dist
+        if self.pending is not None:
+            raise RuntimeError("RowGather.start: the previous gather was not finished")
+        n = int(len(lens))
+        if n > self.n_max:
+            raise ValueError("RowGather: %d windows exceed the agreed maximum %d" % (n, self.n_max))
+        block = np.zeros((self.n_max + 1, 4 + self.l_max), dtype=np.uint8)
+        block[0, :4] = np.asarray([n], dtype="<u4").view(np.uint8)
+        block[1:n + 1, :4] = np.asarray(lens, dtype="<u4").view(np.uint8).reshape(n, 4)
+        w = min(self.l_max, out.shape[1]) if n else 0
+        block[1:n + 1, 4:4 + w] = out[:n, :w]
+        mine = torch.from_numpy(block).to(self.dev, non_blocking=False)
+        gathered = torch.empty((self.world,) + block.shape, dtype=torch.uint8, device=self.dev)
+        try:
+            work = dist.all_gather_into_tensor(gathered, mine, group=self.group, async_op=True)
+            parts = None
+        except Exception:  # a backend without the flat variant
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            work = dist.all_gather(parts, mine, group=self.group, async_op=True)
+        self.pending = (work, gathered, parts, mine)
+
+    def finish(self):
+        if self.pending is None:
+            return None
+        work, gathered, parts, _mine = self.pending
+        self.pending = None
+        work.wait()
+        if self.rank != self.dst:
+            return None
+        torch = self.torch
+        g_dev = torch.stack(parts) if parts is not None else gathered
+        # only the columns some row uses travel to the host (the block is as wide as the caller's row stride)
+        lens_dev = g_dev[:, 1:, :4].contiguous().view(torch.int32)
+        w = min(self.l_max, (int(lens_dev.max()) + 3) // 4 * 4) if lens_dev.numel() else 0
+        cut = g_dev[:, :, :4 + w].contiguous()
+        if cut.is_cuda:
+            if self.host is None:
+                self.host = torch.empty(self.world * (self.n_max + 1) * (4 + self.l_max), dtype=torch.uint8, pin_memory=True)
+            h = self.host[:cut.numel()].view(cut.shape)
+            h.copy_(cut, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            g = h.numpy()
+        else:
+            g = cut.numpy()
+        res = []
+        for r in range(self.world):
+            nr = int(g[r, 0, :4].copy().view("<u4")[0])
+            ll = g[r, 1:nr + 1, :4].copy().view("<u4").reshape(-1)
+            res.append((g[r, 1:nr + 1, 4:], ll.astype(np.uint32)))
+        return res

@@ -42,6 +42,15 @@ def _worker(rank, world, port, n_windows, ret):
         assert flat == full
     else:
         assert rows is None
+    # the asynchronous form: two steps in flight one after the other, fixed block shape
+    rg = shard.RowGather(len(cons), stride, dst=0)
+    for step in range(2):
+        rg.start(out, lens)
+        got = rg.finish()
+        if rank == 0:
+            assert [rr[k, :ll[k]].tobytes() for rr, ll in got for k in range(len(ll))] == full
+        else:
+            assert got is None
     ret[rank] = full
     dist.barrier()
     dist.destroy_process_group()

@@ -133,6 +133,31 @@ def test_sim_edge_cases_ragged_and_degenerate():
         assert ref == cons and (rpol == pol).all()
 
 
+def test_sim_rare_characters_inside_long_runs_of_bases_reach_the_alphabet():
+    """The packer looks at 16 bases at a time and walks a block byte by byte only when it holds something other than
+    ACGT: one lower-case / IUPAC character deep inside a layer (and in the unaligned tail of one) must still be in the
+    window's alphabet — the consensus over it equals the oracle's, which compares characters directly."""
+    from racon_b200 import windows
+    rng = np.random.default_rng(11)
+    bb = bytes(rng.choice(list(b"ACGT"), size=150).astype(np.uint8))
+    lay = []
+    for k, (pos, ch) in enumerate([(3, b"n"), (37, b"R"), (64, b"a"), (149, b"Y"), (100, b"R"), (17, b"n"), (64, b"a")]):
+        t = bytearray(bb)
+        t[pos:pos + 1] = ch
+        lay.append((bytes(t), None, 0, len(bb) - 1))
+    ws = windows.from_lists([[(bb, None, 0, 0)] + lay + [(bb, None, 0, len(bb) - 1)]])
+    cons, pol, st, _, _ = simlib.sim_consensus(ws)
+    ora, opol, _ = ob.oracle_consensus(ws)
+    assert (st == 0).all() and cons == ora and (pol == opol).all()
+    # nine distinct characters: beyond the device's 8-code alphabet -> reported, not computed wrongly
+    t = bytearray(bb)
+    t[20:25] = b"nRaYN"
+    ws9 = windows.from_lists([[(bb, None, 0, 0), (bytes(t), None, 0, len(bb) - 1), (bb, None, 0, len(bb) - 1),
+                               (bb, None, 0, len(bb) - 1)]])
+    _, pol9, st9, _, _ = simlib.sim_consensus(ws9)
+    assert (st9 != 0).all() and not pol9.any()
+
+
 def test_sim_malformed_windows_are_rejected_not_crashed():
     """The reference exit(1)s on these (window.cpp:19-23,49-58); the ABI returns RP_ERR_INVALID instead."""
     from racon_b200 import windows
