@@ -80,7 +80,9 @@ def load(build_if_missing=True):
         for name in ("rp_mirror_align", "rp_mirror_consensus", "rp_mirror_polisher_open", "rp_mirror_polisher_open_with_bp",
                      "rp_mirror_polisher_counts", "rp_mirror_polisher_export", "rp_mirror_polisher_polish",
                      "rp_mirror_polisher_window_consensus", "rp_mirror_polisher_polished", "rp_mirror_polisher_close",
-                     "rp_mirror_polisher_failed", "rp_mirror_format_fasta", "rp_mirror_polisher_stream_fasta"):
+                     "rp_mirror_polisher_failed", "rp_mirror_format_fasta", "rp_mirror_polisher_stream_fasta",
+                     "rp_mirror_input_open", "rp_mirror_input_counts", "rp_mirror_input_export",
+                     "rp_mirror_input_cigar_breaking_points", "rp_mirror_input_close", "rp_mirror_polisher_open_files"):
             if hasattr(host, name):
                 setattr(lib, name, getattr(host, name))
     if hasattr(lib, "rp_mirror_align"):
@@ -425,6 +427,39 @@ class MirrorPolisher:
                                            1 if fragment_correction else 0, len(ov), _ptr(ov), window_length,
                                            quality_threshold, 1 if trim else 0, match, mismatch, gap, device)
 
+    @classmethod
+    def from_files(cls, reads, overlaps, targets, fragment_correction=False, window_length=500, quality_threshold=10.0,
+                   error_threshold=0.3, trim=True, match=3, mismatch=-5, gap=-4, device=0):
+        """createPolisher + initialize on files (reads_io.hpp): parse, filter, align + breaking points on the device
+        (SAM input keeps its own alignments and needs no device here), build the windows."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        L = self.lib
+        vp = C.c_void_p
+        L.rp_mirror_polisher_open_files.restype = vp
+        L.rp_mirror_polisher_open_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.c_double,
+                                                    C.c_double, C.c_int, C.c_int8, C.c_int8, C.c_int8, C.c_uint32, vp,
+                                                    C.c_uint32]
+        L.rp_mirror_polisher_counts.restype = None
+        L.rp_mirror_polisher_counts.argtypes = [vp, vp]
+        L.rp_mirror_polisher_export.restype = None
+        L.rp_mirror_polisher_export.argtypes = [vp] * 11
+        L.rp_mirror_polisher_polish.restype = C.c_uint32
+        L.rp_mirror_polisher_polish.argtypes = [vp, C.c_int]
+        L.rp_mirror_polisher_window_consensus.restype = C.c_uint32
+        L.rp_mirror_polisher_window_consensus.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
+        L.rp_mirror_polisher_polished.restype = C.c_uint64
+        L.rp_mirror_polisher_polished.argtypes = [vp, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint64]
+        L.rp_mirror_polisher_close.restype = None
+        L.rp_mirror_polisher_close.argtypes = [vp]
+        err = C.create_string_buffer(1024)
+        self.h = L.rp_mirror_polisher_open_files(os.fsencode(reads), os.fsencode(overlaps), os.fsencode(targets),
+                                                 1 if fragment_correction else 0, window_length, quality_threshold,
+                                                 error_threshold, 1 if trim else 0, match, mismatch, gap, device, err, 1024)
+        if not self.h:
+            raise RuntimeError(err.value.decode(errors="replace"))
+        return self
+
     def export(self):
         c = (C.c_uint64 * 3)()
         self.lib.rp_mirror_polisher_counts(self.h, c)
@@ -458,12 +493,13 @@ class MirrorPolisher:
 
     def stream_fasta(self, path, names, drop_unpolished=False, mem_bytes=0, banded=False):
         """Polisher::polish_streaming into a FASTA file: two batch objects in flight, every polished sequence written the
-        moment its last window is collected (polisher.cpp:504-537 + main.cpp:159-161).  names: target names by id."""
+        moment its last window is collected (polisher.cpp:504-537 + main.cpp:159-161).  names: target names by id
+        (None: the names of the files a from_files() polisher was opened on)."""
         f = self.lib.rp_mirror_polisher_stream_fasta
         f.restype = C.c_uint32
         f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_uint64, C.c_int]
-        blob = b"".join(n.encode() + b"\0" for n in names) + b"\0"
-        return f(self.h, 1 if drop_unpolished else 0, path.encode(), blob, mem_bytes, 1 if banded else 0)
+        blob = None if names is None else b"".join(n.encode() + b"\0" for n in names) + b"\0"
+        return f(self.h, 1 if drop_unpolished else 0, os.fsencode(path), blob, mem_bytes, 1 if banded else 0)
 
     def failed(self):
         """(overlaps, windows) the device could not finish (see host_mirror.hpp: Polisher::failed_overlaps/windows)."""
@@ -536,3 +572,78 @@ def mirror_consensus(ws, match=3, mismatch=-5, gap=-4, trim=True, window_length=
     if r < 0:
         raise RaconB200Error("rp_mirror_consensus failed (%r)" % r)
     return [out[w, :lens[w]].tobytes() for w in range(n)], pol.astype(bool)
+
+
+class InputFiles:
+    """The input layer of the C++ host layer (reads_io.hpp): sequence + overlap files -> what racon::Polisher::initialize
+    holds before it looks for breaking points — targets first, then the reads that are not a target; overlaps turned into
+    indices and filtered (racon -e, one overlap per read unless -f)."""
+
+    def __init__(self, reads, overlaps, targets, fragment_correction=False, error_threshold=0.3):
+        self.lib = load()
+        L = self.lib
+        vp = C.c_void_p
+        L.rp_mirror_input_open.restype = vp
+        L.rp_mirror_input_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_double, vp, C.c_uint32]
+        L.rp_mirror_input_counts.restype = None
+        L.rp_mirror_input_counts.argtypes = [vp, vp]
+        L.rp_mirror_input_export.restype = None
+        L.rp_mirror_input_export.argtypes = [vp] * 8
+        L.rp_mirror_input_cigar_breaking_points.restype = C.c_uint32
+        L.rp_mirror_input_cigar_breaking_points.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_uint32]
+        L.rp_mirror_input_close.restype = None
+        L.rp_mirror_input_close.argtypes = [vp]
+        err = C.create_string_buffer(1024)
+        self.h = L.rp_mirror_input_open(os.fsencode(reads), os.fsencode(overlaps), os.fsencode(targets),
+                                        1 if fragment_correction else 0, float(error_threshold), err, 1024)
+        if not self.h:
+            raise RuntimeError(err.value.decode(errors="replace"))
+        c = (C.c_uint64 * 7)()
+        L.rp_mirror_input_counts(self.h, c)
+        ns, self.n_targets, nb, no = int(c[0]), int(c[1]), int(c[2]), int(c[3])
+        self.window_type_tgs = bool(c[4])
+        self.bases = np.zeros(nb, np.uint8)
+        self.quals = np.zeros(nb, np.uint8)
+        self.seq_off = np.zeros(ns + 1, np.uint64)
+        self.seq_has_qual = np.zeros(ns, np.uint8)
+        names = np.zeros(max(1, int(c[5])), np.uint8)
+        self.overlaps = np.zeros((no, 9), np.uint32)
+        cigars = np.zeros(max(1, int(c[6])), np.uint8)
+        L.rp_mirror_input_export(self.h, _ptr(self.bases), _ptr(self.quals), _ptr(self.seq_off), _ptr(self.seq_has_qual),
+                                 _ptr(names), _ptr(self.overlaps), _ptr(cigars))
+        self.names = names.tobytes()[:int(c[5])].split(b"\0")[:ns]
+        self.cigars = cigars.tobytes()[:int(c[6])].split(b"\0")[:no]
+
+    def cigar_breaking_points(self, index, window_length=500):
+        """(t, q) breaking points of an overlap that came with a CIGAR (SAM input), from the host layer"""
+        n = self.lib.rp_mirror_input_cigar_breaking_points(self.h, index, window_length, None, 0)
+        out = np.zeros((n, 2), np.uint32)
+        self.lib.rp_mirror_input_cigar_breaking_points(self.h, index, window_length, _ptr(out), n)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.rp_mirror_input_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def polish_files(reads, overlaps, targets, out_path, fragment_correction=False, window_length=500, quality_threshold=10.0,
+                 error_threshold=0.3, trim=True, match=3, mismatch=-5, gap=-4, device=0, drop_unpolished=True,
+                 mem_bytes=0, banded=False):
+    """racon's whole run through the C++ host layer: files in, polished FASTA out (alignment, breaking points and
+    consensus on the device).  Returns (records written, overlaps the device refused, windows the device refused)."""
+    pol = MirrorPolisher.from_files(reads, overlaps, targets, fragment_correction=fragment_correction,
+                                    window_length=window_length, quality_threshold=quality_threshold,
+                                    error_threshold=error_threshold, trim=trim, match=match, mismatch=mismatch, gap=gap,
+                                    device=device)
+    try:
+        n = pol.stream_fasta(out_path, None, drop_unpolished=drop_unpolished, mem_bytes=mem_bytes, banded=banded)
+        return (n,) + pol.failed()
+    finally:
+        pol.close()

@@ -2,7 +2,8 @@
 
   libracon_b200.so       — the product: C-ABI (include/racon_b200.h) + sm_100a CUDA kernels, nothing else
   libracon_b200_host.so  — C++ host layer above the C ABI (racon_b200::Window / BatchProcessor / BatchAligner / Polisher,
-                           the reference interface restated) + the rp_mirror_* hooks tests/ and bench.py drive it with;
+                           the reference interface restated; reads_io: FASTA/FASTQ/PAF/MHAP/SAM input) + the rp_mirror_* hooks tests/ and
+                           bench.py drive it with;
                            links against the product, never part of it
   libracon_synth.so      — synthetic window generator (bench/test input maker, no CUDA)
   libracon_sim.so   — TEST-ONLY host simulation of the device code (tests/ only)
@@ -85,12 +86,13 @@ def build_host(force=False):
     """The C++ host layer above the C ABI + its test hooks, as a library of its own that links against the product."""
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libracon_b200_host.so")
-    src = os.path.join(CSRC, "host_mirror.cpp")
-    deps = [src, os.path.join(CSRC, "host_mirror.hpp"), os.path.join(CSRC, "poa_pack.hpp"),
-            os.path.join(ROOT, "include", "racon_b200.h"), os.path.join(LIBDIR, "libracon_b200.so")]
+    srcs = [os.path.join(CSRC, "host_mirror.cpp"), os.path.join(CSRC, "reads_io.cpp")]
+    deps = srcs + [os.path.join(CSRC, "host_mirror.hpp"), os.path.join(CSRC, "reads_io.hpp"),
+                   os.path.join(CSRC, "poa_pack.hpp"), os.path.join(ROOT, "include", "racon_b200.h"),
+                   os.path.join(LIBDIR, "libracon_b200.so")]
     if force or _newer(out, deps):
         _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-              "-o", out, src, "-L", LIBDIR, "-lracon_b200", "-Wl,-rpath,$ORIGIN"])
+              "-o", out] + srcs + ["-L", LIBDIR, "-lracon_b200", "-lz", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

@@ -10,6 +10,7 @@
 #include <iterator>
 
 #include "racon_b200.h"
+#include "reads_io.hpp"
 
 namespace racon_b200 {
 
@@ -267,11 +268,24 @@ const char* Polisher::reverse_quality(uint32_t id) {
 }
 
 void Polisher::find_overlap_breaking_points(std::vector<Overlap>& overlaps) {
-    rp_aln* aln = nullptr;
+    /* an overlap that came with an alignment (SAM input) keeps it, as in Overlap::find_breaking_points
+     * (overlap.cpp:186-203); only the others are aligned, in batches, on the device */
+    std::vector<size_t> todo;
+    todo.reserve(overlaps.size());
     uint32_t longest = 1;
-    for (const Overlap& o : overlaps) {
-        longest = std::max(longest, std::max(o.q_end - o.q_begin, o.t_end - o.t_begin));
+    for (size_t k = 0; k < overlaps.size(); ++k) {
+        Overlap& o = overlaps[k];
+        if (!o.breaking_points_.empty()) continue;
+        if (!o.cigar.empty()) {
+            breaking_points_from_cigar(o, window_length_);
+            std::string().swap(o.cigar);
+        } else {
+            todo.push_back(k);
+            longest = std::max(longest, std::max(o.q_end - o.q_begin, o.t_end - o.t_begin));
+        }
     }
+    if (todo.empty()) return;
+    rp_aln* aln = nullptr;
     rp_status s = rp_aln_create(&aln, static_cast<int>(device_), 0, longest);
     if (s == RP_OK) s = rp_aln_set_window_length(aln, window_length_);
     if (s != RP_OK) {
@@ -280,10 +294,10 @@ void Polisher::find_overlap_breaking_points(std::vector<Overlap>& overlaps) {
         exit(1);
     }
     size_t i = 0;
-    while (i < overlaps.size()) {
+    while (i < todo.size()) {
         const size_t first = i;
-        for (; i < overlaps.size(); ++i) {
-            const Overlap& o = overlaps[i];
+        for (; i < todo.size(); ++i) {
+            const Overlap& o = overlaps[todo[i]];
             /* the spans racon hands to the aligner (overlap.cpp:193-197) */
             const uint32_t q_start = o.strand ? o.q_length - o.q_end : o.q_begin;
             const char* q = (o.strand ? reverse_complement(o.q_id) : sequences_[o.q_id].data) + q_start;
@@ -307,10 +321,11 @@ void Polisher::find_overlap_breaking_points(std::vector<Overlap>& overlaps) {
                     rp_last_error());
             exit(1);
         }
-        for (size_t k = first; k < i; ++k) {
+        for (size_t j = first; j < i; ++j) {
+            const size_t k = todo[j];
             const uint32_t* pts = nullptr;
             uint32_t n = 0, st = 0;
-            rp_aln_fetch_cigar(aln, static_cast<uint32_t>(k - first), nullptr, nullptr, nullptr, &st);
+            rp_aln_fetch_cigar(aln, static_cast<uint32_t>(j - first), nullptr, nullptr, nullptr, &st);
             if (st != RP_ALN_OK) {
                 /* the reference re-aligns such overlaps with its CPU edlib (cudapolisher.cpp:213); this path has no CPU
                  * aligner, so the overlap contributes no layers and the caller is told */
@@ -318,7 +333,7 @@ void Polisher::find_overlap_breaking_points(std::vector<Overlap>& overlaps) {
                 failed_overlaps_.push_back(k);
                 continue;
             }
-            rp_aln_fetch_breaking_points(aln, static_cast<uint32_t>(k - first), &pts, &n);
+            rp_aln_fetch_breaking_points(aln, static_cast<uint32_t>(j - first), &pts, &n);
             overlaps[k].breaking_points_.clear();
             for (uint32_t b = 0; b < n; ++b) overlaps[k].breaking_points_.emplace_back(pts[2 * b], pts[2 * b + 1]);
         }
@@ -484,6 +499,7 @@ void Polisher::polish_streaming(const std::function<void(const PolishedSequence&
  * that tests/test_pipeline.py compares this pipeline and the unmodified reference Polisher field by field. */
 namespace {
 struct PolHandle {
+    std::unique_ptr<racon_b200::InputSet> input;   // owns the sequence bytes when the polisher was opened on files
     std::unique_ptr<racon_b200::Polisher> polisher;
     std::vector<racon_b200::PolishedSequence> polished;
 };
@@ -504,7 +520,7 @@ extern "C" void* rp_mirror_polisher_open(uint32_t n_seq, const char* bases, cons
     std::vector<Overlap> ovl(n_overlaps);
     for (uint32_t i = 0; i < n_overlaps; ++i) {
         const uint32_t* o = overlaps + 9ull * i;
-        ovl[i] = Overlap{o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], {}};
+        ovl[i] = Overlap{o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], {}, {}};
     }
     PolHandle* h = new PolHandle();
     h->polisher.reset(new Polisher(std::move(seqs), n_targets, window_type_tgs ? WindowType::kTGS : WindowType::kNGS,
@@ -530,7 +546,7 @@ extern "C" void* rp_mirror_polisher_open_with_bp(uint32_t n_seq, const char* bas
     std::vector<Overlap> ovl(n_overlaps);
     for (uint32_t i = 0; i < n_overlaps; ++i) {
         const uint32_t* o = overlaps + 9ull * i;
-        ovl[i] = Overlap{o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], {}};
+        ovl[i] = Overlap{o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], {}, {}};
         for (uint64_t b = bp_off[i]; b < bp_off[i + 1]; ++b) ovl[i].breaking_points_.emplace_back(bp[2 * b], bp[2 * b + 1]);
     }
     PolHandle* h = new PolHandle();
@@ -538,6 +554,31 @@ extern "C" void* rp_mirror_polisher_open_with_bp(uint32_t n_seq, const char* bas
                                    fragment_correction != 0, window_length, quality_threshold, true, 3, -5, -4, 0));
     h->polisher->build_windows(ovl);
     return h;
+}
+
+/* Files in: createPolisher + initialize (polisher.cpp:55-160,200-461) — reads_io's load_input, then alignment and breaking
+ * points on the device (overlaps that carry a CIGAR — SAM input — keep it and need no device) and the window building.
+ * NULL on an input error (message in err).  rp_mirror_polisher_stream_fasta(names = NULL) then is racon's main loop. */
+extern "C" void* rp_mirror_polisher_open_files(const char* reads, const char* overlaps, const char* targets,
+                                               int fragment_correction, uint32_t window_length, double quality_threshold,
+                                               double error_threshold, int trim, int8_t match, int8_t mismatch, int8_t gap,
+                                               uint32_t device, char* err, uint32_t err_cap) {
+    using namespace racon_b200;
+    try {
+        std::unique_ptr<PolHandle> h(new PolHandle());
+        h->input.reset(new InputSet(load_input(reads, overlaps, targets, fragment_correction != 0, error_threshold)));
+        h->polisher.reset(new Polisher(h->input->views(), h->input->targets_size, h->input->window_type,
+                                       fragment_correction != 0, window_length, quality_threshold, trim != 0, match,
+                                       mismatch, gap, device));
+        h->polisher->initialize(h->input->overlaps);
+        return h.release();
+    } catch (const std::exception& e) {
+        if (err && err_cap) {
+            std::strncpy(err, e.what(), err_cap - 1);
+            err[err_cap - 1] = '\0';
+        }
+        return nullptr;
+    }
 }
 
 /* failed[0] = overlaps, failed[1] = windows the device could not finish (Polisher::failed_overlaps/failed_windows) */
@@ -616,13 +657,17 @@ extern "C" uint64_t rp_mirror_polisher_polished(void* hv, uint32_t i, uint64_t* 
     return s.data.size();
 }
 
-/* Streaming polish straight into a FASTA file (names: NUL-separated target names, one per target id); returns the
+/* Streaming polish straight into a FASTA file (names: NUL-separated target names, one per target id; NULL = the names
+ * of the files the polisher was opened on); returns the
  * number of records written.  mem_bytes: budget per batch object (small budgets force many batches). */
 extern "C" uint32_t rp_mirror_polisher_stream_fasta(void* hv, int drop_unpolished, const char* path, const char* names,
                                                      uint64_t mem_bytes, int banded) {
     PolHandle* h = static_cast<PolHandle*>(hv);
     std::vector<std::string> name_of;
     for (const char* p = names; p && *p; p += std::strlen(p) + 1) name_of.emplace_back(p);
+    if (!names && h->input) {
+        for (uint64_t i = 0; i < h->input->targets_size; ++i) name_of.push_back(h->input->sequences[i].name);
+    }
     FILE* f = std::fopen(path, "wb");
     if (!f) return 0;
     uint32_t n = 0;

@@ -141,8 +141,8 @@ private:
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Mirror of the device-facing half of racon::CUDAPolisher: overlaps -> (device) alignment + breaking points ->
- * windows -> (device) consensus -> stitched sequences.  Parsing, overlap filtering and FASTA output stay with the
- * caller (SURVEY §8 out of scope); everything that touches sequence bytes in bulk runs on the GPU.
+ * windows -> (device) consensus -> stitched sequences.  Parsing and overlap filtering are reads_io.hpp's (load_input);
+ * everything that touches sequence bytes in bulk runs on the GPU.
  *   find_overlap_breaking_points : src/cuda/cudapolisher.cpp:72-213  (batched aligner loop)
  *                                  + src/overlap.cpp:226-292          (breaking points, on the device here)
  *   initialize (window building) : src/polisher.cpp:383-461
@@ -156,9 +156,16 @@ struct SequenceView {        // racon::Sequence as the polisher needs it; the by
 
 struct Overlap {             // racon::Overlap after transmute() (src/overlap.hpp:82-98)
     uint32_t q_id, t_id, strand, q_begin, q_end, q_length, t_begin, t_end, t_length;
+    std::string cigar;       // only when the overlap file carried an alignment (SAM): then it is used as it is
     std::vector<std::pair<uint32_t, uint32_t>> breaking_points_;
     const std::vector<std::pair<uint32_t, uint32_t>>& breaking_points() const { return breaking_points_; }
 };
+
+/* Breaking points of an overlap that arrived WITH an alignment (SAM): the (target, query) coordinates of the first and
+ * one-past-the-last aligned base pair inside every window of the target the alignment crosses — what
+ * Overlap::find_breaking_points_from_cigar (overlap.cpp:226-292) finds base by base, computed run by run here.
+ * (Overlaps without a CIGAR get theirs from the device: rp_aln_fetch_breaking_points.) */
+void breaking_points_from_cigar(Overlap& overlap, uint32_t window_length);
 
 struct PolishedSequence {
     uint64_t id;             // target index

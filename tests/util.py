@@ -1,4 +1,7 @@
 """Shared test helpers: random window makers (numpy RNG; test-only) and checker access."""
+import struct
+import zlib
+
 import numpy as np
 
 from racon_b200 import windows
@@ -61,3 +64,19 @@ def make_set(seed, n, types=None, **kw):
     rng = np.random.default_rng(seed)
     wins = [make_window(rng, **kw) for _ in range(n)]
     return windows.from_lists(wins, types)
+
+
+def window_crcs(r):
+    """one CRC-32 per window over its sequences: bases, qualities (where present), begin, end — same function on the
+    reference's window arrays and on MirrorPolisher.export()"""
+    out = []
+    for w in range(len(r["win_first"]) - 1):
+        c = zlib.crc32(bytes([int(r["win_type"][w])]))
+        for s in range(int(r["win_first"][w]), int(r["win_first"][w + 1])):
+            a, b = int(r["seq_off"][s]), int(r["seq_off"][s + 1])
+            c = zlib.crc32(r["bases"][a:b].tobytes(), c)
+            if r["seq_has_qual"][s]:
+                c = zlib.crc32(r["quals"][a:b].tobytes(), c)
+            c = zlib.crc32(struct.pack("<II", int(r["seq_begin"][s]), int(r["seq_end"][s])), c)
+        out.append(c)
+    return np.asarray(out, np.uint32)
