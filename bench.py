@@ -356,6 +356,7 @@ def main():
     ap.add_argument("--frag-reads", type=int, default=400, help="config 5: reads per GPU")
     ap.add_argument("--frag-read-len", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--internal-by-reference", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--e2e-batches", type=int, default=2,
                     help="batch objects the end-to-end arm cycles through (racon's -c/--cudapoa-batches)")
     args = ap.parse_args()
@@ -398,6 +399,9 @@ def main():
     n = ws.n_windows
     n_total = meta.get("windows_total", n * world)
     mem = int(os.environ.get("RP_BENCH_MEM", 40e9))     # device-memory budget per batch object (several are alive)
+    if args.internal_by_reference:
+        print(json.dumps(by_reference_leg(args, api, windows, torch, ws, local, wl, banded, mem)))
+        return
 
     def new_batch():
         return api.PoaBatch(device=local, window_length=wl, banded=banded, mem_bytes=mem)
@@ -640,6 +644,11 @@ def main():
                     "value_default_isolated": n / (kern_avg_ms * 1e-3) * (n_total / n)}}
         if aligner:
             line["aligner"] = aligner
+        if world == 1 and cfg["shape"] != "frag" and not os.environ.get("RP_BENCH_NO_BY_REFERENCE"):
+            br = by_reference(args)
+            if "consensus_fnv_first200" in br:
+                br["same_consensus_as_by_pointer"] = br["consensus_fnv_first200"] == checksum
+            line["e2e"]["by_reference"] = br
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, cfg, banded, world, ws)
         print(json.dumps(line))
@@ -654,6 +663,94 @@ def main():
         else:
             store.wait(["bench_baselines_done"], datetime.timedelta(minutes=20))
         dist.destroy_process_group()
+
+
+def by_reference(args):
+    """The end-to-end arm once more with the windows added BY REFERENCE into a device-resident read store (SURVEY §8 f2;
+    rp_reads_create + rp_poa_add_window_set_refs): the sequences are uploaded once, before the timed region — in a racon run
+    every read belongs to the run, not to a batch —, a step then moves descriptors only and the layers are extracted on the
+    device.  Reported beside `e2e`, which stays the by-pointer call of the reference's own interface.  Own process with a
+    time limit, like the reference's GPU path: the newest code path must not be able to take the bench line down."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, os.path.join(here, "bench.py"), "--internal-by-reference", "--config", str(args.config),
+           "--steps", str(args.steps), "--warmup", str(args.warmup), "--e2e-batches", str(args.e2e_batches)]
+    if args.windows:
+        cmd += ["--windows", str(args.windows)]
+    if args.banded >= 0:
+        cmd += ["--banded", str(args.banded)]
+    try:
+        p = subprocess.run(cmd, cwd=here, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, text=True)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if lines:
+            return json.loads(lines[-1])
+        return {"unavailable": "no output (exit %d): %s" % (p.returncode, p.stderr.strip().splitlines()[-1:] or "")}
+    except Exception as e:  # noqa: BLE001 - reported, never fatal
+        return {"unavailable": "%s" % e}
+
+
+def by_reference_leg(args, api, windows, torch, ws, local, wl, banded, mem):
+    """child process of by_reference(): K timed steps, each = per batch object reset + add-by-reference + run (descriptor
+    H2D, gather kernel, POA kernel, D2H) + sync + fetch_all, two objects in flight; host clock between device syncs"""
+    import numpy as np
+    n = ws.n_windows
+    stride = int(2 * np.diff(ws.seq_off.astype(np.int64)).max() + 64)
+    t0 = time.perf_counter()
+    store = api.ReadStore.from_flat(ws.bases, ws.seq_off, ws.quals, ws.seq_has_qual, device=local)
+    torch.cuda.synchronize()
+    store_ms = 1e3 * (time.perf_counter() - t0)
+    refs = windows.as_refs(ws)
+    nb = max(1, args.e2e_batches)
+    objs = [api.PoaBatch(device=local, window_length=wl, banded=banded, mem_bytes=mem) for _ in range(nb)]
+    bounds = [n * k // nb for k in range(nb + 1)]
+    last = {}
+
+    def steps(n_steps):
+        pending = [None] * nb
+        parts = {}
+
+        def collect(k):
+            objs[k].sync()
+            s_done = pending[k]
+            parts[s_done][k] = objs[k].fetch_all(stride)
+            pending[k] = None
+            if all(x is not None for x in parts[s_done]):
+                done = parts.pop(s_done)
+                last["out"], last["lens"], _, last["st"] = (np.concatenate([d[i] for d in done]) for i in range(4))
+
+        for s_i in range(n_steps):
+            parts[s_i] = [None] * nb
+            for k, b in enumerate(objs):
+                if pending[k] is not None:
+                    collect(k)
+                b.reset()
+                cnt = bounds[k + 1] - bounds[k]
+                assert b.add_window_set_refs(store, refs, first=bounds[k], count=cnt) == cnt
+                b.run()
+                pending[k] = s_i
+        for k in range(nb):
+            if pending[k] is not None:
+                collect(k)
+
+    steps(2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    steps(args.steps)
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0)
+    out, lens = last["out"], last["lens"]
+    res = {"value": n * args.steps / (ms * 1e-3), "unit": "windows/s", "ms_per_step": ms / args.steps,
+           "h2d_bytes_per_step": sum(b.info()["h2d_bytes"] for b in objs),
+           "d2h_bytes_per_step": sum(b.info()["d2h_bytes"] for b in objs),
+           "store_device_bytes": store.device_bytes(), "store_upload_ms_once": store_ms,
+           "device_limit_windows": int((last["st"] != 0).sum()),
+           "consensus_fnv_first200": "%016x" % windows.fnv1a64([out[i, :lens[i]].tobytes() for i in range(min(n, 200))]),
+           "includes": "per step and batch object: rp_poa_reset + rp_poa_add_window_set_refs (metadata only) + rp_poa_run "
+                       "(descriptor H2D, layer-extraction kernel, POA kernel, D2H) + rp_poa_sync + rp_poa_fetch_all; the "
+                       "sequences were uploaded once before the timed region (store_upload_ms_once)"}
+    for b in objs:
+        b.close()
+    store.close()
+    return res
 
 
 def cpu_baseline(args, cfg, banded, world, ws):

@@ -80,6 +80,40 @@ rp_status rp_poa_add_window(rp_poa* p, uint32_t n_seq, const char* const* seq, c
                             const char* const* qual, const uint32_t* begin, const uint32_t* end, int window_type,
                             int trim);
 
+/* ---- device-resident reads: windows whose layers are slices of sequences already in HBM ----------------
+ * The reference builds a window from pointers into its sequences (polisher.cpp:383-461: backbone = a stretch of the
+ * target, layer = a stretch of a read or of its reverse complement) and its CUDA path copies those bytes together on the
+ * host, window by window (cudabatch.cpp:77-175).  With a store, every sequence is uploaded once and a window names its
+ * pieces; the packed arrays the kernel reads are gathered on the device (reverse complement and quality -> weight
+ * included), so no sequence byte is touched on the host when a window is added.
+ *
+ * rp_reads_create: data[i] / length[i] = sequence i (targets and reads, any order); quality[i] NULL (or quality NULL) =
+ * no qualities.  The host arrays must stay valid while the store is alive (backbone copies of windows with < 3 sequences
+ * and the rare exact alphabet scan read them).  One store can serve any number of batch objects on the same device. */
+typedef struct rp_reads rp_reads;
+rp_status rp_reads_create(rp_reads** out, int device, uint32_t n_seqs, const char* const* data,
+                          const char* const* quality, const uint32_t* length);
+void rp_reads_destroy(rp_reads* r);
+/* device bytes the store occupies */
+uint64_t rp_reads_bytes(const rp_reads* r);
+
+/* rp_poa_add_window with the pieces named instead of passed: piece k = length[k] bases of sequence seq_id[k] starting at
+ * offset[k]; reverse[k] != 0: offset counts in the reverse complement of the sequence (racon's
+ * `reverse_complement()[offset]`), and the piece is read back to front, complemented, its qualities reversed.  Piece 0 is
+ * the backbone (never reverse; begin/end ignored).  Same checks, skips, statuses and results as rp_poa_add_window.
+ * A batch holds either windows added this way (all from one store) or windows added by pointer: RP_ERR_STATE otherwise. */
+rp_status rp_poa_add_window_refs(rp_poa* p, const rp_reads* reads, uint32_t n_seq, const uint32_t* seq_id,
+                                 const uint32_t* offset, const uint32_t* length, const uint8_t* reverse,
+                                 const uint32_t* begin, const uint32_t* end, int window_type, int trim);
+
+/* Bulk form of rp_poa_add_window_refs: windows [first, first + count) of a flat description — pieces
+ * win_first[w] .. win_first[w + 1] of the piece arrays belong to window w, backbone first (win_type NULL = all TGS).
+ * Stops at the first window that does not fit; *added = how many were taken (RP_OK when > 0, else RP_BATCH_FULL). */
+rp_status rp_poa_add_window_set_refs(rp_poa* p, const rp_reads* reads, uint32_t first, uint32_t count,
+                                     const uint32_t* seq_id, const uint32_t* offset, const uint32_t* length,
+                                     const uint8_t* reverse, const uint32_t* begin, const uint32_t* end,
+                                     const uint32_t* win_first, const uint8_t* win_type, int trim, uint32_t* added);
+
 /* Bulk form of rp_poa_add_window over flat arrays (see racon_b200/windows.py): adds windows
  * [first, first + count) of the set until the batch is full; *added = how many were taken. */
 rp_status rp_poa_add_window_set(rp_poa* p, uint32_t first, uint32_t count, const char* bases, const char* quals,

@@ -132,6 +132,68 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
+class ReadStore:
+    """Device-resident sequences (rp_reads): uploaded once; windows then name their layers as slices of them
+    (PoaBatch.add_window_refs).  sequences: list of bytes; qualities: list of bytes / None (or None for no qualities)."""
+
+    def __init__(self, sequences, qualities=None, device=0):
+        self.lib = load()
+        n = len(sequences)
+        self._keep = (list(sequences), list(qualities) if qualities is not None else None)
+        sp = (C.c_char_p * n)(*sequences)
+        qp = None
+        if qualities is not None:
+            qp = (C.c_char_p * n)(*[q if q else None for q in qualities])
+        ln = (C.c_uint32 * n)(*[len(x) for x in sequences])
+        self._arrays = (sp, qp, ln)
+        self.h = C.c_void_p()
+        f = self.lib.rp_reads_create
+        f.restype = C.c_int32
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(self.lib, f(C.byref(self.h), device, n, sp, qp, ln), "rp_reads_create")
+
+    @classmethod
+    def from_flat(cls, bases, seq_off, quals=None, seq_has_qual=None, device=0):
+        """Store over flat arrays (numpy uint8 bases / quals, uint64 offsets): sequence i = bases[seq_off[i]:seq_off[i+1]]."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        n = len(seq_off) - 1
+        base = bases.ctypes.data
+        off = np.asarray(seq_off, dtype=np.uint64)
+        ptrs = np.ascontiguousarray(off[:-1] + np.uint64(base))
+        qptrs = None
+        if quals is not None and seq_has_qual is not None and np.any(seq_has_qual):
+            qptrs = np.ascontiguousarray(np.where(np.asarray(seq_has_qual) != 0, off[:-1] + np.uint64(quals.ctypes.data),
+                                                  np.uint64(0)).astype(np.uint64))
+        ln = np.ascontiguousarray(np.diff(off).astype(np.uint32))
+        self._keep = (bases, quals, ptrs, qptrs, ln)
+        self._arrays = None
+        self.h = C.c_void_p()
+        f = self.lib.rp_reads_create
+        f.restype = C.c_int32
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(self.lib, f(C.byref(self.h), device, n, _ptr(ptrs), _ptr(qptrs), _ptr(ln)), "rp_reads_create")
+        return self
+
+    def device_bytes(self):
+        self.lib.rp_reads_bytes.restype = C.c_uint64
+        self.lib.rp_reads_bytes.argtypes = [C.c_void_p]
+        return int(self.lib.rp_reads_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.rp_reads_destroy.restype = None
+            self.lib.rp_reads_destroy.argtypes = [C.c_void_p]
+            self.lib.rp_reads_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PoaBatch:
     """racon::CUDABatchProcessor-shaped batch object (add windows -> run -> fetch)."""
 
@@ -182,6 +244,35 @@ class PoaBatch:
             en[i] = e
         st = self.lib.rp_poa_add_window(self.h, n, sp, ln, qp, bg, en, window_type, 1 if trim else 0)
         return _check(self.lib, st, "rp_poa_add_window")
+
+    def add_window_refs(self, store, pieces, window_type=1, trim=True):
+        """pieces: [(sequence id in `store`, offset, length, reverse, begin, end), ...], backbone first — the window's
+        layers named as slices of a device-resident ReadStore.  Returns RP_OK or RP_BATCH_FULL."""
+        a = np.ascontiguousarray(np.asarray(pieces, dtype=np.int64).reshape(-1, 6))
+        cols = [np.ascontiguousarray(a[:, k].astype(np.uint32)) for k in (0, 1, 2)]
+        rev = np.ascontiguousarray(a[:, 3].astype(np.uint8))
+        bg, en = (np.ascontiguousarray(a[:, k].astype(np.uint32)) for k in (4, 5))
+        f = self.lib.rp_poa_add_window_refs
+        f.restype = C.c_int32
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.c_int, C.c_int]
+        st = f(self.h, store.h, len(a), _ptr(cols[0]), _ptr(cols[1]), _ptr(cols[2]), _ptr(rev), _ptr(bg), _ptr(en),
+               window_type, 1 if trim else 0)
+        return _check(self.lib, st, "rp_poa_add_window_refs")
+
+    def add_window_set_refs(self, store, refs, first=0, count=None, trim=True):
+        """Bulk add_window_refs.  refs: dict of flat arrays seq_id, offset, length, reverse (uint8), begin, end (one entry
+        per piece) + win_first (windows + 1) and optionally win_type.  Returns how many windows fit."""
+        if count is None:
+            count = len(refs["win_first"]) - 1 - first
+        f = self.lib.rp_poa_add_window_set_refs
+        f.restype = C.c_int32
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p]
+        added = C.c_uint32(0)
+        st = f(self.h, store.h, first, count, _ptr(refs["seq_id"]), _ptr(refs["offset"]), _ptr(refs["length"]),
+               _ptr(refs.get("reverse")), _ptr(refs["begin"]), _ptr(refs["end"]), _ptr(refs["win_first"]),
+               _ptr(refs.get("win_type")), 1 if trim else 0, C.byref(added))
+        _check(self.lib, st, "rp_poa_add_window_set_refs")
+        return added.value
 
     def size(self):
         return self.lib.rp_poa_size(self.h)
@@ -491,15 +582,17 @@ class MirrorPolisher:
             out.append((tid.value, tags.value.decode(), data.raw[:k]))
         return cons, out
 
-    def stream_fasta(self, path, names, drop_unpolished=False, mem_bytes=0, banded=False):
+    def stream_fasta(self, path, names, drop_unpolished=False, mem_bytes=0, banded=False, resident_reads=False):
         """Polisher::polish_streaming into a FASTA file: two batch objects in flight, every polished sequence written the
         moment its last window is collected (polisher.cpp:504-537 + main.cpp:159-161).  names: target names by id
-        (None: the names of the files a from_files() polisher was opened on)."""
+        (None: the names of the files a from_files() polisher was opened on).  resident_reads: every sequence is
+        uploaded once and the windows are added by reference (layers extracted on the device)."""
         f = self.lib.rp_mirror_polisher_stream_fasta
         f.restype = C.c_uint32
-        f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_uint64, C.c_int]
+        f.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_uint64, C.c_int, C.c_int]
         blob = None if names is None else b"".join(n.encode() + b"\0" for n in names) + b"\0"
-        return f(self.h, 1 if drop_unpolished else 0, os.fsencode(path), blob, mem_bytes, 1 if banded else 0)
+        return f(self.h, 1 if drop_unpolished else 0, os.fsencode(path), blob, mem_bytes, 1 if banded else 0,
+                 1 if resident_reads else 0)
 
     def failed(self):
         """(overlaps, windows) the device could not finish (see host_mirror.hpp: Polisher::failed_overlaps/windows)."""
@@ -635,7 +728,7 @@ class InputFiles:
 
 def polish_files(reads, overlaps, targets, out_path, fragment_correction=False, window_length=500, quality_threshold=10.0,
                  error_threshold=0.3, trim=True, match=3, mismatch=-5, gap=-4, device=0, drop_unpolished=True,
-                 mem_bytes=0, banded=False):
+                 mem_bytes=0, banded=False, resident_reads=True):
     """racon's whole run through the C++ host layer: files in, polished FASTA out (alignment, breaking points and
     consensus on the device).  Returns (records written, overlaps the device refused, windows the device refused)."""
     pol = MirrorPolisher.from_files(reads, overlaps, targets, fragment_correction=fragment_correction,
@@ -643,7 +736,8 @@ def polish_files(reads, overlaps, targets, out_path, fragment_correction=False, 
                                     error_threshold=error_threshold, trim=trim, match=match, mismatch=mismatch, gap=gap,
                                     device=device)
     try:
-        n = pol.stream_fasta(out_path, None, drop_unpolished=drop_unpolished, mem_bytes=mem_bytes, banded=banded)
+        n = pol.stream_fasta(out_path, None, drop_unpolished=drop_unpolished, mem_bytes=mem_bytes, banded=banded,
+                             resident_reads=resident_reads)
         return (n,) + pol.failed()
     finally:
         pol.close()

@@ -7,6 +7,8 @@
                            links against the product, never part of it
   libracon_synth.so      — synthetic window generator (bench/test input maker, no CUDA)
   libracon_sim.so   — TEST-ONLY host simulation of the device code (tests/ only)
+  simapi/libracon_b200.so, simapi/libracon_b200_host.so — TEST-ONLY: the C ABI and the host layer over a simulated CUDA
+                           runtime (csrc/cuda_sim_runtime.h), for pre-verifying the `gpu` tests on a machine without a GPU
 The checkers (restated CPU model and the compiled reference) have their own recipe outside this package.
 """
 import os
@@ -105,6 +107,25 @@ def build_sim(force=False):
         _run(["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-DRP_HOST_SIM=1", "-x", "c++",
               "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out,
               os.path.join(CSRC, "sim_main.cu")])
+    return out
+
+
+def build_simapi(force=False, subdir="simapi"):
+    """TEST-ONLY: the whole C ABI (rp_api.cu) and the C++ host layer compiled for the host, the CUDA runtime replaced by
+    csrc/cuda_sim_runtime.h and kernel launches by the fibre simulation of the device code.  Lives in lib/simapi/ under the
+    product's file names so that RACON_B200_LIB=<...>/lib/simapi/libracon_b200.so swaps it in for the tests."""
+    d = os.path.join(LIBDIR, subdir)
+    os.makedirs(d, exist_ok=True)
+    out = os.path.join(d, "libracon_b200.so")
+    deps = _csrc_files((".cu", ".cuh", ".h", ".hpp", ".cpp")) + [os.path.join(ROOT, "include", "racon_b200.h")]
+    if force or _newer(out, deps):
+        _run(["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-DRP_HOST_SIM=1", "-x", "c++",
+              "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out, os.path.join(CSRC, "rp_api.cu"), "-lpthread"])
+    host = os.path.join(d, "libracon_b200_host.so")
+    if force or _newer(host, deps + [out]):
+        _run(["g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+              "-o", host, os.path.join(CSRC, "host_mirror.cpp"), os.path.join(CSRC, "reads_io.cpp"),
+              "-L", d, "-lracon_b200", "-lz", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

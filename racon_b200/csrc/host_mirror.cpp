@@ -49,6 +49,13 @@ void Window::add_layer(const char* sequence, uint32_t sequence_length, const cha
     positions_.emplace_back(begin, end);
 }
 
+void Window::add_layer(const char* sequence, uint32_t sequence_length, const char* quality, uint32_t quality_length,
+                       uint32_t begin, uint32_t end, const Origin& origin) {
+    const size_t before = sequences_.size();
+    add_layer(sequence, sequence_length, quality, quality_length, begin, end);
+    if (sequences_.size() > before && origins_.size() == before) origins_.push_back(origin);
+}
+
 std::atomic<uint32_t> BatchProcessor::batches{0};
 
 std::unique_ptr<BatchProcessor> createBatch(uint32_t max_window_depth, uint32_t device, size_t avail_mem, int8_t gap,
@@ -84,9 +91,23 @@ bool BatchProcessor::addWindow(std::shared_ptr<Window> window) {
         begin[i] = window->positions_[i].first;
         end[i] = window->positions_[i].second;
     }
-    rp_status s = rp_poa_add_window(poa_, static_cast<uint32_t>(n), seq.data(), len.data(), qual.data(), begin.data(),
-                                    end.data(), window->type_ == WindowType::kTGS ? RP_WINDOW_TGS : RP_WINDOW_NGS,
-                                    trim_ ? 1 : 0);
+    rp_status s;
+    if (reads_ != nullptr && window->origins_.size() == n) {
+        std::vector<uint32_t> id(n), offset(n);
+        std::vector<uint8_t> reverse(n);
+        for (size_t i = 0; i < n; ++i) {
+            id[i] = window->origins_[i].seq_id;
+            offset[i] = window->origins_[i].offset;
+            reverse[i] = window->origins_[i].reverse ? 1 : 0;
+        }
+        s = rp_poa_add_window_refs(poa_, reads_, static_cast<uint32_t>(n), id.data(), offset.data(), len.data(),
+                                   reverse.data(), begin.data(), end.data(),
+                                   window->type_ == WindowType::kTGS ? RP_WINDOW_TGS : RP_WINDOW_NGS, trim_ ? 1 : 0);
+    } else {
+        s = rp_poa_add_window(poa_, static_cast<uint32_t>(n), seq.data(), len.data(), qual.data(), begin.data(),
+                              end.data(), window->type_ == WindowType::kTGS ? RP_WINDOW_TGS : RP_WINDOW_NGS,
+                              trim_ ? 1 : 0);
+    }
     if (s == RP_BATCH_FULL) return false;
     if (s != RP_OK) {
         fprintf(stderr, "[racon_b200::BatchProcessor::addWindow] error: %s (%s)\n", rp_strerror(s), rp_last_error());
@@ -358,6 +379,7 @@ void Polisher::build_windows(const std::vector<Overlap>& overlaps) {
             const uint32_t length = std::min(j + window_length_, tgt.length) - j;
             windows_.emplace_back(createWindow(i, k, window_type_, tgt.data + j, length,
                                                tgt.quality ? tgt.quality + j : dummy_quality_.data(), length));
+            windows_.back()->set_backbone_origin(static_cast<uint32_t>(i), j);
         }
         id_to_first_window_id[i + 1] = id_to_first_window_id[i] + k;
     }
@@ -392,7 +414,8 @@ void Polisher::build_windows(const std::vector<Overlap>& overlaps) {
 
             windows_[window_id]->add_layer(data, data_length, layer_quality, quality_length,
                                            breaking_points[j].first - window_start,
-                                           breaking_points[j + 1].first - window_start - 1);
+                                           breaking_points[j + 1].first - window_start - 1,
+                                           Window::Origin{o.q_id, breaking_points[j].second, o.strand != 0});
         }
     }
 }
@@ -436,15 +459,39 @@ void Polisher::polish(std::vector<PolishedSequence>& dst, bool drop_unpolished_s
 }
 
 void Polisher::polish_streaming(const std::function<void(const PolishedSequence&)>& sink,
-                                bool drop_unpolished_sequences, size_t memory, bool banded) {
+                                bool drop_unpolished_sequences, size_t memory, bool banded, bool resident_reads) {
     constexpr int kObjects = 2;
     struct InFlight {
         std::unique_ptr<BatchProcessor> batch;
         size_t first = 0, count = 0;
         bool busy = false;
     };
-    InFlight obj[kObjects];
-    for (auto& o : obj) o.batch = createBatch(0, device_, memory, gap_, mismatch_, match_, banded, window_length_, trim_);
+    /* resident reads: every sequence goes to the device once; the windows (whose pieces know their origin, build_windows)
+     * are then added by reference and their layers extracted on the device */
+    struct StoreGuard {
+        rp_reads* reads = nullptr;
+        ~StoreGuard() { rp_reads_destroy(reads); }
+    } store;
+    if (resident_reads) {
+        std::vector<const char*> data(sequences_.size()), quality(sequences_.size());
+        std::vector<uint32_t> length(sequences_.size());
+        for (size_t i = 0; i < sequences_.size(); ++i) {
+            data[i] = sequences_[i].data;
+            quality[i] = sequences_[i].quality;
+            length[i] = sequences_[i].length;
+        }
+        const rp_status s = rp_reads_create(&store.reads, static_cast<int>(device_), static_cast<uint32_t>(data.size()),
+                                            data.data(), quality.data(), length.data());
+        if (s != RP_OK) {
+            fprintf(stderr, "[racon_b200::Polisher::polish_streaming] error: %s (%s)\n", rp_strerror(s), rp_last_error());
+            exit(1);
+        }
+    }
+    InFlight obj[kObjects];   // declared after the store: the batch objects go first
+    for (auto& o : obj) {
+        o.batch = createBatch(0, device_, memory, gap_, mismatch_, match_, banded, window_length_, trim_);
+        o.batch->useReadStore(store.reads);
+    }
     std::string polished_data;
     uint32_t num_polished_windows = 0;
     auto stitch = [&](size_t w, bool polished) {  // polisher.cpp:504-530, one window at a time, in window order
@@ -661,7 +708,7 @@ extern "C" uint64_t rp_mirror_polisher_polished(void* hv, uint32_t i, uint64_t* 
  * of the files the polisher was opened on); returns the
  * number of records written.  mem_bytes: budget per batch object (small budgets force many batches). */
 extern "C" uint32_t rp_mirror_polisher_stream_fasta(void* hv, int drop_unpolished, const char* path, const char* names,
-                                                     uint64_t mem_bytes, int banded) {
+                                                     uint64_t mem_bytes, int banded, int resident_reads) {
     PolHandle* h = static_cast<PolHandle*>(hv);
     std::vector<std::string> name_of;
     for (const char* p = names; p && *p; p += std::strlen(p) + 1) name_of.emplace_back(p);
@@ -677,7 +724,7 @@ extern "C" uint32_t rp_mirror_polisher_stream_fasta(void* hv, int drop_unpolishe
             std::fwrite(rec.data(), 1, rec.size(), f);
             ++n;
         },
-        drop_unpolished != 0, static_cast<size_t>(mem_bytes), banded != 0);
+        drop_unpolished != 0, static_cast<size_t>(mem_bytes), banded != 0, resident_reads != 0);
     std::fclose(f);
     return n;
 }

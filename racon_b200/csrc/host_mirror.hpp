@@ -17,6 +17,7 @@
 
 struct rp_poa;
 struct rp_aln;
+struct rp_reads;
 
 namespace racon_b200 {
 
@@ -41,6 +42,19 @@ public:
     void add_layer(const char* sequence, uint32_t sequence_length, const char* quality, uint32_t quality_length,
                    uint32_t begin, uint32_t end);
 
+    /* Where a piece comes from: sequence `seq_id` of the caller's sequence table from `offset` on — of its reverse
+     * complement when `reverse`.  A window whose backbone and every layer carry their origin can be handed to a batch by
+     * reference into a device-resident read store (BatchProcessor::useReadStore) instead of by its bytes. */
+    struct Origin {
+        uint32_t seq_id, offset;
+        bool reverse;
+    };
+    void set_backbone_origin(uint32_t seq_id, uint32_t offset) { origins_.assign(1, Origin{seq_id, offset, false}); }
+    /* add_layer + the layer's origin (the origin is dropped with the layer when add_layer skips it) */
+    void add_layer(const char* sequence, uint32_t sequence_length, const char* quality, uint32_t quality_length,
+                   uint32_t begin, uint32_t end, const Origin& origin);
+    const std::vector<Origin>& origins() const { return origins_; }
+
     friend std::shared_ptr<Window> createWindow(uint64_t id, uint32_t rank, WindowType type, const char* backbone,
                                                 uint32_t backbone_length, const char* quality,
                                                 uint32_t quality_length);
@@ -59,6 +73,7 @@ private:
     std::vector<std::pair<const char*, uint32_t>> sequences_;
     std::vector<std::pair<const char*, uint32_t>> qualities_;
     std::vector<std::pair<uint32_t, uint32_t>> positions_;
+    std::vector<Origin> origins_;   // empty, or one per entry of sequences_
 };
 
 class BatchProcessor;
@@ -82,6 +97,10 @@ public:
     const std::vector<bool>& collect();
     void reset();
     uint32_t getBatchID() const { return bid_; }
+    /* From now on windows that know the origin of all their pieces (Window::origins) are added by reference into
+     * `reads` (rp_reads_create over the same sequence table, same device): no sequence byte is copied on the host, the
+     * layers are extracted on the device.  nullptr switches back.  Call between batches (after reset()). */
+    void useReadStore(const rp_reads* reads) { reads_ = reads; }
     /* indices (within the batch) of the windows of the last generateConsensus() that hit a device limit (soft RP_WIN_*
      * status): their flag is false and their consensus is the backbone — not what racon would produce; the reference's
      * caller re-runs such windows on the CPU (cudapolisher.cpp:354-370), a caller without a CPU path must treat them as
@@ -100,6 +119,7 @@ private:
     static std::atomic<uint32_t> batches;
     uint32_t bid_ = 0;
     rp_poa* poa_ = nullptr;
+    const rp_reads* reads_ = nullptr;
     bool trim_ = true;
     std::vector<std::shared_ptr<Window>> windows_;
     std::vector<bool> window_consensus_status_;
@@ -191,9 +211,10 @@ public:
     /* Streaming form (polisher.cpp:504-537 + main.cpp:159-161 as a consumer overlapped with the compute): two batch
      * objects stay in flight; while one runs on the GPU the other's finished windows are stitched in window order, and
      * `sink` gets every polished sequence the moment its last window is collected (e.g. a FASTA writer).  `memory` =
-     * device budget per batch object (0 = library default), `banded` = racon -b. */
+     * device budget per batch object (0 = library default), `banded` = racon -b.  `resident_reads`: upload every sequence
+     * once (rp_reads) and add the windows by reference — layer extraction on the device, no host copy of layer bytes. */
     void polish_streaming(const std::function<void(const PolishedSequence&)>& sink, bool drop_unpolished_sequences,
-                          size_t memory = 0, bool banded = false);
+                          size_t memory = 0, bool banded = false, bool resident_reads = false);
     const std::vector<std::shared_ptr<Window>>& windows() const { return windows_; }
     /* Items the device could not finish (soft RP_ALN_* / RP_WIN_* status).  The reference hands such items to its CPU
      * code (cudapolisher.cpp:213 edlib, :354-370 spoa); this library has no CPU path, so a failed overlap contributes

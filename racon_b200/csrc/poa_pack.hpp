@@ -74,6 +74,12 @@ struct PackedBatch {
     GrowBuf<uint8_t> bases, weights, seq_flags, win_flags;
     GrowBuf<uint32_t> seq_off, seq_begin, seq_end, win_first, out_off, out_cap, queue;
     GrowBuf<uint64_t> win_alpha;
+    /* by-reference batches (layers named as slices of a device-resident read store, rp_reads): instead of bases and
+     * weights, per packed sequence the store position of the byte that becomes its first base and how to read it */
+    GrowBuf<uint64_t> src_pos;
+    GrowBuf<uint8_t> src_flags;            // kSrcReverse | kSrcHasQuality | kSrcBackbone
+    bool by_ref = false;
+    uint64_t n_bases = 0;                  // bases of all packed sequences (== bases.size unless by_ref)
     /* host-only bookkeeping, one entry per ADDED window (in add order) */
     std::vector<int32_t> gpu_index;        // index among GPU windows, or -1 (trivial), -2 (alphabet limit)
     std::vector<std::string> trivial;      // consensus of trivial windows (backbone copy), indexed by added order
@@ -87,7 +93,7 @@ struct PackedBatch {
 
     explicit PackedBatch(const HostAllocator* a)
         : bases(a), weights(a), seq_flags(a), win_flags(a), seq_off(a), seq_begin(a), seq_end(a), win_first(a),
-          out_off(a), out_cap(a), queue(a), win_alpha(a) {
+          out_off(a), out_cap(a), queue(a), win_alpha(a), src_pos(a), src_flags(a) {
         reset();
     }
 
@@ -95,6 +101,9 @@ struct PackedBatch {
         bases.clear(); weights.clear(); seq_flags.clear(); win_flags.clear();
         seq_off.clear(); seq_begin.clear(); seq_end.clear(); win_first.clear();
         out_off.clear(); out_cap.clear(); queue.clear(); win_alpha.clear();
+        src_pos.clear(); src_flags.clear();
+        by_ref = false;
+        n_bases = 0;
         seq_off.push(0);
         win_first.push(0);
         gpu_index.clear();
@@ -123,7 +132,25 @@ struct PackedBatch {
     static void prepare(Prep& pr, uint32_t n_seq, const char* const* seq, const uint32_t* len, const uint32_t* begin,
                         const uint32_t* end, uint32_t max_seq_len) {
         pr = Prep();
-        if (n_seq == 0 || !seq || !len || !seq[0] || len[0] == 0 || len[0] > max_seq_len) {  // window.cpp:19-23
+        if (!seq) {
+            pr.status = kPackInvalid;
+            return;
+        }
+        prepare_layout(pr, n_seq, seq, len, begin, end, max_seq_len);
+        if (pr.status != kPackOk || pr.kind != 0) return;
+        /* alphabet: the distinct characters of the window (any order: only equality matters on the device) */
+        uint8_t seen[256];
+        std::memset(seen, 0, sizeof(seen));
+        for (uint32_t i = 0; i < pr.order.size(); ++i)
+            scan_alphabet(reinterpret_cast<const uint8_t*>(seq[pr.order[i]]), len[pr.order[i]], seen);
+        alphabet_from_seen(pr, seen);
+    }
+
+    /* validation, skipped layers, layer order, full-span flags — everything of prepare() that does not look at the bases.
+     * seq may be NULL (by-reference windows): then no per-sequence pointer is checked. */
+    static void prepare_layout(Prep& pr, uint32_t n_seq, const char* const* seq, const uint32_t* len,
+                               const uint32_t* begin, const uint32_t* end, uint32_t max_seq_len) {
+        if (n_seq == 0 || !len || (seq && !seq[0]) || len[0] == 0 || len[0] > max_seq_len) {  // window.cpp:19-23
             pr.status = kPackInvalid;
             return;
         }
@@ -136,7 +163,7 @@ struct PackedBatch {
         uint64_t tot = blen;
         for (uint32_t k = 1; k < n_seq; ++k) {
             if (len[k] == 0 || begin[k] == end[k]) continue;
-            if (!seq[k] || begin[k] >= end[k] || begin[k] > blen || end[k] > blen || len[k] > max_seq_len) {
+            if ((seq && !seq[k]) || begin[k] >= end[k] || begin[k] > blen || end[k] > blen || len[k] > max_seq_len) {
                 pr.status = kPackInvalid;
                 return;
             }
@@ -166,11 +193,9 @@ struct PackedBatch {
             pr.order[i] = k;
             pr.full[i] = full ? 1 : 0;
         }
-        /* alphabet: the distinct characters of the window (any order: only equality matters on the device) */
-        uint8_t seen[256];
-        std::memset(seen, 0, sizeof(seen));
-        for (uint32_t i = 0; i < pr.order.size(); ++i)
-            scan_alphabet(reinterpret_cast<const uint8_t*>(seq[pr.order[i]]), len[pr.order[i]], seen);
+    }
+
+    static void alphabet_from_seen(Prep& pr, const uint8_t* seen) {
         if (seen[0]) {
             pr.status = kPackInvalid;
             return;
@@ -226,21 +251,25 @@ struct PackedBatch {
         const uint32_t cap = 2 * pr.blen + 64;
         /* the batch limits (memory budget, uint32 offsets) make a batch FULL; an empty batch takes any window so
          * that the caller's add-until-full loop always makes progress (cudabatch.cpp:126-132) */
-        if (n_gpu() > 0 && (bases.size + pr.tot > max_bases || n_gpu() >= max_windows || out_total + cap > max_out))
+        if (n_gpu() > 0 && (n_bases + pr.tot > max_bases || n_gpu() >= max_windows || out_total + cap > max_out))
             return kPackFull;
-        if (bases.size + pr.tot > 0xfff00000ull || out_total + cap > 0xfff00000ull) return kPackFull;
+        if (n_bases + pr.tot > 0xfff00000ull || out_total + cap > 0xfff00000ull) return kPackFull;
         /* reserve everything first: a failed allocation must leave the batch as it was */
         const size_t ns = pr.order.size();
-        if (!bases.reserve(bases.size + pr.tot) || !weights.reserve(weights.size + pr.tot) ||
+        if ((!by_ref && (!bases.reserve(bases.size + pr.tot) || !weights.reserve(weights.size + pr.tot))) ||
+            (by_ref && (!src_pos.reserve(src_pos.size + ns) || !src_flags.reserve(src_flags.size + ns))) ||
             !seq_off.reserve(seq_off.size + ns) || !seq_begin.reserve(seq_begin.size + ns) ||
             !seq_end.reserve(seq_end.size + ns) || !seq_flags.reserve(seq_flags.size + ns) ||
             !win_first.reserve(win_first.size + 1) || !win_flags.reserve(win_flags.size + 1) ||
             !win_alpha.reserve(win_alpha.size + 1) || !out_off.reserve(out_off.size + 1) ||
             !out_cap.reserve(out_cap.size + 1))
             return kPackNoMem;
-        pr.base_off = bases.size;
-        bases.extend(pr.tot);
-        weights.extend(pr.tot);
+        pr.base_off = n_bases;
+        n_bases += pr.tot;
+        if (!by_ref) {
+            bases.extend(pr.tot);
+            weights.extend(pr.tot);
+        }
         uint32_t off = seq_off.data[seq_off.size - 1];
         for (uint32_t i = 0; i < ns; ++i) {
             uint32_t k = pr.order[i];

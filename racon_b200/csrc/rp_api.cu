@@ -6,18 +6,24 @@
  * POA batch object = racon::CUDABatchProcessor + cudapoa::Batch (src/cuda/cudabatch.cpp:23-278):
  *   add (copy into pinned staging) -> upload (H2D) -> launch (one persistent kernel) -> download (D2H).
  */
+#if defined(RP_HOST_SIM)
+#include "cuda_sim_runtime.h"   // TEST-ONLY build of this file (lib/simapi): see that header
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <array>
 #include <functional>
 #include <new>
 #include <string>
 #include <thread>
 #include <vector>
 
+#include "gather_core.cuh"
 #include "myers_core.cuh"
 #include "poa_core.cuh"
 #include "poa_pack.hpp"
@@ -75,6 +81,69 @@ constexpr uint32_t kBandPaysFromWindowLength = 768;   // rows of two or more 512
  * windows from an atomic queue — 32/G windows in flight per warp, advancing together wherever their control
  * flow agrees.  Compiled for several group widths and occupancy points (blocks per SM -> register cap);
  * RP_POA_GROUP / RP_BLOCKS_PER_SM select one (defaults in rp_poa_create). */
+#if defined(RP_HOST_SIM)
+/* TEST-ONLY stand-ins of the two kernels (cuda_sim_runtime.h): the same per-window / per-overlap device functions, run as
+ * cooperative fibres, the queue walked by one worker after the other. */
+struct SimLaunch {
+    uint32_t blocks, threads;
+};
+template <int G, int KB>
+struct SimPoaJob {
+    const rp::PoaParams* P;
+    uint32_t w;
+    uint8_t *slot, *smem;
+    static void entry(void* arg) {
+        SimPoaJob* j = static_cast<SimPoaJob*>(arg);
+        rp::poa_window<G, KB>(*j->P, j->w, j->slot, j->smem);
+    }
+};
+template <int G, int KB, int kBlocksPerSm>
+void rp_poa_kernel(rp::PoaParams P, SimLaunch L) {
+    const uint32_t workers = L.blocks * (L.threads / G);
+    std::vector<uint8_t> smem(P.smem_per_group + 64);
+    uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem.data()) + 15) & ~uintptr_t(15));
+    for (;;) {
+        const uint32_t q = (*P.queue_head)++;
+        if (q >= P.n_windows) break;
+        SimPoaJob<G, KB> job{&P, P.queue[q], P.scratch + static_cast<uint64_t>(q % workers) * P.lay.bytes, smem_al};
+        rp::sim::run_warp(SimPoaJob<G, KB>::entry, &job, 256 * 1024, G);
+    }
+}
+typedef void (*PoaKernel)(rp::PoaParams, SimLaunch);
+struct SimGatherJob {
+    const rp::GatherParams* P;
+    uint32_t s;
+    static void entry(void* arg) {
+        SimGatherJob* j = static_cast<SimGatherJob*>(arg);
+        rp::gather_sequence(*j->P, j->s);
+    }
+};
+void rp_gather_kernel(rp::GatherParams P, SimLaunch) {
+    for (uint32_t s = 0; s < P.n_seqs; ++s) {
+        SimGatherJob job{&P, s};
+        rp::sim::run_warp(SimGatherJob::entry, &job);
+    }
+}
+struct SimAlnJob {
+    const rp::AlnParams* P;
+    uint32_t pair;
+    uint8_t* slot;
+    static void entry(void* arg) {
+        SimAlnJob* j = static_cast<SimAlnJob*>(arg);
+        rp::aln_pair(*j->P, j->pair, j->slot);
+    }
+};
+template <int kBlocksPerSm>
+void rp_aln_kernel(rp::AlnParams P, SimLaunch L) {
+    const uint32_t workers = L.blocks * (L.threads / 32);
+    for (;;) {
+        const uint32_t q = (*P.queue_head)++;
+        if (q >= P.n_pairs) break;
+        SimAlnJob job{&P, P.queue[q], P.scratch + static_cast<uint64_t>(q % workers) * P.lay.bytes};
+        rp::sim::run_warp(SimAlnJob::entry, &job);
+    }
+}
+#else
 template <int G, int KB, int kBlocksPerSm>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kernel(rp::PoaParams P) {
     extern __shared__ __align__(16) uint8_t smem_all[];
@@ -92,6 +161,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kern
 }
 
 typedef void (*PoaKernel)(rp::PoaParams);
+#endif
 /* lanes per window x columns per lane of a banded row x blocks per SM (register cap) */
 template <int G, int KB>
 PoaKernel pick_kernel_g(int blocks_per_sm) {
@@ -121,6 +191,14 @@ PoaKernel pick_kernel(int group, int band_k, int blocks_per_sm) {
     }
 }
 
+#if !defined(RP_HOST_SIM)
+/* layer extraction (gather_core.cuh): warps stride over the packed sequences of the batch */
+__global__ void __launch_bounds__(256) rp_gather_kernel(rp::GatherParams P) {
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < P.n_seqs; s += warps)
+        rp::gather_sequence(P, s);
+}
+
 template <int kBlocksPerSm>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_aln_kernel(rp::AlnParams P) {
     const int warp = threadIdx.x >> 5;
@@ -134,6 +212,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_aln_kern
         rp::aln_pair(P, P.queue[q], slot);
     }
 }
+#endif
 
 }  // namespace
 
@@ -170,6 +249,17 @@ struct rp_aln {
     }
 };
 
+/* device-resident sequences (include/racon_b200.h: rp_reads_create) */
+struct rp_reads {
+    int device = 0;
+    std::vector<const char*> data, quality;       // the caller's host arrays (kept valid by the caller)
+    std::vector<uint32_t> length;
+    std::vector<uint64_t> off;                    // position of each sequence in the device arrays, n + 1
+    std::vector<std::array<uint64_t, 4>> chars;   // per sequence: which byte values occur (256-bit set)
+    DevBuf d_bases, d_quals;
+    bool any_quality = false;
+};
+
 struct rp_poa {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -202,6 +292,10 @@ struct rp_poa {
     bool band_counted = true;   // alignments tried in the band / redone with the full matrix (last launch)
     /* escalation pass for windows that exceeded a device limit (never a CPU re-run) */
     DevBuf d_scratch_big, d_queue_big;
+    /* by-reference batches: the store the current batch's windows point into, and the device copy of the descriptors */
+    const rp_reads* reads = nullptr;
+    DevBuf d_src_pos, d_src_flags;
+    uint64_t gather_launches = 0;
     rp::PoaLimits lim_big;
     rp::SlotLayout lay_big;
     uint32_t workers_big = 0;
@@ -416,7 +510,7 @@ void rp_poa_destroy(rp_poa* p) {
     DevBuf* bufs[] = {&p->d_bases, &p->d_weights, &p->d_seq_flags, &p->d_win_flags, &p->d_seq_off, &p->d_seq_begin,
                       &p->d_seq_end, &p->d_win_first, &p->d_out_off, &p->d_out_cap, &p->d_queue, &p->d_win_alpha,
                       &p->d_cons, &p->d_cov, &p->d_len, &p->d_status, &p->d_head, &p->d_stats, &p->d_scratch,
-                      &p->d_scratch_big, &p->d_queue_big};
+                      &p->d_scratch_big, &p->d_queue_big, &p->d_src_pos, &p->d_src_flags};
     for (DevBuf* b : bufs) b->release();
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -447,7 +541,207 @@ rp_status rp_poa_add_window(rp_poa* p, uint32_t n_seq, const char* const* seq, c
                             int trim) {
     if (!p) return fail(RP_ERR_INVALID, "null object");
     if (p->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
+    if (p->batch.by_ref) return fail(RP_ERR_STATE, "this batch holds windows added by reference; reset first");
     return map_pack(p->batch.add(n_seq, seq, len, qual, begin, end, window_type, trim));
+}
+
+rp_status rp_reads_create(rp_reads** out, int device, uint32_t n_seqs, const char* const* data,
+                          const char* const* quality, const uint32_t* length) {
+    if (!out) return fail(RP_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (!data || !length) return fail(RP_ERR_INVALID, "null argument");
+    int ndev = rp_device_count();
+    if (ndev <= 0) return fail(RP_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RP_ERR_INVALID, "device index out of range");
+    RP_CUDA(cudaSetDevice(device));
+    rp_reads* r = new (std::nothrow) rp_reads();
+    if (!r) return fail(RP_ERR_NOMEM, "host allocation failed");
+    r->device = device;
+    r->data.assign(data, data + n_seqs);
+    r->quality.assign(n_seqs, nullptr);
+    r->length.assign(length, length + n_seqs);
+    r->off.assign(n_seqs + 1, 0);
+    r->chars.assign(n_seqs, std::array<uint64_t, 4>{0, 0, 0, 0});
+    for (uint32_t i = 0; i < n_seqs; ++i) {
+        if (length[i] && !data[i]) {
+            delete r;
+            return fail(RP_ERR_INVALID, "null sequence");
+        }
+        if (quality && quality[i] && length[i]) {
+            r->quality[i] = quality[i];
+            r->any_quality = true;
+        }
+        r->off[i + 1] = r->off[i] + length[i];
+        uint8_t seen[256];
+        std::memset(seen, 0, sizeof(seen));
+        rp::PackedBatch::scan_alphabet(reinterpret_cast<const uint8_t*>(data[i]), length[i], seen);
+        if (seen[0]) {
+            delete r;
+            return fail(RP_ERR_INVALID, "NUL byte in a sequence");
+        }
+        for (uint32_t c = 1; c < 256; ++c)
+            if (seen[c]) r->chars[i][c >> 6] |= 1ull << (c & 63);
+    }
+    const uint64_t total = r->off[n_seqs];
+    cudaError_t e = r->d_bases.reserve(total + 16);
+    if (e == cudaSuccess && r->any_quality) e = r->d_quals.reserve(total + 16);
+    /* the caller's sequences are separate pageable strings: stage them through pinned memory in large pieces */
+    const size_t stage_bytes = static_cast<size_t>(std::min<uint64_t>(std::max<uint64_t>(total, 1), 64ull << 20));
+    void* stage = nullptr;
+    if (e == cudaSuccess) e = cudaHostAlloc(&stage, stage_bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        r->d_bases.release();
+        r->d_quals.release();
+        delete r;
+        return fail(RP_ERR_NOMEM, std::string("read store allocation: ") + cudaGetErrorString(e));
+    }
+    cudaStream_t st = nullptr;
+    e = cudaStreamCreate(&st);
+    for (int pass = 0; pass < 2 && e == cudaSuccess; ++pass) {
+        if (pass == 1 && !r->any_quality) break;
+        uint8_t* dst = static_cast<uint8_t*>(pass == 0 ? r->d_bases.p : r->d_quals.p);
+        uint64_t flushed = 0, filled = 0;   // device positions: [flushed, filled) sits in the staging buffer
+        auto flush = [&]() {
+            if (filled > flushed) {
+                e = cudaMemcpyAsync(dst + flushed, stage, filled - flushed, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            }
+            flushed = filled;
+        };
+        for (uint32_t i = 0; i < n_seqs && e == cudaSuccess; ++i) {
+            const char* src = pass == 0 ? r->data[i] : r->quality[i];
+            uint64_t done = 0;
+            while (done < length[i] && e == cudaSuccess) {
+                if (filled - flushed == stage_bytes) flush();
+                const uint64_t n = std::min<uint64_t>(length[i] - done, stage_bytes - (filled - flushed));
+                if (src) {
+                    std::memcpy(static_cast<uint8_t*>(stage) + (filled - flushed), src + done, n);
+                } else {
+                    std::memset(static_cast<uint8_t*>(stage) + (filled - flushed), '!', n);
+                }
+                filled += n;
+                done += n;
+            }
+        }
+        if (e == cudaSuccess) flush();
+    }
+    if (st) cudaStreamDestroy(st);
+    cudaFreeHost(stage);
+    if (e != cudaSuccess) {
+        r->d_bases.release();
+        r->d_quals.release();
+        delete r;
+        return fail(RP_ERR_CUDA, std::string("read store upload: ") + cudaGetErrorString(e));
+    }
+    *out = r;
+    return RP_OK;
+}
+
+void rp_reads_destroy(rp_reads* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    r->d_bases.release();
+    r->d_quals.release();
+    delete r;
+}
+
+uint64_t rp_reads_bytes(const rp_reads* r) { return r ? r->d_bases.cap + r->d_quals.cap : 0; }
+
+rp_status rp_poa_add_window_refs(rp_poa* p, const rp_reads* reads, uint32_t n_seq, const uint32_t* seq_id,
+                                 const uint32_t* offset, const uint32_t* length, const uint8_t* reverse,
+                                 const uint32_t* begin, const uint32_t* end, int window_type, int trim) {
+    if (!p || !reads || !seq_id || !offset || !length || !begin || !end) return fail(RP_ERR_INVALID, "null argument");
+    if (p->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
+    if (reads->device != p->device) return fail(RP_ERR_INVALID, "the read store lives on another device");
+    rp::PackedBatch& b = p->batch;
+    if (b.n_added() > 0 && (!b.by_ref || p->reads != reads))
+        return fail(RP_ERR_STATE, "a batch holds windows added by pointer or by reference into ONE store; reset first");
+    if (n_seq == 0) return fail(RP_ERR_INVALID, "malformed window (see Window::add_layer checks, window.cpp:42-63)");
+    const uint32_t n_store = static_cast<uint32_t>(reads->length.size());
+    for (uint32_t k = 0; k < n_seq; ++k) {
+        if (seq_id[k] >= n_store || static_cast<uint64_t>(offset[k]) + length[k] > reads->length[seq_id[k]])
+            return fail(RP_ERR_INVALID, "window piece outside its sequence");
+    }
+    if (reverse && reverse[0]) return fail(RP_ERR_INVALID, "the backbone cannot be a reverse-complement piece");
+    rp::PackedBatch::Prep pr;
+    rp::PackedBatch::prepare_layout(pr, n_seq, nullptr, length, begin, end, b.max_seq_len);
+    if (pr.status == rp::kPackOk && pr.kind == 0) {
+        /* alphabet: union of the characters of the pieces' sequences (a superset of the window's own, which only matters
+         * when it has more than the 8 codes the device holds: then the pieces themselves are scanned) */
+        std::array<uint64_t, 4> set{0, 0, 0, 0};
+        auto swap_bits = [](std::array<uint64_t, 4>& m, uint8_t a, uint8_t c) {
+            const bool ha = m[a >> 6] >> (a & 63) & 1, hc = m[c >> 6] >> (c & 63) & 1;
+            if (ha != hc) {
+                m[a >> 6] ^= 1ull << (a & 63);
+                m[c >> 6] ^= 1ull << (c & 63);
+            }
+        };
+        for (uint32_t k : pr.order) {
+            std::array<uint64_t, 4> m = reads->chars[seq_id[k]];
+            if (reverse && reverse[k]) {
+                swap_bits(m, 'A', 'T');
+                swap_bits(m, 'C', 'G');
+            }
+            for (int i = 0; i < 4; ++i) set[i] |= m[i];
+        }
+        uint8_t seen[256];
+        int distinct = 0;
+        for (uint32_t c = 0; c < 256; ++c) distinct += seen[c] = set[c >> 6] >> (c & 63) & 1;
+        if (distinct > 8) {
+            std::memset(seen, 0, sizeof(seen));
+            for (uint32_t k : pr.order) {
+                const uint32_t len_k = reads->length[seq_id[k]];
+                const bool rev = reverse && reverse[k];
+                const uint8_t* piece = reinterpret_cast<const uint8_t*>(reads->data[seq_id[k]]) +
+                                       (rev ? len_k - offset[k] - length[k] : offset[k]);
+                uint8_t local[256];
+                std::memset(local, 0, sizeof(local));
+                rp::PackedBatch::scan_alphabet(piece, length[k], local);
+                for (uint32_t c = 0; c < 256; ++c)
+                    if (local[c]) seen[rev ? rp::complement_base(static_cast<uint8_t>(c)) : c] = 1;
+            }
+        }
+        rp::PackedBatch::alphabet_from_seen(pr, seen);
+    }
+    const bool was_empty = b.n_added() == 0;
+    if (was_empty) b.by_ref = true;
+    const char* backbone = reads->data[seq_id[0]] + offset[0];
+    const int rc = b.commit(pr, &backbone, length, begin, end, window_type, trim);
+    if (rc != rp::kPackOk) {
+        if (was_empty) b.by_ref = false;
+        return map_pack(rc);
+    }
+    p->reads = reads;
+    if (pr.kind == 0) {
+        for (size_t i = 0; i < pr.order.size(); ++i) {
+            const uint32_t k = pr.order[i];
+            const uint32_t id = seq_id[k];
+            const bool rev = reverse && reverse[k];
+            b.src_pos.push(reads->off[id] + (rev ? reads->length[id] - 1 - offset[k] : offset[k]));
+            b.src_flags.push(static_cast<uint8_t>((rev ? rp::kSrcReverse : 0) | (reads->quality[id] ? rp::kSrcHasQuality : 0) |
+                                                  (i == 0 ? rp::kSrcBackbone : 0)));
+        }
+    }
+    return RP_OK;
+}
+
+rp_status rp_poa_add_window_set_refs(rp_poa* p, const rp_reads* reads, uint32_t first, uint32_t count,
+                                     const uint32_t* seq_id, const uint32_t* offset, const uint32_t* length,
+                                     const uint8_t* reverse, const uint32_t* begin, const uint32_t* end,
+                                     const uint32_t* win_first, const uint8_t* win_type, int trim, uint32_t* added) {
+    if (!win_first || !seq_id || !offset || !length || !begin || !end) return fail(RP_ERR_INVALID, "null argument");
+    if (added) *added = 0;
+    uint32_t n = 0;
+    rp_status st = RP_OK;
+    for (; n < count; ++n) {
+        const uint32_t s0 = win_first[first + n], s1 = win_first[first + n + 1];
+        st = rp_poa_add_window_refs(p, reads, s1 - s0, seq_id + s0, offset + s0, length + s0, reverse ? reverse + s0 : nullptr,
+                                    begin + s0, end + s0, win_type ? win_type[first + n] : 1, trim);
+        if (st != RP_OK) break;
+    }
+    if (added) *added = n;
+    return st == RP_BATCH_FULL && n > 0 ? RP_OK : st;
 }
 
 rp_status rp_poa_add_window_set(rp_poa* p, uint32_t first, uint32_t count, const char* bases, const char* quals,
@@ -457,6 +751,7 @@ rp_status rp_poa_add_window_set(rp_poa* p, uint32_t first, uint32_t count, const
     if (!p || !bases || !seq_off || !win_first || !seq_begin || !seq_end)
         return fail(RP_ERR_INVALID, "null argument");
     if (p->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
+    if (p->batch.by_ref) return fail(RP_ERR_STATE, "this batch holds windows added by reference; reset first");
     if (added) *added = 0;
     if (count == 0) return RP_OK;
     /* per-window pointer tables (the flat set stores offsets) */
@@ -545,8 +840,15 @@ rp_status rp_poa_upload(rp_poa* p) {
         h2d += bytes;
         return bytes ? cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, p->stream) : cudaSuccess;
     };
-    RP_CUDA(up(p->d_bases, b.bases.data, b.bases.bytes()));
-    RP_CUDA(up(p->d_weights, b.weights.data, b.weights.bytes()));
+    if (b.by_ref) {
+        RP_CUDA(p->d_bases.reserve(b.n_bases + 16));
+        RP_CUDA(p->d_weights.reserve(b.n_bases + 16));
+        RP_CUDA(up(p->d_src_pos, b.src_pos.data, b.src_pos.bytes()));
+        RP_CUDA(up(p->d_src_flags, b.src_flags.data, b.src_flags.bytes()));
+    } else {
+        RP_CUDA(up(p->d_bases, b.bases.data, b.bases.bytes()));
+        RP_CUDA(up(p->d_weights, b.weights.data, b.weights.bytes()));
+    }
     RP_CUDA(up(p->d_seq_off, b.seq_off.data, b.seq_off.bytes()));
     RP_CUDA(up(p->d_seq_begin, b.seq_begin.data, b.seq_begin.bytes()));
     RP_CUDA(up(p->d_seq_end, b.seq_end.data, b.seq_end.bytes()));
@@ -585,6 +887,27 @@ rp_status rp_poa_upload(rp_poa* p) {
     P.status = static_cast<uint32_t*>(p->d_status.p);
     P.stats = p->counters ? static_cast<uint64_t*>(p->d_stats.p) : nullptr;
     P.scratch = static_cast<uint8_t*>(p->d_scratch.p);
+    if (b.by_ref && b.src_pos.size > 0) {
+        /* layer extraction on the device: fills d_bases / d_weights from the store, on this object's stream, ahead of the
+         * POA kernel */
+        rp::GatherParams G;
+        G.store_bases = static_cast<const uint8_t*>(p->reads->d_bases.p);
+        G.store_quals = static_cast<const uint8_t*>(p->reads->d_quals.p);
+        G.bases = static_cast<uint8_t*>(p->d_bases.p);
+        G.weights = static_cast<uint8_t*>(p->d_weights.p);
+        G.seq_off = P.seq_off;
+        G.src_pos = static_cast<const uint64_t*>(p->d_src_pos.p);
+        G.src_flags = static_cast<const uint8_t*>(p->d_src_flags.p);
+        G.n_seqs = static_cast<uint32_t>(b.src_pos.size);
+#if defined(RP_HOST_SIM)
+        rp_gather_kernel(G, SimLaunch{1, 256});
+#else
+        const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(148 * 8, (G.n_seqs + 7) / 8));
+        rp_gather_kernel<<<blocks, 256, 0, p->stream>>>(G);
+        RP_CUDA(cudaGetLastError());
+#endif
+        p->gather_launches += 1;
+    }
     p->last_h2d = h2d;
     p->uploaded = true;
     p->launched = p->downloaded = p->synced = false;
@@ -602,7 +925,11 @@ rp_status rp_poa_launch(rp_poa* p) {
         p->P.band_stats = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(p->d_stats.p) + 128);
         const uint32_t need_blocks = (p->P.n_windows + p->groups_per_block - 1) / p->groups_per_block;
         const uint32_t blocks = std::min<uint32_t>(static_cast<uint32_t>(p->grid), need_blocks);
+#if defined(RP_HOST_SIM)
+        p->kernel(p->P, SimLaunch{blocks, kWarpsPerBlock * 32});
+#else
         p->kernel<<<blocks, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(p->P);
+#endif
         RP_CUDA(cudaGetLastError());
         p->launches += 1;
     }
@@ -685,7 +1012,11 @@ static rp_status escalate(rp_poa* p) {
     P.band_stats = nullptr;
     uint32_t blocks = std::min<uint32_t>(p->workers_big / p->groups_per_block,
                                          (static_cast<uint32_t>(redo.size()) + p->groups_per_block - 1) / p->groups_per_block);
+#if defined(RP_HOST_SIM)
+    p->kernel(P, SimLaunch{blocks, kWarpsPerBlock * 32});
+#else
     p->kernel<<<blocks, kWarpsPerBlock * 32, p->smem_block, p->stream>>>(P);
+#endif
     RP_CUDA(cudaGetLastError());
     p->launches += 1;
     p->escalated += redo.size();
@@ -1033,12 +1364,16 @@ rp_status rp_aln_launch(rp_aln* a) {
     RP_CUDA(cudaSetDevice(a->device));
     if (a->P.n_pairs > 0) {
         RP_CUDA(cudaMemsetAsync(a->d_head.p, 0, 4, a->stream));
+#if defined(RP_HOST_SIM)
+        rp_aln_kernel<4>(a->P, SimLaunch{static_cast<uint32_t>(a->grid), kWarpsPerBlock * 32});
+#else
         if (a->blocks_per_sm == 8)
             rp_aln_kernel<8><<<a->grid, kWarpsPerBlock * 32, 0, a->stream>>>(a->P);
         else if (a->blocks_per_sm == 6)
             rp_aln_kernel<6><<<a->grid, kWarpsPerBlock * 32, 0, a->stream>>>(a->P);
         else
             rp_aln_kernel<4><<<a->grid, kWarpsPerBlock * 32, 0, a->stream>>>(a->P);
+#endif
         RP_CUDA(cudaGetLastError());
         a->launches += 1;
     }

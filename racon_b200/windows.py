@@ -180,6 +180,19 @@ def slice_windows(ws, lo, hi):
                      win_type=ws.win_type[lo:hi].copy())
 
 
+def as_refs(ws):
+    """The window set described by reference (api.PoaBatch.add_window_set_refs) into a read store built over its own
+    arrays (api.ReadStore.from_flat(ws.bases, ws.seq_off, ws.quals, ws.seq_has_qual)): sequence s of the set is
+    sequence s of the store, taken whole and forward."""
+    n = ws.n_seqs
+    return dict(seq_id=np.arange(n, dtype=np.uint32), offset=np.zeros(n, np.uint32),
+                length=np.ascontiguousarray(np.diff(ws.seq_off.astype(np.int64)).astype(np.uint32)),
+                reverse=np.zeros(n, np.uint8), begin=np.ascontiguousarray(ws.seq_begin, dtype=np.uint32),
+                end=np.ascontiguousarray(ws.seq_end, dtype=np.uint32),
+                win_first=np.ascontiguousarray(ws.win_first, dtype=np.uint32),
+                win_type=np.ascontiguousarray(ws.win_type, dtype=np.uint8))
+
+
 def fnv1a64(chunks):
     lib = _synth_lib()
     h = 1469598103934665603

@@ -50,6 +50,27 @@ def test_files_to_polished_fasta_equals_the_reference(case, tmp_path):
     assert names == g[case + "/polished_names"].tobytes().decode().split("\n")
 
 
+@pytest.mark.parametrize("case", ["fastq_sam", "fasta_paf", "frag_fastq_paf"])
+def test_files_to_polished_fasta_with_resident_reads(case, tmp_path):
+    """The same run with every sequence uploaded once and the windows added by reference (layers
+    extracted on the device, reverse complements and weights included): the reference's bytes again."""
+    g = np.load(GOLD)
+    reads, overlaps, target, frag, e = CASES[case]
+    pol = api.MirrorPolisher.from_files(os.path.join(DATA, reads), os.path.join(DATA, overlaps), os.path.join(DATA, target),
+                                        fragment_correction=frag, error_threshold=e)
+    try:
+        out = str(tmp_path / "polished.fasta")
+        n = pol.stream_fasta(out, None, drop_unpolished=False, resident_reads=True, mem_bytes=256 << 20)
+        assert pol.failed() == (0, 0)
+    finally:
+        pol.close()
+    names, seqs = _records(out)
+    count, bases = (int(x) for x in g[case + "/polished"])
+    assert n == count == len(seqs) and sum(len(s) for s in seqs) == bases
+    assert hashlib.md5(b"".join(seqs)).hexdigest() == g[case + "/polished_md5"].tobytes().decode()
+    assert names == g[case + "/polished_names"].tobytes().decode().split("\n")
+
+
 def test_polish_files_drops_unpolished_like_the_cli(tmp_path):
     """api.polish_files = the racon command line's default (unpolished sequences dropped): the lambda sample gives the
     one polished contig of the reference's CPU run (md5 of `racon` stdout: b0e2a2788440a4982e544e2e9b3bf378)."""
