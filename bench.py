@@ -400,7 +400,12 @@ def main():
     n_total = meta.get("windows_total", n * world)
     mem = int(os.environ.get("RP_BENCH_MEM", 40e9))     # device-memory budget per batch object (several are alive)
     if args.internal_by_reference:
-        print(json.dumps(by_reference_leg(args, api, windows, torch, ws, local, wl, banded, mem)))
+        res = by_reference_leg(args, api, windows, torch, ws, local, wl, banded, mem, dist if distributed else None, n_total)
+        if rank == 0:
+            res["host_cpu_binding"] = host_binding
+            print(json.dumps(res))
+        if distributed:
+            dist.destroy_process_group()
         return
 
     def new_batch():
@@ -644,8 +649,8 @@ def main():
                     "value_default_isolated": n / (kern_avg_ms * 1e-3) * (n_total / n)}}
         if aligner:
             line["aligner"] = aligner
-        if world == 1 and cfg["shape"] != "frag" and not os.environ.get("RP_BENCH_NO_BY_REFERENCE"):
-            br = by_reference(args)
+        if cfg["shape"] != "frag" and not os.environ.get("RP_BENCH_NO_BY_REFERENCE"):
+            br = by_reference(args, world)
             if "consensus_fnv_first200" in br:
                 br["same_consensus_as_by_pointer"] = br["consensus_fnv_first200"] == checksum
             line["e2e"]["by_reference"] = br
@@ -665,21 +670,36 @@ def main():
         dist.destroy_process_group()
 
 
-def by_reference(args):
+def by_reference(args, world):
     """The end-to-end arm once more with the windows added BY REFERENCE into a device-resident read store (SURVEY §8 f2;
     rp_reads_create + rp_poa_add_window_set_refs): the sequences are uploaded once, before the timed region — in a racon run
     every read belongs to the run, not to a batch —, a step then moves descriptors only and the layers are extracted on the
     device.  Reported beside `e2e`, which stays the by-pointer call of the reference's own interface.  Own process with a
     time limit, like the reference's GPU path: the newest code path must not be able to take the bench line down."""
     here = os.path.dirname(os.path.abspath(__file__))
-    cmd = [sys.executable, os.path.join(here, "bench.py"), "--internal-by-reference", "--config", str(args.config),
-           "--steps", str(args.steps), "--warmup", str(args.warmup), "--e2e-batches", str(args.e2e_batches)]
+    cmd = [sys.executable]
+    env = dict(os.environ)
+    if world > 1:
+        # the same ranks once more, as a job of its own: one process per GPU under torchrun, on another port
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        for key in list(env):
+            if key in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE",
+                       "MASTER_ADDR", "MASTER_PORT", "ROLE_RANK", "ROLE_NAME", "ROLE_WORLD_SIZE") or \
+                    key.startswith("TORCHELASTIC_"):
+                del env[key]
+        cmd += ["-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                "--master-port", str(port)]
+    cmd += [os.path.join(here, "bench.py"), "--internal-by-reference", "--gpus", str(world), "--config", str(args.config),
+            "--steps", str(args.steps), "--warmup", str(args.warmup), "--e2e-batches", str(args.e2e_batches)]
     if args.windows:
         cmd += ["--windows", str(args.windows)]
     if args.banded >= 0:
         cmd += ["--banded", str(args.banded)]
     try:
-        p = subprocess.run(cmd, cwd=here, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, text=True)
+        p = subprocess.run(cmd, cwd=here, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, text=True)
         lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
         if lines:
             return json.loads(lines[-1])
@@ -688,11 +708,19 @@ def by_reference(args):
         return {"unavailable": "%s" % e}
 
 
-def by_reference_leg(args, api, windows, torch, ws, local, wl, banded, mem):
-    """child process of by_reference(): K timed steps, each = per batch object reset + add-by-reference + run (descriptor
-    H2D, gather kernel, POA kernel, D2H) + sync + fetch_all, two objects in flight; host clock between device syncs"""
+def by_reference_leg(args, api, windows, torch, ws, local, wl, banded, mem, dist=None, n_total=None):
+    """child process(es) of by_reference(): K timed steps, each = per batch object reset + add-by-reference + run
+    (descriptor H2D, gather kernel, POA kernel, D2H) + sync + fetch_all, two objects in flight; host clock between device
+    syncs (+ a barrier on both sides and the max over ranks when there are several)"""
     import numpy as np
     n = ws.n_windows
+    n_total = n_total or n
+
+    def fence():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     stride = int(2 * np.diff(ws.seq_off.astype(np.int64)).max() + 64)
     t0 = time.perf_counter()
     store = api.ReadStore.from_flat(ws.bases, ws.seq_off, ws.quals, ws.seq_has_qual, device=local)
@@ -732,21 +760,27 @@ def by_reference_leg(args, api, windows, torch, ws, local, wl, banded, mem):
                 collect(k)
 
     steps(2)
-    torch.cuda.synchronize()
+    fence()
     t0 = time.perf_counter()
     steps(args.steps)
-    torch.cuda.synchronize()
+    fence()
     ms = 1e3 * (time.perf_counter() - t0)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
     out, lens = last["out"], last["lens"]
-    res = {"value": n * args.steps / (ms * 1e-3), "unit": "windows/s", "ms_per_step": ms / args.steps,
+    res = {"value": n_total * args.steps / (ms * 1e-3), "unit": "windows/s", "ms_per_step": ms / args.steps,
            "h2d_bytes_per_step": sum(b.info()["h2d_bytes"] for b in objs),
            "d2h_bytes_per_step": sum(b.info()["d2h_bytes"] for b in objs),
-           "store_device_bytes": store.device_bytes(), "store_upload_ms_once": store_ms,
+           "per_rank": dist is not None, "store_device_bytes": store.device_bytes(), "store_upload_ms_once": store_ms,
            "device_limit_windows": int((last["st"] != 0).sum()),
            "consensus_fnv_first200": "%016x" % windows.fnv1a64([out[i, :lens[i]].tobytes() for i in range(min(n, 200))]),
            "includes": "per step and batch object: rp_poa_reset + rp_poa_add_window_set_refs (metadata only) + rp_poa_run "
                        "(descriptor H2D, layer-extraction kernel, POA kernel, D2H) + rp_poa_sync + rp_poa_fetch_all; the "
-                       "sequences were uploaded once before the timed region (store_upload_ms_once)"}
+                       "sequences were uploaded once before the timed region (store_upload_ms_once)"
+                       + ("; one process per GPU, barrier on both sides, max over ranks, no consensus gather"
+                          if dist is not None else "")}
     for b in objs:
         b.close()
     store.close()
