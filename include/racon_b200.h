@@ -196,6 +196,13 @@ rp_status rp_aln_add(rp_aln* a, const char* q, uint32_t ql, const char* t, uint3
 rp_status rp_aln_set_window_length(rp_aln* a, uint32_t window_length);
 rp_status rp_aln_add_overlap(rp_aln* a, const char* q, uint32_t ql, const char* t, uint32_t tl, uint32_t t_begin,
                              uint32_t q_start);
+/* The same overlap named instead of passed (device-resident reads, rp_reads_create): query = q_len bases of sequence q_id
+ * from q_start on — of its reverse complement when q_reverse (racon's `reverse_complement()[q_length - q_end]`,
+ * overlap.cpp:193-195) —, target = t_len bases of sequence t_id from t_begin on.  The spans are gathered on the device;
+ * nothing but the descriptor crosses the bus.  A batch holds overlaps of one kind (by pointer, or by reference into one
+ * store): RP_ERR_STATE otherwise. */
+rp_status rp_aln_add_overlap_ref(rp_aln* a, const rp_reads* reads, uint32_t q_id, uint32_t q_start, uint32_t q_len,
+                                 int q_reverse, uint32_t t_id, uint32_t t_begin, uint32_t t_len);
 rp_status rp_aln_fetch_breaking_points(rp_aln* a, uint32_t i, const uint32_t** points, uint32_t* n_points);
 uint32_t rp_aln_size(const rp_aln* a);
 /* CUDABatchAligner::alignAll (async) / generate_cigar_strings (sync), cudaaligner.cpp:80-104 */

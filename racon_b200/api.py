@@ -378,6 +378,17 @@ class AlnBatch:
         _check(self.lib, st, "rp_aln_add")
         return True
 
+    def add_ref(self, store, q_id, q_start, q_len, q_reverse, t_id, t_begin, t_len):
+        """The overlap named as slices of a device-resident ReadStore (rp_aln_add_overlap_ref): query = q_len bases of
+        sequence q_id from q_start on (of its reverse complement when q_reverse), target = t_len bases of t_id from
+        t_begin on.  False = batch full (like add)."""
+        f = self.lib.rp_aln_add_overlap_ref
+        f.restype = C.c_int32
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                      C.c_uint32]
+        return _check(self.lib, f(self.h, store.h, q_id, q_start, q_len, 1 if q_reverse else 0, t_id, t_begin, t_len),
+                      "rp_aln_add_overlap_ref") == RP_OK
+
     def size(self):
         return self.lib.rp_aln_size(self.h)
 
@@ -520,17 +531,18 @@ class MirrorPolisher:
 
     @classmethod
     def from_files(cls, reads, overlaps, targets, fragment_correction=False, window_length=500, quality_threshold=10.0,
-                   error_threshold=0.3, trim=True, match=3, mismatch=-5, gap=-4, device=0):
+                   error_threshold=0.3, trim=True, match=3, mismatch=-5, gap=-4, device=0, resident_reads=False):
         """createPolisher + initialize on files (reads_io.hpp): parse, filter, align + breaking points on the device
-        (SAM input keeps its own alignments and needs no device here), build the windows."""
+        (SAM input keeps its own alignments and needs no device here), build the windows.  resident_reads: the sequences
+        are uploaded once and the aligner (and later the consensus) name their inputs instead of copying them."""
         self = cls.__new__(cls)
         self.lib = load()
         L = self.lib
         vp = C.c_void_p
         L.rp_mirror_polisher_open_files.restype = vp
         L.rp_mirror_polisher_open_files.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.c_double,
-                                                    C.c_double, C.c_int, C.c_int8, C.c_int8, C.c_int8, C.c_uint32, vp,
-                                                    C.c_uint32]
+                                                    C.c_double, C.c_int, C.c_int8, C.c_int8, C.c_int8, C.c_uint32, C.c_int,
+                                                    vp, C.c_uint32]
         L.rp_mirror_polisher_counts.restype = None
         L.rp_mirror_polisher_counts.argtypes = [vp, vp]
         L.rp_mirror_polisher_export.restype = None
@@ -546,7 +558,8 @@ class MirrorPolisher:
         err = C.create_string_buffer(1024)
         self.h = L.rp_mirror_polisher_open_files(os.fsencode(reads), os.fsencode(overlaps), os.fsencode(targets),
                                                  1 if fragment_correction else 0, window_length, quality_threshold,
-                                                 error_threshold, 1 if trim else 0, match, mismatch, gap, device, err, 1024)
+                                                 error_threshold, 1 if trim else 0, match, mismatch, gap, device,
+                                                 1 if resident_reads else 0, err, 1024)
         if not self.h:
             raise RuntimeError(err.value.decode(errors="replace"))
         return self
@@ -734,7 +747,7 @@ def polish_files(reads, overlaps, targets, out_path, fragment_correction=False, 
     pol = MirrorPolisher.from_files(reads, overlaps, targets, fragment_correction=fragment_correction,
                                     window_length=window_length, quality_threshold=quality_threshold,
                                     error_threshold=error_threshold, trim=trim, match=match, mismatch=mismatch, gap=gap,
-                                    device=device)
+                                    device=device, resident_reads=resident_reads)
     try:
         n = pol.stream_fasta(out_path, None, drop_unpolished=drop_unpolished, mem_bytes=mem_bytes, banded=banded,
                              resident_reads=resident_reads)

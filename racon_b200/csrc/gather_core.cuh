@@ -20,7 +20,7 @@ struct GatherParams {
     const uint8_t* store_bases;   // every sequence of the store, concatenated
     const uint8_t* store_quals;   // same offsets; only read for sequences that have qualities
     uint8_t* bases;               // packed batch arrays (PoaParams::bases / weights)
-    uint8_t* weights;
+    uint8_t* weights;             // NULL: bases only (the aligner's inputs)
     const uint32_t* seq_off;      // packed offsets, n_seqs + 1
     const uint64_t* src_pos;      // store position of the byte that becomes the sequence's first base
     const uint8_t* src_flags;
@@ -47,7 +47,8 @@ RP_DEV void gather_sequence(const GatherParams& P, uint32_t s) {
         const uint64_t at = reverse ? pos - j : pos + j;
         const uint8_t c = P.store_bases[at];
         P.bases[first + j] = reverse ? complement_base(c) : c;
-        P.weights[first + j] = (flags & kSrcHasQuality) ? static_cast<uint8_t>(P.store_quals[at] - 33) : flat_weight;
+        if (P.weights)
+            P.weights[first + j] = (flags & kSrcHasQuality) ? static_cast<uint8_t>(P.store_quals[at] - 33) : flat_weight;
     }
 }
 

@@ -258,7 +258,26 @@ Polisher::Polisher(std::vector<SequenceView> sequences, uint64_t targets_size, W
     }
 }
 
-Polisher::~Polisher() {}
+Polisher::~Polisher() { rp_reads_destroy(store_); }
+
+const rp_reads* Polisher::read_store() {
+    if (store_ == nullptr) {
+        std::vector<const char*> data(sequences_.size()), quality(sequences_.size());
+        std::vector<uint32_t> length(sequences_.size());
+        for (size_t i = 0; i < sequences_.size(); ++i) {
+            data[i] = sequences_[i].data;
+            quality[i] = sequences_[i].quality;
+            length[i] = sequences_[i].length;
+        }
+        const rp_status s = rp_reads_create(&store_, static_cast<int>(device_), static_cast<uint32_t>(data.size()),
+                                            data.data(), quality.data(), length.data());
+        if (s != RP_OK) {
+            fprintf(stderr, "[racon_b200::Polisher] error: read store: %s (%s)\n", rp_strerror(s), rp_last_error());
+            exit(1);
+        }
+    }
+    return store_;
+}
 
 const char* Polisher::reverse_complement(uint32_t id) {  // Sequence::create_reverse_complement, sequence.cpp:58-93
     std::string& r = reverse_complement_[id];
@@ -321,9 +340,14 @@ void Polisher::find_overlap_breaking_points(std::vector<Overlap>& overlaps) {
             const Overlap& o = overlaps[todo[i]];
             /* the spans racon hands to the aligner (overlap.cpp:193-197) */
             const uint32_t q_start = o.strand ? o.q_length - o.q_end : o.q_begin;
-            const char* q = (o.strand ? reverse_complement(o.q_id) : sequences_[o.q_id].data) + q_start;
-            const char* t = sequences_[o.t_id].data + o.t_begin;
-            s = rp_aln_add_overlap(aln, q, o.q_end - o.q_begin, t, o.t_end - o.t_begin, o.t_begin, q_start);
+            if (resident_reads_) {
+                s = rp_aln_add_overlap_ref(aln, read_store(), o.q_id, q_start, o.q_end - o.q_begin, o.strand != 0, o.t_id,
+                                           o.t_begin, o.t_end - o.t_begin);
+            } else {
+                const char* q = (o.strand ? reverse_complement(o.q_id) : sequences_[o.q_id].data) + q_start;
+                const char* t = sequences_[o.t_id].data + o.t_begin;
+                s = rp_aln_add_overlap(aln, q, o.q_end - o.q_begin, t, o.t_end - o.t_begin, o.t_begin, q_start);
+            }
             if (s == RP_BATCH_FULL) break;
             if (s != RP_OK) {
                 fprintf(stderr, "[racon_b200::Polisher::find_overlap_breaking_points] error: %s (%s)\n",
@@ -468,29 +492,11 @@ void Polisher::polish_streaming(const std::function<void(const PolishedSequence&
     };
     /* resident reads: every sequence goes to the device once; the windows (whose pieces know their origin, build_windows)
      * are then added by reference and their layers extracted on the device */
-    struct StoreGuard {
-        rp_reads* reads = nullptr;
-        ~StoreGuard() { rp_reads_destroy(reads); }
-    } store;
-    if (resident_reads) {
-        std::vector<const char*> data(sequences_.size()), quality(sequences_.size());
-        std::vector<uint32_t> length(sequences_.size());
-        for (size_t i = 0; i < sequences_.size(); ++i) {
-            data[i] = sequences_[i].data;
-            quality[i] = sequences_[i].quality;
-            length[i] = sequences_[i].length;
-        }
-        const rp_status s = rp_reads_create(&store.reads, static_cast<int>(device_), static_cast<uint32_t>(data.size()),
-                                            data.data(), quality.data(), length.data());
-        if (s != RP_OK) {
-            fprintf(stderr, "[racon_b200::Polisher::polish_streaming] error: %s (%s)\n", rp_strerror(s), rp_last_error());
-            exit(1);
-        }
-    }
-    InFlight obj[kObjects];   // declared after the store: the batch objects go first
+    const rp_reads* store = (resident_reads || resident_reads_) ? read_store() : nullptr;
+    InFlight obj[kObjects];
     for (auto& o : obj) {
         o.batch = createBatch(0, device_, memory, gap_, mismatch_, match_, banded, window_length_, trim_);
-        o.batch->useReadStore(store.reads);
+        o.batch->useReadStore(store);
     }
     std::string polished_data;
     uint32_t num_polished_windows = 0;
@@ -609,7 +615,7 @@ extern "C" void* rp_mirror_polisher_open_with_bp(uint32_t n_seq, const char* bas
 extern "C" void* rp_mirror_polisher_open_files(const char* reads, const char* overlaps, const char* targets,
                                                int fragment_correction, uint32_t window_length, double quality_threshold,
                                                double error_threshold, int trim, int8_t match, int8_t mismatch, int8_t gap,
-                                               uint32_t device, char* err, uint32_t err_cap) {
+                                               uint32_t device, int resident_reads, char* err, uint32_t err_cap) {
     using namespace racon_b200;
     try {
         std::unique_ptr<PolHandle> h(new PolHandle());
@@ -617,6 +623,7 @@ extern "C" void* rp_mirror_polisher_open_files(const char* reads, const char* ov
         h->polisher.reset(new Polisher(h->input->views(), h->input->targets_size, h->input->window_type,
                                        fragment_correction != 0, window_length, quality_threshold, trim != 0, match,
                                        mismatch, gap, device));
+        h->polisher->use_resident_reads(resident_reads != 0);
         h->polisher->initialize(h->input->overlaps);
         return h.release();
     } catch (const std::exception& e) {

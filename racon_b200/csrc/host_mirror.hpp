@@ -203,6 +203,10 @@ public:
              uint32_t window_length, double quality_threshold, bool trim, int8_t match, int8_t mismatch, int8_t gap,
              uint32_t device);
     ~Polisher();
+    /* Device-resident reads: every sequence is uploaded once (rp_reads_create, at first use) and both device stages name
+     * their inputs instead of copying them — the aligner its two spans per overlap (rp_aln_add_overlap_ref), the consensus
+     * its window pieces (rp_poa_add_window_refs).  Call before initialize(). */
+    void use_resident_reads(bool on) { resident_reads_ = on; }
     void find_overlap_breaking_points(std::vector<Overlap>& overlaps);
     void initialize(std::vector<Overlap>& overlaps);
     /* the window-building half of initialize() alone, for overlaps whose breaking points are already known */
@@ -244,6 +248,9 @@ private:
     std::vector<uint32_t> targets_coverages_;
     std::vector<std::shared_ptr<Window>> windows_;
     std::vector<size_t> failed_overlaps_, failed_windows_;
+    bool resident_reads_ = false;
+    rp_reads* store_ = nullptr;
+    const rp_reads* read_store();
 };
 
 }  // namespace racon_b200

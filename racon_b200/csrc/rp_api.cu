@@ -216,6 +216,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_aln_kern
 
 }  // namespace
 
+/* device-resident sequences (include/racon_b200.h: rp_reads_create) */
+struct rp_reads {
+    int device = 0;
+    std::vector<const char*> data, quality;       // the caller's host arrays (kept valid by the caller)
+    std::vector<uint32_t> length;
+    std::vector<uint64_t> off;                    // position of each sequence in the device arrays, n + 1
+    std::vector<std::array<uint64_t, 4>> chars;   // per sequence: which byte values occur (256-bit set)
+    DevBuf d_bases, d_quals;
+    bool any_quality = false;
+};
+
 struct rp_aln {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -227,6 +238,14 @@ struct rp_aln {
     uint64_t bp_total = 0;
     std::vector<uint32_t> pre_status;      // per pair: soft status decided on the host (too long) or 0
     uint64_t run_total = 0;
+    /* by-reference batches: both spans of every pair as slices of a device-resident store, gathered at upload */
+    const rp_reads* reads = nullptr;
+    bool by_ref = false;
+    uint64_t n_bases = 0;              // == bases.size unless by_ref
+    rp::GrowBuf<uint64_t> src_pos;     // two entries per pair: query, target
+    rp::GrowBuf<uint8_t> src_flags;
+    rp::GrowBuf<uint32_t> span_off;    // packed offsets of the 2 n spans, + total
+    DevBuf d_src_pos, d_src_flags, d_span_off;
     DevBuf d_bases, d_q_off, d_q_len, d_t_off, d_t_len, d_run_off, d_run_cap, d_queue, d_runs, d_n_runs, d_dist,
         d_status, d_head, d_scratch, d_t_begin, d_q_start, d_bp_off, d_bp_cap, d_bp, d_n_bp;
     rp::GrowBuf<uint32_t> h_runs, h_n_runs, h_status, h_bp, h_n_bp;
@@ -243,21 +262,10 @@ struct rp_aln {
     rp_aln()
         : bases(&kPinned), q_off(&kPinned), q_len(&kPinned), t_off(&kPinned), t_len(&kPinned), run_off(&kPinned),
           run_cap(&kPinned), queue(&kPinned), t_begin(&kPinned), q_start(&kPinned), bp_off(&kPinned),
-          bp_cap(&kPinned), h_runs(&kPinned), h_n_runs(&kPinned), h_status(&kPinned), h_bp(&kPinned),
-          h_n_bp(&kPinned), h_dist(&kPinned) {
+          bp_cap(&kPinned), src_pos(&kPinned), src_flags(&kPinned), span_off(&kPinned), h_runs(&kPinned),
+          h_n_runs(&kPinned), h_status(&kPinned), h_bp(&kPinned), h_n_bp(&kPinned), h_dist(&kPinned) {
         std::memset(&P, 0, sizeof(P));
     }
-};
-
-/* device-resident sequences (include/racon_b200.h: rp_reads_create) */
-struct rp_reads {
-    int device = 0;
-    std::vector<const char*> data, quality;       // the caller's host arrays (kept valid by the caller)
-    std::vector<uint32_t> length;
-    std::vector<uint64_t> off;                    // position of each sequence in the device arrays, n + 1
-    std::vector<std::array<uint64_t, 4>> chars;   // per sequence: which byte values occur (256-bit set)
-    DevBuf d_bases, d_quals;
-    bool any_quality = false;
 };
 
 struct rp_poa {
@@ -310,6 +318,7 @@ struct rp_poa {
 extern "C" {
 
 static rp_status configure(rp_poa* p, uint32_t wl);
+static rp_status aln_add_metadata(rp_aln* a, uint32_t ql, uint32_t tl, uint32_t t_begin, uint32_t q_start, bool too_long);
 
 const char* rp_strerror(rp_status s) {
     switch (s) {
@@ -1218,7 +1227,8 @@ void rp_aln_destroy(rp_aln* a) {
     if (a->stream) cudaStreamSynchronize(a->stream);
     DevBuf* bufs[] = {&a->d_bases, &a->d_q_off, &a->d_q_len, &a->d_t_off, &a->d_t_len, &a->d_run_off, &a->d_run_cap,
                       &a->d_queue, &a->d_runs, &a->d_n_runs, &a->d_dist, &a->d_status, &a->d_head, &a->d_scratch,
-                      &a->d_t_begin, &a->d_q_start, &a->d_bp_off, &a->d_bp_cap, &a->d_bp, &a->d_n_bp};
+                      &a->d_t_begin, &a->d_q_start, &a->d_bp_off, &a->d_bp_cap, &a->d_bp, &a->d_n_bp, &a->d_src_pos,
+                      &a->d_src_flags, &a->d_span_off};
     for (DevBuf* b : bufs) b->release();
     if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
     delete a;
@@ -1252,16 +1262,54 @@ rp_status rp_aln_add_overlap(rp_aln* a, const char* q, uint32_t ql, const char* 
     if (static_cast<uint64_t>(t_begin) + tl > 0xffffffffull || static_cast<uint64_t>(q_start) + ql > 0xffffffffull)
         return fail(RP_ERR_INVALID, "coordinates exceed 32 bits");
     if (a->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
+    if (a->by_ref) return fail(RP_ERR_STATE, "this batch holds overlaps added by reference; reset first");
     const bool too_long = ql > a->max_len || tl > a->max_len;
     const uint64_t add = too_long ? 0 : static_cast<uint64_t>(ql) + tl;
-    if (a->bases.size + add > a->max_bases) return RP_BATCH_FULL;
-    uint32_t off = static_cast<uint32_t>(a->bases.size);
+    if (a->n_bases + add > a->max_bases) return RP_BATCH_FULL;
     if (!too_long) {
         uint8_t* b = a->bases.extend(add);
         if (!b) return fail(RP_ERR_NOMEM, "pinned staging allocation failed");
         std::memcpy(b, q, ql);
         std::memcpy(b + ql, t, tl);
     }
+    return aln_add_metadata(a, ql, tl, t_begin, q_start, too_long);
+}
+
+rp_status rp_aln_add_overlap_ref(rp_aln* a, const rp_reads* reads, uint32_t q_id, uint32_t q_start, uint32_t q_len,
+                                 int q_reverse, uint32_t t_id, uint32_t t_begin, uint32_t t_len) {
+    if (!a || !reads) return fail(RP_ERR_INVALID, "null argument");
+    if (a->uploaded) return fail(RP_ERR_STATE, "batch already uploaded; reset first");
+    if (reads->device != a->device) return fail(RP_ERR_INVALID, "the read store lives on another device");
+    if (!a->pre_status.empty() && (!a->by_ref || a->reads != reads))
+        return fail(RP_ERR_STATE, "a batch holds overlaps added by pointer or by reference into ONE store; reset first");
+    const uint32_t n_store = static_cast<uint32_t>(reads->length.size());
+    if (q_id >= n_store || t_id >= n_store || static_cast<uint64_t>(q_start) + q_len > reads->length[q_id] ||
+        static_cast<uint64_t>(t_begin) + t_len > reads->length[t_id])
+        return fail(RP_ERR_INVALID, "overlap span outside its sequence");
+    const bool too_long = q_len > a->max_len || t_len > a->max_len;
+    const uint64_t add = too_long ? 0 : static_cast<uint64_t>(q_len) + t_len;
+    if (a->n_bases + add > a->max_bases) return RP_BATCH_FULL;
+    if (!a->src_pos.reserve(a->src_pos.size + 2) || !a->src_flags.reserve(a->src_flags.size + 2) ||
+        !a->span_off.reserve(a->span_off.size + 3))
+        return fail(RP_ERR_NOMEM, "pinned staging allocation failed");
+    if (a->span_off.size == 0) a->span_off.push(0);
+    const uint32_t at = static_cast<uint32_t>(a->n_bases);
+    a->src_pos.push(reads->off[q_id] + (q_reverse ? reads->length[q_id] - 1 - q_start : q_start));
+    a->src_flags.push(q_reverse ? rp::kSrcReverse : 0);
+    a->span_off.push(at + (too_long ? 0 : q_len));
+    a->src_pos.push(reads->off[t_id] + t_begin);
+    a->src_flags.push(0);
+    a->span_off.push(at + static_cast<uint32_t>(add));
+    a->by_ref = true;
+    a->reads = reads;
+    return aln_add_metadata(a, q_len, t_len, t_begin, q_start, too_long);
+}
+
+/* the part of adding an overlap that does not touch its bases */
+static rp_status aln_add_metadata(rp_aln* a, uint32_t ql, uint32_t tl, uint32_t t_begin, uint32_t q_start, bool too_long) {
+    const uint64_t add = too_long ? 0 : static_cast<uint64_t>(ql) + tl;
+    const uint32_t off = static_cast<uint32_t>(a->n_bases);
+    a->n_bases += add;
     const uint32_t cap = too_long ? 0 : (ql + tl) / 3 + 64;
     if (!a->q_off.push(off) || !a->q_len.push(too_long ? 0 : ql) || !a->t_off.push(off + (too_long ? 0 : ql)) ||
         !a->t_len.push(too_long ? 0 : tl) || !a->run_off.push(static_cast<uint32_t>(a->run_total)) ||
@@ -1304,7 +1352,33 @@ rp_status rp_aln_upload(rp_aln* a) {
         h2d += bytes;
         return bytes ? cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, a->stream) : cudaSuccess;
     };
-    RP_CUDA(up(a->d_bases, a->bases.data, a->bases.bytes()));
+    if (a->by_ref) {
+        RP_CUDA(a->d_bases.reserve(a->n_bases + 16));
+        RP_CUDA(up(a->d_src_pos, a->src_pos.data, a->src_pos.bytes()));
+        RP_CUDA(up(a->d_src_flags, a->src_flags.data, a->src_flags.bytes()));
+        RP_CUDA(up(a->d_span_off, a->span_off.data, a->span_off.bytes()));
+        /* both spans of every pair are cut out of the store on the device (reverse complement included) */
+        rp::GatherParams G;
+        G.store_bases = static_cast<const uint8_t*>(a->reads->d_bases.p);
+        G.store_quals = nullptr;
+        G.bases = static_cast<uint8_t*>(a->d_bases.p);
+        G.weights = nullptr;
+        G.seq_off = static_cast<const uint32_t*>(a->d_span_off.p);
+        G.src_pos = static_cast<const uint64_t*>(a->d_src_pos.p);
+        G.src_flags = static_cast<const uint8_t*>(a->d_src_flags.p);
+        G.n_seqs = static_cast<uint32_t>(a->src_pos.size);
+        if (G.n_seqs > 0) {
+#if defined(RP_HOST_SIM)
+            rp_gather_kernel(G, SimLaunch{1, 256});
+#else
+            const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(148 * 8, (G.n_seqs + 7) / 8));
+            rp_gather_kernel<<<blocks, 256, 0, a->stream>>>(G);
+            RP_CUDA(cudaGetLastError());
+#endif
+        }
+    } else {
+        RP_CUDA(up(a->d_bases, a->bases.data, a->bases.bytes()));
+    }
     RP_CUDA(up(a->d_q_off, a->q_off.data, a->q_off.bytes()));
     RP_CUDA(up(a->d_q_len, a->q_len.data, a->q_len.bytes()));
     RP_CUDA(up(a->d_t_off, a->t_off.data, a->t_off.bytes()));
@@ -1477,6 +1551,9 @@ rp_status rp_aln_reset(rp_aln* a) {
     a->bases.clear(); a->q_off.clear(); a->q_len.clear(); a->t_off.clear(); a->t_len.clear();
     a->run_off.clear(); a->run_cap.clear(); a->queue.clear();
     a->t_begin.clear(); a->q_start.clear(); a->bp_off.clear(); a->bp_cap.clear();
+    a->src_pos.clear(); a->src_flags.clear(); a->span_off.clear();
+    a->by_ref = false;
+    a->n_bases = 0;
     a->pre_status.clear();
     a->run_total = 0;
     a->bp_total = 0;

@@ -197,3 +197,49 @@ def test_by_reference_budget_back_pressure_and_statuses():
     s9, q9, p9 = _as_store(w9, seed=2)
     _, pol, st, _, _ = _by_reference(w9, s9, q9, p9)
     assert (st != 0).all() and not pol.any()
+
+
+def test_aligner_by_reference_equals_by_pointer_and_edlib():
+    """rp_aln_add_overlap_ref: both spans of an overlap cut out of the store on the device, the query as a slice of the
+    reverse complement for a '-' strand overlap — CIGAR, edit distance and breaking points equal to the by-pointer call on
+    the same bytes and to the unmodified edlib (when it was built here)."""
+    rng = np.random.default_rng(17)
+    reads, pairs = [], []
+    for k in range(10):
+        t = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(200, 700))).astype(np.uint8))
+        q = util.mutate(rng, t, 0.12) or t[:1]
+        pre_t = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 600))).astype(np.uint8))
+        pre_q = bytes(rng.choice(list(b"ACGTN"), size=int(rng.integers(0, 40))).astype(np.uint8))
+        suf_q = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 40))).astype(np.uint8))
+        rev = k % 2
+        stored_q = pre_q + q + suf_q
+        if rev:
+            stored_q = stored_q.translate(COMP)[::-1]
+        reads += [pre_t + t + b"GATTACA", stored_q]
+        pairs.append(dict(q=q, t=t, q_id=2 * k + 1, q_start=len(pre_q), rev=rev, t_id=2 * k, t_begin=len(pre_t)))
+    store = api.ReadStore(reads)
+    a, b = api.AlnBatch(), api.AlnBatch()
+    try:
+        for batch in (a, b):
+            batch.set_window_length(100)
+        for p in pairs:
+            assert a.add_ref(store, p["q_id"], p["q_start"], len(p["q"]), p["rev"], p["t_id"], p["t_begin"], len(p["t"]))
+            assert b.add(p["q"], p["t"], t_begin=p["t_begin"], q_start=p["q_start"])
+        with pytest.raises(api.RaconB200Error, match="call order"):
+            a.add(pairs[0]["q"], pairs[0]["t"])
+        with pytest.raises(api.RaconB200Error, match="outside its sequence"):
+            a.add_ref(store, 1, len(reads[1]) - 5, 10, 0, 0, 0, 10)
+        for batch in (a, b):
+            batch.run()
+            batch.sync()
+        assert a.info()["h2d_bytes"] < b.info()["h2d_bytes"] - sum(len(p["q"]) + len(p["t"]) for p in pairs) // 2
+        for i, p in enumerate(pairs):
+            ca, cb = a.fetch(i), b.fetch(i)
+            assert ca == cb and ca[2] == 0
+            assert (a.fetch_breaking_points(i) == b.fetch_breaking_points(i)).all()
+            if ob.have_ref():
+                assert ca[0].decode() == ob.ref_edlib_cigar(p["q"], p["t"])[0]
+    finally:
+        a.close()
+        b.close()
+        store.close()

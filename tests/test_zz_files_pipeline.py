@@ -52,12 +52,12 @@ def test_files_to_polished_fasta_equals_the_reference(case, tmp_path):
 
 @pytest.mark.parametrize("case", ["fastq_sam", "fasta_paf", "frag_fastq_paf"])
 def test_files_to_polished_fasta_with_resident_reads(case, tmp_path):
-    """The same run with every sequence uploaded once and the windows added by reference (layers
-    extracted on the device, reverse complements and weights included): the reference's bytes again."""
+    """The same run with every sequence uploaded once, the aligner's spans and the windows' pieces named by reference
+    (extracted on the device, reverse complements and weights included): the reference's bytes again."""
     g = np.load(GOLD)
     reads, overlaps, target, frag, e = CASES[case]
     pol = api.MirrorPolisher.from_files(os.path.join(DATA, reads), os.path.join(DATA, overlaps), os.path.join(DATA, target),
-                                        fragment_correction=frag, error_threshold=e)
+                                        fragment_correction=frag, error_threshold=e, resident_reads=True)
     try:
         out = str(tmp_path / "polished.fasta")
         n = pol.stream_fasta(out, None, drop_unpolished=False, resident_reads=True, mem_bytes=256 << 20)
