@@ -1,6 +1,6 @@
 """The C ABI on a machine without a GPU: rp_api.cu compiled over the simulated CUDA runtime (csrc/cuda_sim_runtime.h,
 build.build_simapi) runs the same entry points with the kernels as cooperative fibres.  Here the CPU suite
-runs the by-reference / device-resident-reads tests (tests/test_gpu_resident.py) that way, in a process of their own with
+runs the by-reference / device-resident-reads tests (tests/test_zz_gpu_resident.py) that way, in a process of their own with
 RACON_B200_LIB pointing at the simulated build — the product library is not involved and still refuses to work without a
 device (tests/test_abi.py)."""
 import os
@@ -14,7 +14,7 @@ def test_gpu_marked_resident_read_tests_pass_over_the_simulated_runtime():
     from racon_b200 import build
     lib = build.build_simapi()
     env = dict(os.environ, RACON_B200_LIB=lib)
-    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_resident.py", "-m", "gpu", "-x", "-q", "-p",
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_zz_gpu_resident.py", "-m", "gpu", "-x", "-q", "-p",
                         "no:cacheprovider"], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
                        timeout=1500)
     tail = "\n".join(r.stdout.splitlines()[-15:])
