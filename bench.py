@@ -170,6 +170,15 @@ def make_windows(cfg_id, args, rank, world, sample=None):
     raise SystemExit("bench.py: config %d has its own driver" % cfg_id)
 
 
+def config_key(cfg, args, banded=None):
+    """`config` of the JSON line: names the workload and nothing else, identical in both arms (`--impl reference` included) so
+    that the driver compares like with like; what THIS run did beyond that (window counts, batch objects, host binding,
+    checksums ...) goes into the line's `run` object."""
+    return {"workload": cfg["workload"], "baseline_config": args.config,
+            "l2": "GPU arm: a step's inputs (hundreds of MB) + DP scratch (tens of GB) exceed the 126 MB L2, no explicit flush; "
+                  "reference arm: host cores, bounded sample of the same windows"}
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation (Window::generate_consensus over spoa, compiled unmodified into
     oracle/_ref) on all host threads.  Each step = a bounded sample of the same workload."""
@@ -210,7 +219,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": cfg["metric"], "value": value, "unit": "windows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "baseline_config": args.config, "sample": sample, "wall_s": wall},
+        "config": config_key(cfg, args), "run": {"sample": sample, "wall_s": wall},
         "cpu_baseline": {"value": value, "unit": "windows/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -536,38 +545,57 @@ def main():
             gather.start(out, lens)
         last["out"], last["lens"] = out, lens
 
+    # where the host spends a step (wall clock of this rank's calling thread, summed over the timed steps): filling the
+    # objects, queueing H2D + kernel + D2H, waiting for a kernel to finish, reading results back, the consensus gather
+    phase = {"add": 0.0, "run": 0.0, "wait": 0.0, "fetch": 0.0, "gather": 0.0}
+    clock = time.perf_counter
+
     def plugin_steps(n_steps):
         pending = [None] * nb
         parts = {}
 
         def collect(k):
+            t_a = clock()
             objs[k].sync()
+            t_b = clock()
             s_done = pending[k]
             parts[s_done][k] = objs[k].fetch_all(stride)
+            t_c = clock()
             pending[k] = None
             if all(x is not None for x in parts[s_done]):
                 finalize(parts.pop(s_done))
+            phase["wait"] += t_b - t_a
+            phase["fetch"] += t_c - t_b
+            phase["gather"] += clock() - t_c
 
         for s_i in range(n_steps):
             parts[s_i] = [None] * nb
             for k, b in enumerate(objs):
                 if pending[k] is not None:
                     collect(k)
+                t_a = clock()
                 b.reset()
                 cnt = bounds[k + 1] - bounds[k]
                 assert b.add_window_set(ws, first=bounds[k], count=cnt) == cnt
+                t_b = clock()
                 b.run()
+                phase["add"] += t_b - t_a
+                phase["run"] += clock() - t_b
                 pending[k] = s_i
         for k in range(nb):
             if pending[k] is not None:
                 collect(k)
+        t_a = clock()
         if gather is not None:
             got = gather.finish()
             if got is not None:
                 last["gathered"] = got
+        phase["gather"] += clock() - t_a
 
     plugin_steps(2)
     barrier()
+    for key in phase:
+        phase[key] = 0.0
     t0 = time.perf_counter()
     plugin_steps(args.steps)
     barrier()
@@ -605,7 +633,8 @@ def main():
             "metric": cfg["metric"], "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"],
             "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": dict({"workload": cfg["workload"], "baseline_config": args.config, "windows_rank0": n,
+            "config": config_key(cfg, args),
+            "run": dict({"windows_rank0": n,
                             "window_len": wl, "banded": banded,
                             "parallelism": "windows sharded across %d GPU(s), no data-path collective" % world,
                             "l2": "inputs (%.0f MB) + per-step DP scratch (>> 126 MB) exceed L2; no explicit flush"
@@ -618,6 +647,7 @@ def main():
             "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": "windows/s",
                     "h2d_bytes_per_step": io["h2d_bytes"], "d2h_bytes_per_step": io["d2h_bytes"],
                     "batch_objects": nb,
+                    "host_ms_per_step_rank0": {k2: round(1e3 * v / args.steps, 2) for k2, v in phase.items()},
                     "includes": "every step, per batch object: rp_poa_reset + rp_poa_add_window_set (host buffers -> pinned "
                                 "staging) + rp_poa_run (H2D, kernel, D2H) + rp_poa_sync + rp_poa_fetch_all; the objects stay "
                                 "in flight across steps (as CUDAPolisher keeps its batches busy), timed from the first add "
