@@ -122,6 +122,11 @@ RP_HD SlotLayout make_layout(const PoaLimits& L) {
 /* Launch-wide parameters (plain pointers into HBM). */
 struct PoaParams {
     int32_t match, mismatch, gap;
+    /* per-register constants of a full-matrix DP row, derived from `gap` by set_scores(): [r] = (0, (r+1)g) bridge
+     * offsets, [8+r] = ((r+1)g, (r+9)g) carry offsets, [16] = (g, g).  Kept in the parameter block so that the row loop
+     * takes them straight from the constant bank as instruction operands — as loop-invariant registers they do not
+     * survive the kernel's register cap and were rebuilt (about 35 instructions) in every row. */
+    uint32_t row_consts[17];
     uint32_t n_windows;
     /* inputs, packed by the host in processing order (backbone first, layers sorted as window.cpp:85-86) */
     const uint8_t* bases;
@@ -155,6 +160,21 @@ struct PoaParams {
     uint32_t band_margin;         // columns the traceback must keep from a cut band edge to be trusted
     unsigned long long* band_stats;  // [0] alignments tried in the band, [1] redone with the full matrix (may be null)
 };
+
+/* scores + everything derived from them (host side, both the product and the test builds fill PoaParams through this) */
+inline void set_scores(PoaParams& P, int32_t match, int32_t mismatch, int32_t gap) {
+    P.match = match;
+    P.mismatch = mismatch;
+    P.gap = gap;
+    auto pk = [](int32_t lo, int32_t hi) {
+        return (static_cast<uint32_t>(lo) & 0xffffu) | (static_cast<uint32_t>(hi) << 16);
+    };
+    for (int r = 0; r < 8; ++r) {
+        P.row_consts[r] = pk(0, (r + 1) * gap);
+        P.row_consts[8 + r] = pk((r + 1) * gap, (r + 9) * gap);
+    }
+    P.row_consts[16] = pk(gap, gap);
+}
 
 /* Row layout.  A lane owns 16 consecutive columns; inside that 32-byte block register r (0..7) packs
  * column r in its low half and column 8+r in its high half, so the in-row gap recurrence runs as two
@@ -213,6 +233,20 @@ RP_DEV Row8 load_row_smem(const int16_t* row, int lane) {
     o.r[0] = a.x; o.r[1] = a.y; o.r[2] = a.z; o.r[3] = a.w;
     o.r[4] = c.x; o.r[5] = c.y; o.r[6] = c.z; o.r[7] = c.w;
     return o;
+}
+/* the same with the lane's two (swizzled) granule indices handed in: dp() derives them once per alignment */
+RP_DEV Row8 load_row_smem_at(const int16_t* row, uint32_t p0, uint32_t p1) {
+    const U4* b = reinterpret_cast<const U4*>(row);
+    U4 a = b[p0], c = b[p1];
+    Row8 o;
+    o.r[0] = a.x; o.r[1] = a.y; o.r[2] = a.z; o.r[3] = a.w;
+    o.r[4] = c.x; o.r[5] = c.y; o.r[6] = c.z; o.r[7] = c.w;
+    return o;
+}
+RP_DEV void store_row_smem_at(int16_t* row, uint32_t p0, uint32_t p1, const Row8& v) {
+    U4* b = reinterpret_cast<U4*>(row);
+    b[p0] = U4{v.r[0], v.r[1], v.r[2], v.r[3]};
+    b[p1] = U4{v.r[4], v.r[5], v.r[6], v.r[7]};
 }
 RP_DEV void store_row_smem(int16_t* row, int lane, const Row8& v) {
     uint32_t q0 = 2u * static_cast<uint32_t>(lane);
@@ -700,15 +734,11 @@ struct PoaWarp {
          * the carry between chunks goes through a small per-row array), so shared memory only ever holds one
          * chunk: the profile chunk and a ring of the last `ring_rows` rows. */
         const int32_t g = P->gap;
-        const uint32_t g2 = pack16(g, g);
+        const uint32_t g2 = P->row_consts[16];
         const uint32_t nch = lpa / kCC;
         const int32_t negsafe = -32768 - 16 * g;  // see kMaxGapInt16
-        uint32_t gb[8], gc[8];  // bridge / carry offsets per register
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            gb[r] = pack16(0, (r + 1) * g);
-            gc[r] = pack16((r + 1) * g, (r + 9) * g);
-        }
+        const uint32_t* gb = P->row_consts;       // bridge / carry offsets per register (constant bank, see PoaParams)
+        const uint32_t* gc = P->row_consts + 8;
         for (uint32_t col = lane; col < lpa; col += G) H[perm(col)] = static_cast<int16_t>(static_cast<int32_t>(col) * g);
         const uint32_t sink_ch = len / kCC, sink_e = swz(len % kCC);
         int32_t best = kNeg32;
@@ -716,6 +746,12 @@ struct PoaWarp {
         int16_t* cc_prev = ccarry;        // last column of the previous chunk, per row (multi-chunk rows only)
         int16_t* cc_cur = ccarry + (nmax + 2);
         const uint32_t lanem = static_cast<uint32_t>(lane);
+        /* this lane's two granules of a shared-memory row (load_row_smem's swizzle), pinned in registers for the row
+         * loop: re-derived per row they start every row's dependency chain with an S2R of the thread index */
+        uint32_t sw0 = (2u * lanem) ^ (((2u * lanem) >> 3) & 1u);
+        uint32_t sw1 = (2u * lanem + 1u) ^ (((2u * lanem + 1u) >> 3) & 1u);
+        RP_KEEP_IN_REGISTER(sw0);
+        RP_KEEP_IN_REGISTER(sw1);
         for (uint32_t ch = 0; ch < nch; ++ch) {
             build_profile(seq, len, ch);
             for (uint32_t c = lane; c < kCC; c += G)  // root row (rank 0) -> ring slot 0
@@ -728,21 +764,28 @@ struct PoaWarp {
             uint32_t rec_a_lo = 0, rec_a_hi = 0, rec_b_lo = 0, rec_b_hi = 0;
             int16_t* hrow = H + static_cast<uint64_t>(ch) * kCC;  // row i of this chunk = hrow + i*lpa
             uint32_t myslot = 0;  // i % ring_rows, kept incrementally (any ring size, no division)
-            for (uint32_t i = 1; i <= nrows; ++i) {
+            Row8 prev;            // the row computed last (this lane's registers of it)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) prev.r[r] = 0;
+            /* rows in blocks of G: lane l fetches the record of row i0 + l once per block (a loop level of its own, so that
+             * the row loop carries no predicated-off copy of the fetch), every row then takes its record by shuffle */
+            for (uint32_t i0 = 1; i0 <= nrows; i0 += G) {
+              {
+                  const Rec t = rec[i0 + lane];  // rec[] is padded
+                  rec_a_lo = static_cast<uint32_t>(t.a);
+                  rec_a_hi = static_cast<uint32_t>(t.a >> 32);
+                  rec_b_lo = static_cast<uint32_t>(t.b);
+                  rec_b_hi = static_cast<uint32_t>(t.b >> 32);
+              }
+              const uint32_t i_last = i0 + G - 1 < nrows ? i0 + G - 1 : nrows;
+              for (uint32_t i = i0; i <= i_last; ++i) {
                 myslot = myslot + 1 == ring_rows ? 0u : myslot + 1;
-                const uint32_t ti = (i - 1) & (G - 1);
-                if (ti == 0) {
-                    Rec t = rec[i + lane];  // rec[] is padded
-                    rec_a_lo = static_cast<uint32_t>(t.a);
-                    rec_a_hi = static_cast<uint32_t>(t.a >> 32);
-                    rec_b_lo = static_cast<uint32_t>(t.b);
-                    rec_b_hi = static_cast<uint32_t>(t.b >> 32);
-                }
+                const uint32_t ti = i - i0;
                 const uint32_t lo = shfl(rec_a_lo, ti);
                 const uint32_t cidx = lo & 0xff;
                 const uint32_t np = (lo >> 8) & 0x7f;
                 const bool sink = (lo >> 15) & 1;
-                const Row8 pf = load_row_smem(prof + cidx * kCC, lane);
+                const Row8 pf = load_row_smem_at(prof + cidx * kCC, sw0, sw1);
                 /* max over predecessors distributes over both terms of the recurrence:
                  *   max_p(H[p][c-1] + s(c), H[p][c] + g) = max(max_p H[p][c-1] + s(c), max_p H[p][c] + g),
                  * so predecessor rows are first combined with a packed max (8 ops per extra predecessor) and the
@@ -753,7 +796,7 @@ struct PoaWarp {
                     const uint32_t dist = i - p;
                     if (dist < ring_rows) {  // warp-uniform
                         const uint32_t slot = myslot >= dist ? myslot - dist : myslot + ring_rows - dist;
-                        pr = load_row_smem(ring + slot * kCC, lane);
+                        pr = load_row_smem_at(ring + slot * kCC, sw0, sw1);
                     } else
                         pr = load_row_gmem(hrow + static_cast<uint64_t>(p) * lpa, lane);
                     if (multi) {
@@ -769,7 +812,20 @@ struct PoaWarp {
                 };
                 /* the first predecessor is loaded by every group of the warp together; only the groups whose row has
                  * more predecessors enter the nested part */
-                load_pred(np ? (lo >> 16) : 0u, pm);
+                {
+                    const uint32_t p0 = np ? (lo >> 16) : 0u;
+                    if (p0 + 1 == i && p0 != 0) {  // group-uniform
+                        /* the first predecessor is the row just computed (4 of 10 rows): it still is in registers — no
+                         * trip through the shared-memory ring, whose store -> load latency would start this row */
+                        pm = prev;
+                        if (multi) {
+                            int32_t lv = cc_prev[p0];
+                            lvm = lv > lvm ? lv : lvm;
+                        }
+                    } else {
+                        load_pred(p0, pm);
+                    }
+                }
                 if (np > 1) {
                     const uint32_t hi = shfl(rec_a_hi, ti);
                     more(hi & 0xffff);
@@ -834,8 +890,9 @@ struct PoaWarp {
                 Row8 out;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) out.r[r] = acc[r];
+                prev = out;
                 int16_t* myrow_s = ring + myslot * kCC;
-                store_row_smem(myrow_s, lane, out);
+                store_row_smem_at(myrow_s, sw0, sw1, out);
                 store_row_gmem(hrow + static_cast<uint64_t>(i) * lpa, lane, out);
                 if (nch > 1 && lanem == G - 1) cc_cur[i] = static_cast<int16_t>(hi16(acc[7]));
                 syncwarp();
@@ -849,6 +906,7 @@ struct PoaWarp {
                         ++nb;
                     }
                 }
+              }
             }
             if (nch > 1) {
                 if (lane == 0) cc_cur[0] = static_cast<int16_t>((ch + 1) * kCC * g - g);  // root row, last column
@@ -1270,10 +1328,12 @@ struct PoaWarp {
     }
 
     template <bool BAND>
-    static RP_DEV_NOINLINE int traceback_step_wide(const int16_t* H, const uint8_t* bs, const Rec* rec,
-                                                   const uint16_t* pred_ovf, uint32_t ki, int lane, int32_t g, uint32_t i,
-                                                   uint32_t j, uint32_t npe, int32_t hij, int32_t mc, uint32_t lpa,
-                                                   uint32_t* found) {
+    /* returns (move << 16) | predecessor rank, 0 when no predecessor matches — a packed value, not an output pointer: the
+     * caller's variable would then live in local memory, on the dependency chain of every step of the walk */
+    static RP_DEV_NOINLINE uint32_t traceback_step_wide(const int16_t* H, const uint8_t* bs, const Rec* rec,
+                                                        const uint16_t* pred_ovf, uint32_t ki, int lane, int32_t g,
+                                                        uint32_t i, uint32_t j, uint32_t npe, int32_t hij, int32_t mc,
+                                                        uint32_t lpa) {
         for (int pass = 1; pass <= 2; ++pass) {
             if (pass == 1 && j == 0) continue;
             for (uint32_t k0 = 0; k0 < npe; k0 += G) {
@@ -1286,10 +1346,7 @@ struct PoaWarp {
                                    : (hij == hcell_at<BAND>(H, bs, g, lpa, p, j) + g);
                 }
                 const uint32_t msk = gballot<G>(ok);
-                if (msk) {
-                    *found = gshfl<G>(p, ffs_(msk) - 1);
-                    return pass;
-                }
+                if (msk) return (static_cast<uint32_t>(pass) << 16) | (gshfl<G>(p, ffs_(msk) - 1) & 0xffffu);
             }
         }
         return 0;
@@ -1333,7 +1390,13 @@ struct PoaWarp {
         Rec* trec = reinterpret_cast<Rec*>(smem + kTileRows * kTileCols * 2);                      // [kTileRows]
         uint8_t* tbs = smem + kTileRows * (kTileCols * 2 + 16);                                    // [kTileRows]
         uint8_t* tseq = tbs + ((kTileRows + 15) & ~15u);
-        for (uint32_t c = lane; c < len; c += G) tseq[c] = seq[c];  // the walk reads seq[j-1] every step
+        /* the walk compares the row's character with seq[j-1] every step: kept as window-alphabet code indices, the
+         * form the row records hold (a character is in the alphabet exactly once, so codes compare like characters) */
+        for (uint32_t c = lane; c < len; c += G) tseq[c] = static_cast<uint8_t>(code_index(seq[c]));
+        /* read back relative to the tile base, which the walk keeps in a register anyway */
+        const uint8_t* tile_b = reinterpret_cast<const uint8_t*>(tile);
+        uint32_t tseq_at = static_cast<uint32_t>(tseq - tile_b);
+        RP_KEEP_IN_REGISTER(tseq_at);
         const uint32_t nblk = (len + 16) >> 4;
         const uint32_t margin = P->band_margin;
         const U4 f4 = U4{pack16(kBandFloor, kBandFloor), pack16(kBandFloor, kBandFloor), pack16(kBandFloor, kBandFloor),
@@ -1345,6 +1408,24 @@ struct PoaWarp {
         uint32_t t_top = 0, t_rows = 0, t_col0 = 0;  // tile covers ranks (t_top - t_rows, t_top], cols [t_col0, t_col0+32)
         bool have_tile = false, bad = false;
         uint32_t quality = 0;
+        /* aln[] is written one position per diagonal / horizontal step, positions falling by one: lane (c mod G) keeps
+         * the value of position c and the group stores G finished positions with one coalesced write (put_aln) instead
+         * of a lane-0 store — and its address arithmetic — inside every step */
+        /* element index (inside a stored row) of columns j and j-1, carried along: one perm() per step to the left */
+        uint32_t pj = BAND ? perm_band(j) : perm(j);
+        uint32_t pjm = j > 0 ? (BAND ? perm_band(j - 1) : perm(j - 1)) : 0u;
+        auto step_left = [&]() {
+            --j;
+            pj = pjm;
+            pjm = j > 0 ? (BAND ? perm_band(j - 1) : perm(j - 1)) : 0u;
+        };
+        uint32_t pend = kNone;
+        auto put_aln = [&](uint32_t c, uint32_t v) {   // c = j - 1, group-uniform
+            if ((c & (G - 1)) == static_cast<uint32_t>(lane)) pend = v;
+            if ((c & (G - 1)) == 0) {   // group-uniform: positions c .. c+G-1 are complete
+                if (c + lane < len) aln[c + lane] = static_cast<uint16_t>(pend);
+            }
+        };
         while (i != 0) {
             bool need = !have_tile || i + t_rows <= t_top || (j > 0 && j - 1 < t_col0);
             /* when a group that runs in lock step with this one refills, refill too: the groups of a warp then
@@ -1357,6 +1438,16 @@ struct PoaWarp {
                 const uint32_t cbj = j >> 4;
                 const uint32_t cba = cbj ? cbj - 1 : 0;
                 t_col0 = cba << 4;
+                /* the rows' records first (at most three per lane at 32 lanes): their loads are in flight while the
+                 * granule loop below waits for its own */
+                Rec tr[3];
+                if (G == 32) {
+#pragma unroll
+                    for (uint32_t k = 0; k < 3; ++k) {
+                        const uint32_t q = static_cast<uint32_t>(lane) + 32u * k;
+                        if (q < t_rows) tr[k] = rec[t_top - q];
+                    }
+                }
                 /* four lanes per tile row, one 16-byte granule each: consecutive lanes write consecutive 16-byte
                  * granules of the tile (no shared-memory bank conflict) and read one 64-byte piece of an H row */
                 for (uint32_t e = lane; e < 4 * t_rows; e += G) {
@@ -1386,7 +1477,15 @@ struct PoaWarp {
                     }
                     reinterpret_cast<U4*>(tile)[e] = v;
                 }
-                for (uint32_t q = lane; q < t_rows; q += G) trec[q] = rec[t_top - q];
+                if (G == 32) {
+#pragma unroll
+                    for (uint32_t k = 0; k < 3; ++k) {
+                        const uint32_t q = static_cast<uint32_t>(lane) + 32u * k;
+                        if (q < t_rows) trec[q] = tr[k];
+                    }
+                } else {
+                    for (uint32_t q = lane; q < t_rows; q += G) trec[q] = rec[t_top - q];
+                }
                 have_tile = true;
                 syncwarp();
             }
@@ -1395,8 +1494,8 @@ struct PoaWarp {
             const uint32_t lo = static_cast<uint32_t>(rc.a);
             const uint32_t cidx = lo & 0xff, np = (lo >> 8) & 0x7f;
             const uint32_t npe = np ? np : 1;
-            const uint32_t ej = (BAND ? perm_band(j) : perm(j)) - t_col0;   // element of column j inside a tile row
-            const uint32_t ejm = j > 0 ? (BAND ? perm_band(j - 1) : perm(j - 1)) - t_col0 : 0;     // column j-1
+            const uint32_t ej = pj - t_col0;                // element of column j inside a tile row
+            const uint32_t ejm = j > 0 ? pjm - t_col0 : 0;  // column j-1
             const int32_t hij = tile[q * kTileCols + ej];
             if (BAND) {
                 const uint32_t si = tbs[q];
@@ -1407,10 +1506,41 @@ struct PoaWarp {
                 }
             }
             int32_t mc = 0;
-            if (j > 0) mc = (static_cast<uint8_t>(alpha >> (8 * cidx)) == tseq[j - 1]) ? m : x;
+            if (j > 0) mc = cidx == tile_b[tseq_at + j - 1] ? m : x;
             uint32_t found_p = 0;
             int move = 0;  // 1 diag, 2 vert, 3 horiz
-            if (npe <= G) {
+            if (np <= 1) {  // group-uniform
+                /* Rows with one predecessor (or only the virtual root), ~9 of 10 steps: every lane evaluates the same
+                 * candidate, so the step needs no vote, no lane election and no indexed record field — the same
+                 * decisions as the general case below with lane 0 as the only candidate. */
+                const uint32_t p = np ? (lo >> 16) : 0u;   // pred0 (Rec::a bits 16..31)
+                int32_t a, b;
+                uint32_t sp = 0;
+                if (p + t_rows > t_top) {  // predecessor row is inside the tile
+                    const int16_t* pr = tile + (t_top - p) * kTileCols;
+                    a = pr[ejm];
+                    b = pr[ej];
+                    if (BAND) sp = tbs[t_top - p];
+                } else {
+                    a = hcell<BAND>(lpa, p, j > 0 ? j - 1 : 0);
+                    b = hcell<BAND>(lpa, p, j);
+                    if (BAND) sp = bs[p];
+                }
+                if (BAND && p != 0) {  // the candidate cells must be trustworthy too (see the general case)
+                    const int32_t dlp = static_cast<int32_t>(j) - 1 - static_cast<int32_t>(16u * sp);
+                    const int32_t drp = static_cast<int32_t>(16u * (sp + NB)) - 1 - static_cast<int32_t>(j);
+                    if ((sp > 0 && dlp < static_cast<int32_t>(margin)) ||
+                        (sp + NB < nblk && drp < static_cast<int32_t>(margin))) {
+                        bad = true;
+                        break;
+                    }
+                }
+                if (j > 0 && hij == a + mc)
+                    move = 1;
+                else if (hij == b + g)
+                    move = 2;
+                found_p = p;
+            } else if (npe <= G) {
                 /* one predecessor per lane; all diagonal candidates outrank any vertical one (sisd :392-442) */
                 uint32_t p = 0;
                 bool okd = false, okv = false, unsure = false;
@@ -1457,7 +1587,9 @@ struct PoaWarp {
                     bad = true;
                     break;
                 }
-                move = traceback_step_wide<BAND>(H, bs, rec, pred_ovf, ki, lane, g, i, j, npe, hij, mc, lpa, &found_p);
+                const uint32_t mp = traceback_step_wide<BAND>(H, bs, rec, pred_ovf, ki, lane, g, i, j, npe, hij, mc, lpa);
+                move = static_cast<int>(mp >> 16);
+                found_p = mp & 0xffffu;
             }
             if (!move) move = 3;
             if (BAND) {
@@ -1476,9 +1608,9 @@ struct PoaWarp {
             if ((P->debug_flags & 8u) && lane == 0) g_audit_path[BAND ? 1 : 0].push_back({i, j, static_cast<uint32_t>(move), found_p, hij});
 #endif
             if (move == 1) {
-                if (lane == 0) aln[j - 1] = static_cast<uint16_t>(i);   // rank for now, node below
+                put_aln(j - 1, i);   // rank for now, node below
                 i = found_p;
-                --j;
+                step_left();
             } else if (move == 2) {
                 i = found_p;
             } else {
@@ -1489,9 +1621,14 @@ struct PoaWarp {
                         fail(kWinInternal);
                     break;
                 }
-                if (lane == 0) aln[j - 1] = kNone;
-                --j;
+                put_aln(j - 1, kNone);
+                step_left();
             }
+        }
+        /* positions j .. of the block the walk stopped in (nothing pending when j is a multiple of G) */
+        if ((j & (G - 1)) != 0) {
+            const uint32_t c = (j & ~static_cast<uint32_t>(G - 1)) + lane;
+            if (c >= j && c < len) aln[c] = static_cast<uint16_t>(pend);
         }
         syncwarp();
         if (bad) return false;

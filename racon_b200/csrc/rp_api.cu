@@ -150,7 +150,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) rp_poa_kern
     const uint32_t grp = threadIdx.x / G;
     const uint32_t worker = blockIdx.x * (blockDim.x / G) + grp;
     uint8_t* slot = P.scratch + static_cast<uint64_t>(worker) * P.lay.bytes;
-    uint8_t* smem = smem_all + grp * P.smem_per_group;
+    /* the group's shared-memory address (shared state space, 32 bits) is pinned in a register: left alone, the compiler
+     * re-derives it — S2R of the CTA's shared window and of the thread index, shift, multiply — wherever a shared-memory
+     * address is rebuilt inside the hot loops, at the head of every DP row's and every traceback step's dependency chain */
+    uint32_t smem_s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_all)) + grp * P.smem_per_group;
+    RP_KEEP_IN_REGISTER(smem_s);
+    uint8_t* smem = static_cast<uint8_t*>(__cvta_shared_to_generic(smem_s));
     for (;;) {
         uint32_t q = 0;
         if (rp::glane<G>() == 0) q = atomicAdd(P.queue_head, 1u);
@@ -182,6 +187,11 @@ PoaKernel pick_kernel_narrow(int blocks_per_sm) {   // 32 lanes, narrow banded r
     }
 }
 PoaKernel pick_kernel(int group, int band_k, int blocks_per_sm) {
+#if defined(RP_ONLY_DEFAULT_KERNEL)
+    /* development builds for SASS inspection (tools/sass_by_line.py --quick): one instantiation, seconds to compile */
+    (void)group; (void)band_k; (void)blocks_per_sm;
+    return rp_poa_kernel<32, 16, 4>;
+#else
     if (group == 32 && band_k == 4) return pick_kernel_narrow<4>(blocks_per_sm);
     if (group == 32 && band_k == 8) return pick_kernel_narrow<8>(blocks_per_sm);
     switch (group) {
@@ -189,6 +199,7 @@ PoaKernel pick_kernel(int group, int band_k, int blocks_per_sm) {
         case 16: return pick_kernel_g<16, 16>(blocks_per_sm);
         default: return pick_kernel_g<32, 16>(blocks_per_sm);
     }
+#endif
 }
 
 #if !defined(RP_HOST_SIM)
@@ -362,9 +373,7 @@ rp_status rp_poa_create(rp_poa** out, int device, size_t mem_bytes, int8_t match
         delete p;
         return fail(RP_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
-    p->P.match = match;
-    p->P.mismatch = mismatch;
-    p->P.gap = gap;
+    rp::set_scores(p->P, match, mismatch, gap);
     p->P.banded = banded ? 1 : 0;   // the request; configure() decides whether the band layout is used (window length)
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);

@@ -22,11 +22,15 @@
 #define RP_DEV_NOINLINE
 #define RP_HD inline
 #define RP_GLOBAL
+#define RP_KEEP_IN_REGISTER(x) do { } while (0)
 #else
 #include <cuda_runtime.h>
 #define RP_DEV __device__ __forceinline__
 #define RP_DEV_NOINLINE __device__ __noinline__
 #define RP_HD __host__ __device__ __forceinline__
+/* makes a 32-bit value opaque to the compiler at this point: it then has to keep it in a register instead of
+ * re-deriving it (from the thread index, the parameter block ...) inside a loop.  No instruction is emitted. */
+#define RP_KEEP_IN_REGISTER(x) asm volatile("" : "+r"(x))
 #endif
 
 namespace rp {

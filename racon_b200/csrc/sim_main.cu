@@ -190,9 +190,7 @@ int rp_sim_poa(uint32_t n_windows, const char* bases, const char* quals, const u
 
     rp::PoaParams P;
     std::memset(&P, 0, sizeof(P));
-    P.match = match;
-    P.mismatch = mismatch;
-    P.gap = gap;
+    rp::set_scores(P, match, mismatch, gap);
     P.n_windows = pb.n_gpu();
     P.bases = pb.bases.data;
     P.weights = pb.weights.data;
