@@ -729,13 +729,24 @@ struct PoaWarp {
 
     RP_DEV void dp(const uint8_t* seq, uint32_t nrows, uint32_t len, uint32_t lpa, uint32_t ring_rows,
                    uint32_t* best_row, int32_t* best_score, uint32_t* n_best) {
+        /* rows of one 512-column chunk (every window of up to 511 bases: the common case) get a copy of the row loop
+         * without the chunk-carry code, which otherwise rides along as ~14 predicated-off instructions per row */
+        if (lpa / kCC > 1)
+            dp_rows<true>(seq, nrows, len, lpa, ring_rows, best_row, best_score, n_best);
+        else
+            dp_rows<false>(seq, nrows, len, lpa, ring_rows, best_row, best_score, n_best);
+    }
+
+    template <bool CHUNKS>
+    RP_DEV void dp_rows(const uint8_t* seq, uint32_t nrows, uint32_t len, uint32_t lpa, uint32_t ring_rows,
+                        uint32_t* best_row, int32_t* best_score, uint32_t* n_best) {
         /* Row-synchronous: the whole warp computes one row (512-column chunk) at a time; lane l owns columns
          * 16l..16l+15.  Rows longer than 512 columns are done chunk by chunk (one pass over all rows per chunk,
          * the carry between chunks goes through a small per-row array), so shared memory only ever holds one
          * chunk: the profile chunk and a ring of the last `ring_rows` rows. */
         const int32_t g = P->gap;
         const uint32_t g2 = P->row_consts[16];
-        const uint32_t nch = lpa / kCC;
+        const uint32_t nch = CHUNKS ? lpa / kCC : 1u;
         const int32_t negsafe = -32768 - 16 * g;  // see kMaxGapInt16
         const uint32_t* gb = P->row_consts;       // bridge / carry offsets per register (constant bank, see PoaParams)
         const uint32_t* gc = P->row_consts + 8;
@@ -757,13 +768,16 @@ struct PoaWarp {
             for (uint32_t c = lane; c < kCC; c += G)  // root row (rank 0) -> ring slot 0
                 ring[swz(c)] = static_cast<int16_t>(static_cast<int32_t>(ch * kCC + c) * g);
             syncwarp();
-            const bool multi = ch > 0;
+            const bool multi = CHUNKS && ch > 0;
             /* columns beyond the read's last one are computed but never read by anything that matters (dependencies run
              * left to right and the walk starts at column len): lanes that only hold such columns do not vote */
             const bool scan_lane = ch * kCC + lanem * 16u <= len;
             uint32_t rec_a_lo = 0, rec_a_hi = 0, rec_b_lo = 0, rec_b_hi = 0;
             int16_t* hrow = H + static_cast<uint64_t>(ch) * kCC;  // row i of this chunk = hrow + i*lpa
             uint32_t myslot = 0;  // i % ring_rows, kept incrementally (any ring size, no division)
+            /* where this lane stores its 16 columns of row i in the HBM copy: a running pointer (rows come in order), so
+             * that the row loop carries one 64-bit add instead of rebuilding the address from the parameter block */
+            U4* hst = reinterpret_cast<U4*>(hrow + lpa) + 2u * lanem;
             Row8 prev;            // the row computed last (this lane's registers of it)
 #pragma unroll
             for (int r = 0; r < 8; ++r) prev.r[r] = 0;
@@ -893,8 +907,10 @@ struct PoaWarp {
                 prev = out;
                 int16_t* myrow_s = ring + myslot * kCC;
                 store_row_smem_at(myrow_s, sw0, sw1, out);
-                store_row_gmem(hrow + static_cast<uint64_t>(i) * lpa, lane, out);
-                if (nch > 1 && lanem == G - 1) cc_cur[i] = static_cast<int16_t>(hi16(acc[7]));
+                hst[0] = U4{out.r[0], out.r[1], out.r[2], out.r[3]};
+                hst[1] = U4{out.r[4], out.r[5], out.r[6], out.r[7]};
+                hst += CHUNKS ? lpa / 8u : kCC / 8u;   // next row (a U4 holds 8 cells; one chunk: lpa == kCC)
+                if (CHUNKS && lanem == G - 1) cc_cur[i] = static_cast<int16_t>(hi16(acc[7]));
                 syncwarp();
                 if (sink && ch == sink_ch) {  // warp-uniform
                     int32_t sc = myrow_s[sink_e];
@@ -908,7 +924,7 @@ struct PoaWarp {
                 }
               }
             }
-            if (nch > 1) {
+            if (CHUNKS) {
                 if (lane == 0) cc_cur[0] = static_cast<int16_t>((ch + 1) * kCC * g - g);  // root row, last column
                 int16_t* tmp = cc_prev;
                 cc_prev = cc_cur;
