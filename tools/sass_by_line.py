@@ -41,6 +41,9 @@ def main():
     ap.add_argument("--kernel", default="rp_poa_kernelILi32ELi16ELi4E")
     ap.add_argument("--lines", help="file.cuh:first-last : print the SASS generated for that source range")
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--range", help="lo-hi (hex addresses): plain listing of that address range, source lines beside it")
+    ap.add_argument("--where", help="file.cuh:line : address ranges (clusters) of the instructions generated for that line, "
+                                    "e.g. a loop statement -> the extent of each copy of the loop")
     ap.add_argument("--grep", help="regular expression over the instruction text: list the matches with their source lines")
     args = ap.parse_args()
     lines = disassemble(args.lib, args.kernel)
@@ -59,6 +62,26 @@ def main():
             n += 1
             listing.append((cur, m.group(1), m.group(2).strip()))
     print("kernel %s: %d instructions" % (args.kernel, n))
+    if args.range:
+        lo, _, hi = args.range.partition("-")
+        lo, hi = int(lo, 16), int(hi, 16)
+        for (cf, cl), addr, ins in listing:
+            if lo <= int(addr, 16) <= hi:
+                print("/*%s*/  %-60s // %s:%d" % (addr, ins + " ;", cf, cl))
+        return
+    if args.where:
+        f, _, ln = args.where.partition(":")
+        ads = sorted(int(addr, 16) for (cf, cl), addr, ins in listing if cf == f and cl == int(ln))
+        start = prev = None
+        for a in ads:
+            if start is None or a - prev > 0x3000:
+                if start is not None:
+                    print("0x%x-0x%x" % (start, prev))
+                start = a
+            prev = a
+        if start is not None:
+            print("0x%x-0x%x" % (start, prev))
+        return
     if args.grep:
         for (cf, cl), addr, ins in listing:
             if re.search(args.grep, ins):
