@@ -39,6 +39,33 @@ def test_sass_contains_dpx_and_vector_shared_loads():
     assert "LDS.128" in sass and "STG.E.128" in sass
 
 
+def test_sass_of_the_poa_kernel_keeps_shared_memory_accesses_in_the_shared_state_space():
+    """The group's shared-memory pointer goes through a cvta round trip to be pinned in a register (rp_api.cu): the compiler
+    must still know it is shared memory — no generic LD/ST anywhere in the default POA kernel — and neither hot loop may touch
+    local memory (spills, address-taken locals): the remaining LDL/STL belong to per-window set-up code."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", build.build_cuda()], stdout=subprocess.PIPE, text=True).stdout
+    body, on = [], False
+    for line in sass.splitlines():
+        if "Function :" in line:
+            on = "rp_poa_kernelILi32ELi16ELi4E" in line
+        elif on:
+            m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(.*?);", line)
+            if m:
+                body.append(m.group(1).strip())
+    assert len(body) > 10000
+    ops = [re.sub(r"^@!?U?P\d+\s+", "", b).split()[0] for b in body]
+    generic = [o for o in ops if re.match(r"^(LD|ST)(\.|$)", o)]
+    assert not generic, generic[:5]
+    assert sum(o.startswith("LDS") for o in ops) > 100 and sum(o.startswith("STS") for o in ops) > 50
+    local = sum(o.startswith(("LDL", "STL")) for o in ops)
+    assert local <= 40, "local-memory instructions in the default POA kernel: %d" % local
+
+
 def test_no_device_means_hard_error_not_fallback():
     lib = api.load()
     if lib.rp_device_count() > 0:
