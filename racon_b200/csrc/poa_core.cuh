@@ -1465,10 +1465,17 @@ struct PoaWarp {
                     }
                 }
                 /* four lanes per tile row, one 16-byte granule each: consecutive lanes write consecutive 16-byte
-                 * granules of the tile (no shared-memory bank conflict) and read one 64-byte piece of an H row */
+                 * granules of the tile (no shared-memory bank conflict) and read one 64-byte piece of an H row.
+                 * Full matrix: asynchronous copies (cp.async), all of a lane's granules — up to 12 — in flight at once;
+                 * the loop used to wait one HBM latency per granule (a load into registers, then the store). */
                 for (uint32_t e = lane; e < 4 * t_rows; e += G) {
                     const uint32_t q = e >> 2, gq = e & 3u;
                     const uint32_t rk = t_top - q;
+                    if (!BAND) {
+                        copy16_async(reinterpret_cast<U4*>(tile) + e,
+                                     reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0) + gq);
+                        continue;
+                    }
                     U4 v;
                     if (BAND) {
                         const uint32_t sr = bs[rk];
@@ -1488,8 +1495,6 @@ struct PoaWarp {
                             if (blk - sr >= NB) v = f4;
                         }
                         if (gq == 0) tbs[q] = static_cast<uint8_t>(sr);
-                    } else {
-                        v = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0)[gq];
                     }
                     reinterpret_cast<U4*>(tile)[e] = v;
                 }
@@ -1502,6 +1507,7 @@ struct PoaWarp {
                 } else {
                     for (uint32_t q = lane; q < t_rows; q += G) trec[q] = rec[t_top - q];
                 }
+                if (!BAND) copy_async_wait();
                 have_tile = true;
                 syncwarp();
             }

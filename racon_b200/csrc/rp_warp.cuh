@@ -126,6 +126,9 @@ inline int lanes() { return current()->n; }
 
 inline int lane_id() { return sim::current()->cur; }
 inline void syncwarp() { sim::collective(0, 0); }
+/* 16-byte asynchronous global -> shared copy (cp.async on the device): here an ordinary copy, nothing to wait for */
+inline void copy16_async(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 16); }
+inline void copy_async_wait() {}
 inline uint32_t ballot(bool p) {
     sim::collective(p ? 1 : 0, 0);
     uint32_t m = 0;
@@ -200,6 +203,17 @@ inline uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
 /* ------------------------------------------------------------------ sm_100a */
 RP_DEV int lane_id() { return static_cast<int>(threadIdx.x & 31); }
 RP_DEV void syncwarp() { __syncwarp(); }
+/* 16-byte asynchronous global -> shared copy (LDGSTS): the data goes from HBM / L2 into shared memory without passing
+ * through registers, and any number of copies can be in flight per lane; both addresses 16-byte aligned.
+ * copy_async_wait(): every copy this lane has issued has landed (a __syncwarp then publishes them to the other lanes). */
+RP_DEV void copy16_async(void* smem_dst, const void* gsrc) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+RP_DEV void copy_async_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 RP_DEV uint32_t ballot(bool p) { return __ballot_sync(kFull, p); }
 template <typename T>
 RP_DEV T shfl(T v, int src) {
