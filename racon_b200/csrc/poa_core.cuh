@@ -783,19 +783,24 @@ struct PoaWarp {
             for (int r = 0; r < 8; ++r) prev.r[r] = 0;
             /* rows in blocks of G: lane l fetches the record of row i0 + l once per block (a loop level of its own, so that
              * the row loop carries no predicated-off copy of the fetch), every row then takes its record by shuffle */
+            Rec nxt = rec[1 + lane];  // rec[] is padded (SlotLayout: + 160 records)
             for (uint32_t i0 = 1; i0 <= nrows; i0 += G) {
               {
-                  const Rec t = rec[i0 + lane];  // rec[] is padded
-                  rec_a_lo = static_cast<uint32_t>(t.a);
-                  rec_a_hi = static_cast<uint32_t>(t.a >> 32);
-                  rec_b_lo = static_cast<uint32_t>(t.b);
-                  rec_b_hi = static_cast<uint32_t>(t.b >> 32);
+                  /* this block's records were requested one block ago: their HBM latency ran under 32 rows of work */
+                  rec_a_lo = static_cast<uint32_t>(nxt.a);
+                  rec_a_hi = static_cast<uint32_t>(nxt.a >> 32);
+                  rec_b_lo = static_cast<uint32_t>(nxt.b);
+                  rec_b_hi = static_cast<uint32_t>(nxt.b >> 32);
+                  nxt = rec[i0 + G + lane];
               }
               const uint32_t i_last = i0 + G - 1 < nrows ? i0 + G - 1 : nrows;
+              uint32_t lo_next = shfl(rec_a_lo, 0);
               for (uint32_t i = i0; i <= i_last; ++i) {
                 myslot = myslot + 1 == ring_rows ? 0u : myslot + 1;
                 const uint32_t ti = i - i0;
-                const uint32_t lo = shfl(rec_a_lo, ti);
+                /* the record word of the NEXT row is shuffled out now: its latency runs under this row */
+                const uint32_t lo = lo_next;
+                lo_next = shfl(rec_a_lo, (ti + 1) & (G - 1));
                 const uint32_t cidx = lo & 0xff;
                 const uint32_t np = (lo >> 8) & 0x7f;
                 const bool sink = (lo >> 15) & 1;
