@@ -390,6 +390,10 @@ def main():
     host_binding = bind_near_gpu(torch.cuda.get_device_properties(local)) if distributed else "single rank: not bound"
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # The POA kernel is persistent and fills every SM's shared memory: a collective's kernel only gets on the GPU where a
+        # POA block retires.  On a high-priority stream it takes those slots ahead of the next POA launch already waiting for
+        # them (the per-step consensus gather then completes inside the running step instead of behind the next kernel).
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     cfg = CONFIGS[args.config]
