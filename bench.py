@@ -543,7 +543,7 @@ def main():
     def finalize(parts):
         out, lens, pol, st = (np.concatenate([p[i] for p in parts]) for i in range(4))
         if gather is not None:
-            got = gather.finish()
+            got = gather.finish(block=False)   # schedules the read-back of the previous step's gather, never waits
             if got is not None:
                 last["gathered"] = got
             gather.start(out, lens)

@@ -118,9 +118,12 @@ class RowGather:
     per-rank window count, agreed with one all-reduce here; l_max = the caller's row stride), so a step needs no shape
     exchange and no rank waits for another one inside its step: the next step's packing and kernels overlap the gather."""
 
-    def __init__(self, n_local, l_max, device=None, group=None, dst=0):
-        import torch
+    def __init__(self, n_local, l_max, device=None, group=None, dst=0, _torch=None):
         import torch.distributed as dist
+        if _torch is None:   # tests hand in a stand-in that plays a CUDA device on the CPU (tests/test_shard_gloo.py)
+            import torch
+        else:
+            torch = _torch
         self.torch, self.dist, self.group, self.dst = torch, dist, group, dst
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -130,7 +133,12 @@ class RowGather:
         self.n_max = int(t[0])
         self.l_max = max(4, (int(l_max) + 3) // 4 * 4)
         self.pending = None
-        self.host = None
+        self.inflight = []   # read-backs queued on the device: (event, pinned view, device tensor kept alive, pinned buffer)
+        self.bufs = []       # up to three pinned buffers, reused
+        self.done = None     # newest completed gather not handed out yet
+        self.done_buf = None # its pinned buffer: not reused while the caller may still read the returned views
+        self.up = []         # pinned staging blocks of start(): [tensor, event of its last upload]
+        self.n_started = 0
 
     def start(self, out, lens):
         torch, dist = self.torch, self.dist
@@ -139,13 +147,33 @@ class RowGather:
         n = int(len(lens))
         if n > self.n_max:
             raise ValueError("RowGather: %d windows exceed the agreed maximum %d" % (n, self.n_max))
-        block = np.zeros((self.n_max + 1, 4 + self.l_max), dtype=np.uint8)
+        shape = (self.n_max + 1, 4 + self.l_max)
+        on_gpu = str(self.dev).startswith("cuda")
+        if on_gpu:
+            # pinned staging, three blocks in rotation (a block is rewritten two steps after its upload was queued; the
+            # event makes that safe whatever the timing), uploaded without blocking the host
+            if len(self.up) < 3:
+                self.up.append([torch.empty(shape, dtype=torch.uint8, pin_memory=True), None])
+            slot = self.up[self.n_started % len(self.up)] if len(self.up) == 3 else self.up[-1]
+            if slot[1] is not None:
+                slot[1].synchronize()
+            block = slot[0].numpy()
+            block[:] = 0
+        else:
+            block = np.zeros(shape, dtype=np.uint8)
+        self.n_started += 1
         block[0, :4] = np.asarray([n], dtype="<u4").view(np.uint8)
         block[1:n + 1, :4] = np.asarray(lens, dtype="<u4").view(np.uint8).reshape(n, 4)
         w = min(self.l_max, out.shape[1]) if n else 0
         block[1:n + 1, 4:4 + w] = out[:n, :w]
-        mine = torch.from_numpy(block).to(self.dev, non_blocking=False)
-        gathered = torch.empty((self.world,) + block.shape, dtype=torch.uint8, device=self.dev)
+        if on_gpu:
+            mine = torch.empty(shape, dtype=torch.uint8, device=self.dev)
+            mine.copy_(slot[0], non_blocking=True)
+            slot[1] = torch.cuda.Event()
+            slot[1].record()
+        else:
+            mine = torch.from_numpy(block).to(self.dev)
+        gathered = torch.empty((self.world,) + shape, dtype=torch.uint8, device=self.dev)
         try:
             work = dist.all_gather_into_tensor(gathered, mine, group=self.group, async_op=True)
             parts = None
@@ -154,32 +182,57 @@ class RowGather:
             work = dist.all_gather(parts, mine, group=self.group, async_op=True)
         self.pending = (work, gathered, parts, mine)
 
-    def finish(self):
-        if self.pending is None:
-            return None
-        work, gathered, parts, _mine = self.pending
-        self.pending = None
-        work.wait()
-        if self.rank != self.dst:
-            return None
-        torch = self.torch
-        g_dev = torch.stack(parts) if parts is not None else gathered
-        # only the columns some row uses travel to the host (the block is as wide as the caller's row stride)
-        lens_dev = g_dev[:, 1:, :4].contiguous().view(torch.int32)
-        w = min(self.l_max, (int(lens_dev.max()) + 3) // 4 * 4) if lens_dev.numel() else 0
-        cut = g_dev[:, :, :4 + w].contiguous()
-        if cut.is_cuda:
-            if self.host is None:
-                self.host = torch.empty(self.world * (self.n_max + 1) * (4 + self.l_max), dtype=torch.uint8, pin_memory=True)
-            h = self.host[:cut.numel()].view(cut.shape)
-            h.copy_(cut, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            g = h.numpy()
-        else:
-            g = cut.numpy()
+    def _parse(self, g):
         res = []
         for r in range(self.world):
             nr = int(g[r, 0, :4].copy().view("<u4")[0])
             ll = g[r, 1:nr + 1, :4].copy().view("<u4").reshape(-1)
             res.append((g[r, 1:nr + 1, 4:], ll.astype(np.uint32)))
         return res
+
+    def finish(self, block=True):
+        """Completes the gather queued by start().  block=True (default): waits for it and returns, on rank `dst`,
+        [(rows_r, lens_r)] in rank order (None on the other ranks).  block=False: never waits on the host — the read-back of
+        the gather just queued is only scheduled, and what is returned is the newest EARLIER gather that has completed
+        meanwhile (or None); a final finish(block=True) collects the rest.
+
+        On a GPU nothing here launches a kernel or synchronises the host in the non-blocking form: the read-back is one
+        device-to-host copy of the (contiguous) gathered block on the copy engine, ordered after the collective by the
+        stream.  That matters next to a persistent kernel that fills every SM: any kernel queued here — even a tiny slicing
+        or reduction kernel — would wait for that kernel to drain, and a host thread waiting for it cannot launch the next
+        batch."""
+        torch = self.torch
+        if self.pending is not None:
+            work, gathered, parts, _mine = self.pending
+            self.pending = None
+            work.wait()          # NCCL: orders the current stream after the collective, does not block the host
+            if self.rank == self.dst:
+                g_dev = torch.stack(parts) if parts is not None else gathered
+                if str(self.dev).startswith("cuda"):
+                    while len(self.inflight) >= 2:   # keep one of the three buffers for the result not handed out yet
+                        ev, h, _keep, buf_done = self.inflight.pop(0)
+                        ev.synchronize()
+                        self.done, self.done_buf = h, buf_done
+                    n = g_dev.numel()
+                    if len(self.bufs) < 3:
+                        self.bufs.append(torch.empty(n, dtype=torch.uint8, pin_memory=True))
+                    busy = {id(x[3]) for x in self.inflight}
+                    busy.add(id(self.done_buf))
+                    buf = next(b for b in self.bufs if id(b) not in busy and b.numel() >= n)
+                    h = buf[:n].view(g_dev.shape)
+                    h.copy_(g_dev, non_blocking=True)      # plain D2H memcpy (both sides contiguous)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    self.inflight.append((ev, h, g_dev, buf))
+                else:
+                    self.done = g_dev
+        if self.rank != self.dst:
+            return None
+        while self.inflight and (block or self.inflight[0][0].query()):
+            ev, h, _keep, buf_done = self.inflight.pop(0)
+            ev.synchronize()
+            self.done, self.done_buf = h, buf_done
+        if self.done is None:
+            return None
+        g, self.done = self.done.numpy(), None   # done_buf stays reserved until the next result replaces it
+        return self._parse(g)

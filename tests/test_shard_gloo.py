@@ -18,6 +18,52 @@ def _free_port():
     return p
 
 
+class _FakeCudaTorch:
+    """torch with a pretend CUDA device: device 'cuda' means the CPU, pinned memory is ordinary memory, events complete one
+    query late (so that the not-yet-complete paths of RowGather run too)."""
+
+    def __init__(self):
+        import torch
+        self._t = torch
+        self.events_recorded = 0
+        self.pinned_allocations = 0
+        outer = self
+
+        class Event:
+            def __init__(self):
+                self.polls = 0
+
+            def record(self):
+                outer.events_recorded += 1
+
+            def query(self):
+                self.polls += 1
+                return self.polls > 1
+
+            def synchronize(self):
+                self.polls = 2
+
+        class Cuda:
+            pass
+        self.cuda = Cuda()
+        self.cuda.Event = Event
+
+    def __getattr__(self, k):
+        return getattr(self._t, k)
+
+    @staticmethod
+    def _dev(device):
+        return None if device is not None and str(device).startswith("cuda") else device
+
+    def empty(self, *a, pin_memory=False, device=None, **kw):
+        if pin_memory:
+            self.pinned_allocations += 1
+        return self._t.empty(*a, device=self._dev(device), **kw)
+
+    def tensor(self, data, device=None, **kw):
+        return self._t.tensor(data, device=self._dev(device), **kw)
+
+
 def _worker(rank, world, port, n_windows, ret):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -51,6 +97,32 @@ def _worker(rank, world, port, n_windows, ret):
             assert [rr[k, :ll[k]].tobytes() for rr, ll in got for k in range(len(ll))] == full
         else:
             assert got is None
+    # the branch a GPU rank takes (pinned staging in rotation, non-blocking upload, read-back scheduled with an event, no
+    # host wait in finish(block=False)), driven here with a stand-in for torch that plays a CUDA device on the CPU:
+    # several steps with changing content, results must arrive in order and complete
+    fake = _FakeCudaTorch()
+    rg = shard.RowGather(len(cons), stride, device="cuda", dst=0, _torch=fake)
+    seen = []   # (first byte, rows without their first byte) of every result, copied on receipt: the views are only valid
+                # until the next finish()
+
+    def note(got):
+        if got is not None:
+            seen.append((int(got[0][0][0, 0]), [rr[k, 1:ll[k]].tobytes() for rr, ll in got for k in range(len(ll))]))
+
+    for step in range(6):
+        o2 = out.copy()
+        o2[:, 0] = step          # every step's rows differ in their first byte
+        note(rg.finish(block=False))
+        rg.start(o2, lens)
+    note(rg.finish())
+    if rank == 0:
+        assert seen, "no gather result reached rank 0"
+        first_bytes = [fb for fb, _ in seen]
+        assert first_bytes == sorted(set(first_bytes)) and first_bytes[-1] == 5, first_bytes
+        assert all(rows == [c[1:] for c in full] for _, rows in seen)
+        assert fake.events_recorded >= 12 and fake.pinned_allocations <= 6
+    else:
+        assert not seen
     ret[rank] = full
     dist.barrier()
     dist.destroy_process_group()
