@@ -1536,37 +1536,63 @@ struct PoaWarp {
             if (j > 0) mc = cidx == tile_b[tseq_at + j - 1] ? m : x;
             uint32_t found_p = 0;
             int move = 0;  // 1 diag, 2 vert, 3 horiz
-            if (np <= 1) {  // group-uniform
-                /* Rows with one predecessor (or only the virtual root), ~9 of 10 steps: every lane evaluates the same
-                 * candidate, so the step needs no vote, no lane election and no indexed record field — the same
-                 * decisions as the general case below with lane 0 as the only candidate. */
-                const uint32_t p = np ? (lo >> 16) : 0u;   // pred0 (Rec::a bits 16..31)
-                int32_t a, b;
-                uint32_t sp = 0;
-                if (p + t_rows > t_top) {  // predecessor row is inside the tile
-                    const int16_t* pr = tile + (t_top - p) * kTileCols;
-                    a = pr[ejm];
-                    b = pr[ej];
-                    if (BAND) sp = tbs[t_top - p];
-                } else {
-                    a = hcell<BAND>(lpa, p, j > 0 ? j - 1 : 0);
-                    b = hcell<BAND>(lpa, p, j);
-                    if (BAND) sp = bs[p];
-                }
-                if (BAND && p != 0) {  // the candidate cells must be trustworthy too (see the general case)
-                    const int32_t dlp = static_cast<int32_t>(j) - 1 - static_cast<int32_t>(16u * sp);
-                    const int32_t drp = static_cast<int32_t>(16u * (sp + NB)) - 1 - static_cast<int32_t>(j);
-                    if ((sp > 0 && dlp < static_cast<int32_t>(margin)) ||
-                        (sp + NB < nblk && drp < static_cast<int32_t>(margin))) {
-                        bad = true;
-                        break;
+            if (np <= 7) {  // group-uniform: every predecessor is in the row's record
+                /* 7 of 10 steps of the walk are on rows with several predecessors (the consensus path runs through the
+                 * nodes many reads agree on), and on nearly all of them the FIRST in-edge — the oldest, heaviest one — is the
+                 * diagonal match.  So the lanes do not spread the candidates over themselves and vote: every lane walks
+                 * them in spoa's order (sisd :392-442: any diagonal beats any vertical, lowest in-edge first) and stops at
+                 * the first diagonal match — no vote, no lane election, no indexed record field, and the common step costs
+                 * what a single-predecessor row costs.  The banded walk looks at every candidate (its acceptance rule
+                 * covers all of them, see the general case below). */
+                uint64_t pq = rc.a >> 16;     // pred0..2, then rc.b = pred3..6
+                uint32_t pd = 0, pv = 0;
+                bool okd = false, okv = false, unsure = false;
+                for (uint32_t k = 0; k < npe; ++k) {
+                    const uint32_t p = np ? static_cast<uint32_t>(pq) & 0xffffu : 0u;
+                    pq = k == 2 ? rc.b : pq >> 16;
+                    int32_t a, b;
+                    uint32_t sp = 0;
+                    if (p + t_rows > t_top) {  // predecessor row is inside the tile
+                        const int16_t* pr = tile + (t_top - p) * kTileCols;
+                        a = pr[ejm];
+                        b = pr[ej];
+                        if (BAND) sp = tbs[t_top - p];
+                    } else if (!BAND) {        // a rare long edge: straight from the HBM copy, with the element
+                        const int16_t* hr = H + static_cast<uint64_t>(p) * lpa;   // indices the walk carries anyway
+                        a = hr[pjm];
+                        b = hr[pj];
+                    } else {
+                        a = hcell<BAND>(lpa, p, j > 0 ? j - 1 : 0);
+                        b = hcell<BAND>(lpa, p, j);
+                        sp = bs[p];
+                    }
+                    if (BAND && p != 0) {  // the candidate cells must be trustworthy too (see the general case)
+                        const int32_t dlp = static_cast<int32_t>(j) - 1 - static_cast<int32_t>(16u * sp);
+                        const int32_t drp = static_cast<int32_t>(16u * (sp + NB)) - 1 - static_cast<int32_t>(j);
+                        unsure |= (sp > 0 && dlp < static_cast<int32_t>(margin)) ||
+                                  (sp + NB < nblk && drp < static_cast<int32_t>(margin));
+                    }
+                    if (!okv && hij == b + g) {
+                        okv = true;
+                        pv = p;
+                    }
+                    if (!okd && j > 0 && hij == a + mc) {
+                        okd = true;
+                        pd = p;
+                        if (!BAND) break;
                     }
                 }
-                if (j > 0 && hij == a + mc)
+                if (BAND && unsure) {
+                    bad = true;
+                    break;
+                }
+                if (okd) {
                     move = 1;
-                else if (hij == b + g)
+                    found_p = pd;
+                } else if (okv) {
                     move = 2;
-                found_p = p;
+                    found_p = pv;
+                }
             } else if (npe <= G) {
                 /* one predecessor per lane; all diagonal candidates outrank any vertical one (sisd :392-442) */
                 uint32_t p = 0;
