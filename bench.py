@@ -662,6 +662,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "traffic_source": (traffic or {}).get("source"),
                          "kernel": "rp_poa_kernel", "kernel_ms": kern_avg_ms,
                          "achieved_overlapped": alg_bytes / (ms_per_step * 1e-3) / 1e9 * (n / max(1, n_total / world)),
                          "algorithmic_bytes_per_launch": alg_bytes,
