@@ -34,6 +34,19 @@
 #include <vector>
 #endif
 
+/* A/B switches for measuring the round-2 changes one by one on the device; all on by default, set with
+ * RP_NVCC_DEFINES="-DRP_POA_SERIAL_WALK_MAX=0 -DRP_POA_PREV_ROW=0 -DRP_POA_ASYNC_REFILL=0" python -c 'from racon_b200 import
+ * build; build.build_cuda(force=True)' (results are identical either way). */
+#ifndef RP_POA_SERIAL_WALK_MAX
+#define RP_POA_SERIAL_WALK_MAX 7   /* rows with up to this many predecessors: candidates walked serially (0: only root rows) */
+#endif
+#ifndef RP_POA_PREV_ROW
+#define RP_POA_PREV_ROW 1          /* a predecessor that is the row just computed comes from registers */
+#endif
+#ifndef RP_POA_ASYNC_REFILL
+#define RP_POA_ASYNC_REFILL 1      /* traceback tile refill by cp.async */
+#endif
+
 namespace rp {
 
 constexpr uint16_t kNone = 0xffffu;
@@ -833,7 +846,7 @@ struct PoaWarp {
                  * more predecessors enter the nested part */
                 {
                     const uint32_t p0 = np ? (lo >> 16) : 0u;
-                    if (p0 + 1 == i && p0 != 0) {  // group-uniform
+                    if (RP_POA_PREV_ROW && p0 + 1 == i && p0 != 0) {  // group-uniform
                         /* the first predecessor is the row just computed (4 of 10 rows): it still is in registers — no
                          * trip through the shared-memory ring, whose store -> load latency would start this row */
                         pm = prev;
@@ -1476,13 +1489,15 @@ struct PoaWarp {
                 for (uint32_t e = lane; e < 4 * t_rows; e += G) {
                     const uint32_t q = e >> 2, gq = e & 3u;
                     const uint32_t rk = t_top - q;
-                    if (!BAND) {
+                    if (!BAND && RP_POA_ASYNC_REFILL) {
                         copy16_async(reinterpret_cast<U4*>(tile) + e,
                                      reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0) + gq);
                         continue;
                     }
                     U4 v;
-                    if (BAND) {
+                    if (!BAND) {
+                        v = reinterpret_cast<const U4*>(H + static_cast<uint64_t>(rk) * lpa + t_col0)[gq];
+                    } else {
                         const uint32_t sr = bs[rk];
                         const uint32_t blk = cba + (gq >> 1);
                         if (rk == 0) {  // virtual root row: H[0][c] = c * g, in the row's register order
@@ -1512,7 +1527,7 @@ struct PoaWarp {
                 } else {
                     for (uint32_t q = lane; q < t_rows; q += G) trec[q] = rec[t_top - q];
                 }
-                if (!BAND) copy_async_wait();
+                if (!BAND && RP_POA_ASYNC_REFILL) copy_async_wait();
                 have_tile = true;
                 syncwarp();
             }
@@ -1536,7 +1551,8 @@ struct PoaWarp {
             if (j > 0) mc = cidx == tile_b[tseq_at + j - 1] ? m : x;
             uint32_t found_p = 0;
             int move = 0;  // 1 diag, 2 vert, 3 horiz
-            if (np <= 7) {  // group-uniform: every predecessor is in the row's record
+            static_assert(RP_POA_SERIAL_WALK_MAX <= 7, "only the predecessors held in the record are walked serially");
+            if (np <= RP_POA_SERIAL_WALK_MAX) {  // group-uniform: every predecessor is in the row's record
                 /* 7 of 10 steps of the walk are on rows with several predecessors (the consensus path runs through the
                  * nodes many reads agree on), and on nearly all of them the FIRST in-edge — the oldest, heaviest one — is the
                  * diagonal match.  So the lanes do not spread the candidates over themselves and vote: every lane walks
