@@ -277,6 +277,22 @@ RP_DEV Row8 load_row_gmem(const int16_t* row, int lane) {
     o.r[4] = c.x; o.r[5] = c.y; o.r[6] = c.z; o.r[7] = c.w;
     return o;
 }
+/* A row that has left the shared-memory ring (2 % of the predecessors), fetched from the HBM copy by an out-of-line helper,
+ * 8 bytes per call: kept out of line on purpose — inlined, the compiler turns the rare branch into ~18 predicated-off
+ * instructions that every predecessor of every row then issues. */
+static RP_DEV_NOINLINE uint64_t load_far_u64(const int16_t* row, uint32_t idx) {
+    return reinterpret_cast<const uint64_t*>(row)[idx];
+}
+RP_DEV Row8 load_row_far(const int16_t* row, int lane) {
+    Row8 o;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+        const uint64_t v = load_far_u64(row, 4u * static_cast<uint32_t>(lane) + k);
+        o.r[2 * k] = static_cast<uint32_t>(v);
+        o.r[2 * k + 1] = static_cast<uint32_t>(v >> 32);
+    }
+    return o;
+}
 RP_DEV void store_row_gmem(int16_t* row, int lane, const Row8& v) {
     U4* b = reinterpret_cast<U4*>(row) + 2u * static_cast<uint32_t>(lane);
     b[0] = U4{v.r[0], v.r[1], v.r[2], v.r[3]};
@@ -826,11 +842,11 @@ struct PoaWarp {
                 int32_t lvm = kNegDiag;
                 auto load_pred = [&](uint32_t p, Row8& pr) {
                     const uint32_t dist = i - p;
-                    if (dist < ring_rows) {  // warp-uniform
+                    if (__builtin_expect(dist < ring_rows, 1)) {  // warp-uniform; 98 % of the predecessors
                         const uint32_t slot = myslot >= dist ? myslot - dist : myslot + ring_rows - dist;
                         pr = load_row_smem_at(ring + slot * kCC, sw0, sw1);
                     } else
-                        pr = load_row_gmem(hrow + static_cast<uint64_t>(p) * lpa, lane);
+                        pr = load_row_far(hrow + static_cast<uint64_t>(p) * lpa, lane);
                     if (multi) {
                         int32_t lv = cc_prev[p];
                         lvm = lv > lvm ? lv : lvm;
