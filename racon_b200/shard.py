@@ -115,7 +115,7 @@ class RowGather:
     rank's fixed-size block [n_max + 1, 4 + l_max] (row 0: window count; then length prefix + padded consensus per window)
     and returns at once; finish() waits for it and, on rank `dst`, copies the gathered blocks to the host and returns
     [(rows_r, lens_r)] in rank (= window) order (views of a reused pinned buffer: valid until the next finish()).  The block shape is fixed when the object is made (n_max = the largest
-    per-rank window count, agreed with one all-reduce here; l_max = the caller's row stride), so a step needs no shape
+    per-rank window count, l_max = the largest row stride of any rank: both agreed with one all-reduce here), so a step needs no shape
     exchange and no rank waits for another one inside its step: the next step's packing and kernels overlap the gather."""
 
     def __init__(self, n_local, l_max, device=None, group=None, dst=0, _torch=None):
@@ -128,10 +128,12 @@ class RowGather:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.dev = device if device is not None else "cpu"
-        t = torch.tensor([int(n_local)], dtype=torch.int64, device=self.dev)
+        # both dimensions of the block are agreed here, once: every rank must hand the collective the same shape, and the
+        # ranks' row strides differ as soon as their windows do (found by tools/mock_bench.py --mock-world 2)
+        t = torch.tensor([int(n_local), int(l_max)], dtype=torch.int64, device=self.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
         self.n_max = int(t[0])
-        self.l_max = max(4, (int(l_max) + 3) // 4 * 4)
+        self.l_max = max(4, (int(t[1]) + 3) // 4 * 4)
         self.pending = None
         self.inflight = []   # read-backs queued on the device: (event, pinned view, device tensor kept alive, pinned buffer)
         self.bufs = []       # up to three pinned buffers, reused

@@ -76,7 +76,7 @@ def _worker(rank, world, port, n_windows, ret):
     assert (st == 0).all()
     full = shard.gather_consensus(cons)
     # the array form the bench uses: one data collective, result on rank 0 only
-    stride = 200
+    stride = 200 + 8 * rank   # the ranks' row strides differ, as they do when the ranks' windows differ
     out = np.zeros((len(cons), stride), np.uint8)
     lens = np.zeros(len(cons), np.uint32)
     for k, c in enumerate(cons):
