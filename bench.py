@@ -705,6 +705,24 @@ def main():
         dist.destroy_process_group()
 
 
+def run_group(cmd, timeout, **kw):
+    """subprocess.run with a time limit that takes the child's whole process group down (a torchrun child has workers of its
+    own: killing only the launcher would leave them on the GPUs).  Returns (returncode, stdout, stderr)."""
+    import signal
+    p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=kw.pop("stderr", subprocess.PIPE), text=True,
+                         start_new_session=True, **kw)
+    try:
+        out, err = p.communicate(timeout=timeout)
+        return p.returncode, out, err or ""
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)   # the session we started: nothing else is in it
+        except ProcessLookupError:
+            pass
+        p.communicate()
+        raise
+
+
 def by_reference(args, world):
     """The end-to-end arm once more with the windows added BY REFERENCE into a device-resident read store (SURVEY §8 f2;
     rp_reads_create + rp_poa_add_window_set_refs): the sequences are uploaded once, before the timed region — in a racon run
@@ -734,11 +752,11 @@ def by_reference(args, world):
     if args.banded >= 0:
         cmd += ["--banded", str(args.banded)]
     try:
-        p = subprocess.run(cmd, cwd=here, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, text=True)
-        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        rc, out, err = run_group(cmd, 300, cwd=here, env=env)
+        lines = [l for l in out.splitlines() if l.startswith("{")]
         if lines:
             return json.loads(lines[-1])
-        return {"unavailable": "no output (exit %d): %s" % (p.returncode, p.stderr.strip().splitlines()[-1:] or "")}
+        return {"unavailable": "no output (exit %d): %s" % (rc, err.strip().splitlines()[-1:] or "")}
     except Exception as e:  # noqa: BLE001 - reported, never fatal
         return {"unavailable": "%s" % e}
 
@@ -863,9 +881,9 @@ def gpu_reference(args, cfg, banded, world):
     if banded:
         cmd.append("--banded")
     try:
-        p = subprocess.run(cmd, cwd=here, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=240, text=True)
-        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
-        return json.loads(lines[-1]) if lines else {"unavailable": "no output (exit %d)" % p.returncode}
+        rc, out, _ = run_group(cmd, 240, cwd=here, stderr=subprocess.DEVNULL)
+        lines = [l for l in out.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"unavailable": "no output (exit %d)" % rc}
     except Exception as e:  # noqa: BLE001 - reported, never fatal
         return {"unavailable": "%s" % e}
 
