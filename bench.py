@@ -332,6 +332,9 @@ def parse_cpulist(text):
     return cpus
 
 
+_AFFINITY_BEFORE_BINDING = []   # bind_near_gpu() notes what it narrowed; the CPU baselines get the whole host back
+
+
 def bind_near_gpu(props):
     """Multi-rank runs: keep this rank's host threads (and with them its pinned staging buffers, first touched after this
     call) on the CPUs of the socket its GPU hangs off (sysfs local_cpulist of the PCI device), as `numactl` would on a
@@ -348,6 +351,7 @@ def bind_near_gpu(props):
         if not use or use == have:
             return "none needed (%d cpus, all local to %s)" % (len(have), dev)
         os.sched_setaffinity(0, use)
+        _AFFINITY_BEFORE_BINDING.append(have)
         return "%d of %d cpus, local to %s" % (len(use), len(have), dev)
     except Exception as e:  # noqa: BLE001 — sysfs layout differs between boxes; the run is valid without the binding
         return "unavailable (%s)" % type(e).__name__
@@ -844,6 +848,11 @@ def cpu_baseline(args, cfg, banded, world, ws):
     """oracle/_ref (the unmodified reference) on the box's host cores, bounded sample (~10-30 s of CPU work)."""
     from oracle import bindings as ob
     from racon_b200 import windows
+    if _AFFINITY_BEFORE_BINDING:   # the timed GPU arms are over: the reference runs on every core of the host, not on the
+        try:                       # socket this rank was bound to
+            os.sched_setaffinity(0, _AFFINITY_BEFORE_BINDING[0])
+        except OSError:
+            pass
     cores = host_cores()
     if ob.have_ref():
         kind, fn = "reference", ob.ref_consensus
