@@ -17,7 +17,7 @@ def test_two_rank_bench_flow_over_the_simulated_runtime():
     env = dict(os.environ, RP_BENCH_NO_BY_REFERENCE="1")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "RACON_B200_LIB"):
         env.pop(k, None)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mock_bench.py"), "--mock-world", "2", "--windows", "2",
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "mock_bench.py"), "--mock-world", "2", "--windows", "1",
                         "--steps", "1", "--warmup", "1", "--no-cpu-baseline"], cwd=ROOT, env=env, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=900)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
